@@ -1,0 +1,140 @@
+/*
+ * mrvi_b200.h -- C ABI of the B200-native counterfactual local-sample-distance path.
+ *
+ * The reference (YosefLab/mrvi) has no FFI: the path is the Python method
+ * MrVI.get_local_sample_distances (src/mrvi/_model.py:627-714), whose device work is
+ *   mapped_inference_fn(...)  -> z[B,S,L]          (src/mrvi/_model.py:326-365)
+ *   _compute_distances_from_representations(...)   (src/mrvi/_model.py:542-584)
+ *   the per-category running sums                  (src/mrvi/_model.py:469-504)
+ * executed by JAX/XLA.  This header is what a binding for that device work would bind: plain
+ * pointers and sizes, no torch / jax types.  The Python host side (mrvi_b200/_model.py) mirrors
+ * the reference method and calls these entry points through ctypes; INTEGRATION.md shows the
+ * stub a maintainer would add to the reference.
+ *
+ * Conventions: every function returns 0 on success or a negative MrviStatus; nothing throws or
+ * aborts; the message of the last failure on the calling thread is mrvi_last_error().  The caller
+ * owns all I/O buffers.  One handle per GPU; a handle is not thread-safe; handles are independent.
+ */
+#ifndef MRVI_B200_H_
+#define MRVI_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MRVI_B200_ABI_VERSION 1
+
+typedef struct MrviHandle MrviHandle;
+
+typedef enum MrviStatus {
+  MRVI_OK = 0,
+  MRVI_ERR_INVALID_ARG = -1,   /* bad dims / null pointer / unsupported value            */
+  MRVI_ERR_PARAM = -2,         /* missing parameter, wrong element count                 */
+  MRVI_ERR_CUDA = -3,          /* CUDA runtime error (message has the cudaError string)  */
+  MRVI_ERR_NO_DEVICE = -4,     /* no sm_100 device / device index out of range           */
+  MRVI_ERR_UNSUPPORTED = -5    /* hyper-parameters outside what the kernels are built for */
+} MrviStatus;
+
+/* Hyper-parameters that shape the path: MrVAE fields (src/mrvi/_module.py:209-230) and the
+ * EncoderUZ / AttentionBlock fields (src/mrvi/_module.py:114-128, _components.py:165-179). */
+typedef struct MrviDims {
+  int32_t n_input;          /* G  genes                                                   */
+  int32_t n_sample;         /* S  samples                                                 */
+  int32_t n_latent;         /* L                                                          */
+  int32_t n_latent_u;       /* Lu, or 0 when u and z are isomorphic (Lu == L)             */
+  int32_t encoder_n_hidden; /* H  (default 128)                                           */
+  int32_t encoder_n_layers; /* ResnetBlocks in NormalDistOutputNN (default 2)             */
+  int32_t n_latent_sample;  /* E  outerprod_dim (default 16)                              */
+  int32_t n_channels;       /* C  (default 4) == attention head_dim                       */
+  int32_t n_heads;          /* nh (default 2)                                             */
+  int32_t qz_n_hidden;      /* M  ResnetBlock output width inside the qz MLPs (default 32) */
+  int32_t qz_n_layers;      /* ResnetBlocks in the second qz MLP (default 1)              */
+  int32_t use_map;          /* 1: qz emits L values; 0: 2L, first L kept (_module.py:326-329) */
+} MrviDims;
+
+/* Arithmetic of the dense contractions (fixed at create time). */
+typedef enum MrviPrecision {
+  MRVI_PRECISION_FP32 = 0, /* fp32 FFMA everywhere; parity bar 1e-5                       */
+  MRVI_PRECISION_TC = 1    /* tcgen05 tensor cores, 16-bit/TF32 operands, fp32 accumulate; parity bar 1e-3 */
+} MrviPrecision;
+
+/* norm of _compute_distances_from_representations (src/mrvi/_model.py:548-556) */
+typedef enum MrviNorm { MRVI_NORM_L2 = 0, MRVI_NORM_L1 = 1, MRVI_NORM_LINF = 2 } MrviNorm;
+
+/* ABI version of the loaded library (compare with MRVI_B200_ABI_VERSION). */
+int mrvi_abi_version(void);
+
+/* Message of the last error raised on this thread ("" if none). Never NULL. */
+const char* mrvi_last_error(void);
+
+/* Number of kernels this library has launched in this process (for bench accounting). */
+int64_t mrvi_kernel_launch_count(void);
+
+/*
+ * Build a handle from the trained parameters {"params": module.params} (src/mrvi/_model.py:324),
+ * flattened to n_params named float32 arrays in HOST memory: names[i] is the flax path
+ * ("qu/Dense_0/kernel", ...; schema in mrvi_b200/_params.py and DESIGN.md), numels[i] its
+ * element count.  Weights are copied and re-packed on `device`; per-sample tables (LayerNorm'd
+ * sample embeddings, attention K/V rows) are precomputed there.
+ */
+int mrvi_create(const MrviDims* dims, int32_t n_params, const char* const* names,
+                const float* const* values, const int64_t* numels, int32_t device,
+                int32_t precision, MrviHandle** out);
+
+int mrvi_destroy(MrviHandle* h);
+
+/*
+ * One pass of the path over n_cells cells with every buffer in DEVICE memory on the handle's
+ * device; all work is enqueued on `stream` (a cudaStream_t, NULL = default stream) and the call
+ * returns without synchronising.
+ *
+ *   X            [n_cells, ldx] float32 counts, row-major, ldx >= n_input  (array_dict["X"], _model.py:378)
+ *   sample_idx   [n_cells] int32 in [0, S): each cell's own sample code    (array_dict["sample"])
+ *   n_keys       number of groupby keys (may be 0)
+ *   group_codes  n_keys device pointers, each [n_cells] int32 in [0, n_groups[k]) or -1 (= in no group)
+ *   n_groups     HOST array [n_keys]
+ *   norm         MrviNorm
+ *   cell_out     [n_cells, S, S] float32 or NULL          (the "cell" reduction, _model.py:485-491)
+ *   group_sums   n_keys device pointers, each [n_groups[k], S, S] float64; the per-category sums
+ *                of _model.py:469-484 are ADDED into them (caller zeroes; lets shards accumulate)
+ *   z_out        [n_cells, S, L] float32 or NULL          (mean representations, _model.py:396-404)
+ *   u_out        [n_cells, Lq]   float32 or NULL          (qu.mean, _module.py:312-314)
+ */
+int mrvi_run_device(MrviHandle* h, int64_t n_cells, const float* X, int64_t ldx,
+                    const int32_t* sample_idx, int32_t n_keys, const int32_t* const* group_codes,
+                    const int32_t* n_groups, int32_t norm, float* cell_out,
+                    double* const* group_sums, float* z_out, float* u_out, void* stream);
+
+/*
+ * Same pass with every buffer in HOST memory (pinned or pageable).  Cells are streamed through
+ * the GPU in chunks of `chunk_cells` (0 = library default) with the host->device copy of chunk
+ * i+1 and the device->host copy of chunk i-1 overlapping the kernels of chunk i.  Returns after
+ * all results are in the host buffers.  group_sums[k] is OVERWRITTEN with the float64 sums over
+ * these n_cells; group_counts[k] ([n_groups[k]] int64, may be NULL) with the number of cells per code.
+ */
+int mrvi_run_host(MrviHandle* h, int64_t n_cells, const float* X, int64_t ldx,
+                  const int32_t* sample_idx, int32_t n_keys, const int32_t* const* group_codes,
+                  const int32_t* n_groups, int32_t norm, float* cell_out,
+                  double* const* group_sums, int64_t* const* group_counts, float* z_out,
+                  float* u_out, int64_t chunk_cells);
+
+/*
+ * Stage (3) alone on device buffers: pairwise distances of given representations
+ * z [n_cells, S, L] (the seam of _compute_distances_from_representations, _model.py:542-584),
+ * with the same outputs as mrvi_run_device.  Used by the parity tests to isolate the stage.
+ */
+int mrvi_distances_device(MrviHandle* h, int64_t n_cells, const float* z, int32_t n_keys,
+                          const int32_t* const* group_codes, const int32_t* n_groups,
+                          int32_t norm, float* cell_out, double* const* group_sums, void* stream);
+
+/* Timing taps: device milliseconds spent in each stage of the most recent mrvi_run_* call
+ * (CUDA events on the launching stream; valid after that stream is synchronised).
+ * out_ms[0]=encoder (x->u), [1]=q(z|u,s) chain, [2]=distances+reductions, [3]=whole call. */
+int mrvi_last_stage_ms(MrviHandle* h, float out_ms[4]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MRVI_B200_H_ */

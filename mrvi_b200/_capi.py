@@ -1,0 +1,215 @@
+"""ctypes binding of ``include/mrvi_b200.h`` (the C-ABI shared library ``libmrvi_b200.so``).
+
+There is no CPU fallback: if the library is missing or no sm_100 GPU is visible the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Mapping, Optional, Sequence
+
+import numpy as np
+
+from ._params import MrviDims
+
+ABI_VERSION = 1
+PRECISION_FP32 = 0
+PRECISION_TC = 1
+NORMS = {"l2": 0, "l1": 1, "linf": 2}
+
+_LIB_NAME = "libmrvi_b200.so"
+_lib = None
+
+#: every symbol declared in include/mrvi_b200.h (checked by tests/test_capi_symbols.py)
+EXPORTED_SYMBOLS = (
+    "mrvi_abi_version",
+    "mrvi_last_error",
+    "mrvi_kernel_launch_count",
+    "mrvi_create",
+    "mrvi_destroy",
+    "mrvi_run_device",
+    "mrvi_run_host",
+    "mrvi_distances_device",
+    "mrvi_last_stage_ms",
+)
+
+
+class MrviError(RuntimeError):
+    """A non-zero status from the C-ABI (message from ``mrvi_last_error``)."""
+
+    def __init__(self, status: int, message: str):
+        super().__init__(f"mrvi_b200 C-ABI error {status}: {message}")
+        self.status = status
+
+
+class _CDims(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "n_input", "n_sample", "n_latent", "n_latent_u", "encoder_n_hidden", "encoder_n_layers",
+        "n_latent_sample", "n_channels", "n_heads", "qz_n_hidden", "qz_n_layers", "use_map")]
+
+
+def library_path() -> str:
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), _LIB_NAME)
+
+
+def load_library():
+    """dlopen the in-tree ``libmrvi_b200.so``; raises if it has not been built (``__graft_entry__.build()``)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not os.path.exists(path):
+        raise MrviError(-100, f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(mrvi_b200 has no CPU fallback)")
+    lib = C.CDLL(path)
+    vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
+    lib.mrvi_abi_version.restype = C.c_int
+    lib.mrvi_last_error.restype = C.c_char_p
+    lib.mrvi_kernel_launch_count.restype = i64
+    lib.mrvi_create.restype = C.c_int
+    lib.mrvi_create.argtypes = [C.POINTER(_CDims), i32, C.POINTER(C.c_char_p), C.POINTER(vp),
+                                C.POINTER(i64), i32, i32, C.POINTER(vp)]
+    lib.mrvi_destroy.restype = C.c_int
+    lib.mrvi_destroy.argtypes = [vp]
+    lib.mrvi_run_device.restype = C.c_int
+    lib.mrvi_run_device.argtypes = [vp, i64, vp, i64, vp, i32, C.POINTER(vp), C.POINTER(i32), i32, vp,
+                                    C.POINTER(vp), vp, vp, vp]
+    lib.mrvi_run_host.restype = C.c_int
+    lib.mrvi_run_host.argtypes = [vp, i64, vp, i64, vp, i32, C.POINTER(vp), C.POINTER(i32), i32, vp,
+                                  C.POINTER(vp), C.POINTER(vp), vp, vp, i64]
+    lib.mrvi_distances_device.restype = C.c_int
+    lib.mrvi_distances_device.argtypes = [vp, i64, vp, i32, C.POINTER(vp), C.POINTER(i32), i32, vp,
+                                          C.POINTER(vp), vp]
+    lib.mrvi_last_stage_ms.restype = C.c_int
+    lib.mrvi_last_stage_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    if lib.mrvi_abi_version() != ABI_VERSION:
+        raise MrviError(-101, f"ABI version mismatch: library {lib.mrvi_abi_version()}, binding {ABI_VERSION}")
+    _lib = lib
+    return lib
+
+
+def _check(status: int):
+    if status != 0:
+        raise MrviError(status, load_library().mrvi_last_error().decode("utf-8", "replace"))
+
+
+def _ptr_array(ptrs: Sequence[int]):
+    arr = (C.c_void_p * max(len(ptrs), 1))()
+    for i, p in enumerate(ptrs):
+        arr[i] = p
+    return arr
+
+
+def _i32_array(vals: Sequence[int]):
+    arr = (C.c_int32 * max(len(vals), 1))()
+    for i, v in enumerate(vals):
+        arr[i] = int(v)
+    return arr
+
+
+def kernel_launch_count() -> int:
+    return int(load_library().mrvi_kernel_launch_count())
+
+
+class Handle:
+    """Owns one ``MrviHandle`` (weights + workspaces on one GPU)."""
+
+    def __init__(self, dims: MrviDims, flat_params: Mapping[str, np.ndarray], device: int = 0,
+                 precision: int = PRECISION_FP32):
+        lib = load_library()
+        self.dims = dims
+        self.device = int(device)
+        self.precision = int(precision)
+        cd = _CDims(dims.n_input, dims.n_sample, dims.n_latent, dims.n_latent_u or 0, dims.encoder_n_hidden,
+                    dims.encoder_n_layers, dims.n_latent_sample, dims.n_channels, dims.n_heads,
+                    dims.qz_n_hidden, dims.qz_n_layers, int(dims.use_map))
+        names = list(flat_params.keys())
+        arrays = [np.ascontiguousarray(flat_params[k], dtype=np.float32) for k in names]
+        c_names = (C.c_char_p * len(names))(*[n.encode() for n in names])
+        c_vals = _ptr_array([a.ctypes.data for a in arrays])
+        c_numels = (C.c_int64 * len(names))(*[a.size for a in arrays])
+        out = C.c_void_p()
+        self._h = None
+        _check(lib.mrvi_create(C.byref(cd), len(names), c_names, c_vals, c_numels, self.device,
+                               self.precision, C.byref(out)))
+        self._h = out
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and _lib is not None:
+            _lib.mrvi_destroy(self._h)
+            self._h = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- device-resident pass: integer device addresses (e.g. torch.Tensor.data_ptr())
+    def run_device(self, n_cells: int, X_ptr: int, ldx: int, sample_ptr: int, group_code_ptrs: Sequence[int] = (),
+                   n_groups: Sequence[int] = (), norm: str = "l2", cell_out_ptr: int = 0,
+                   group_sum_ptrs: Sequence[int] = (), z_out_ptr: int = 0, u_out_ptr: int = 0, stream: int = 0):
+        if norm not in NORMS:
+            raise ValueError(f"norm {norm} not supported")
+        _check(load_library().mrvi_run_device(
+            self._h, int(n_cells), X_ptr, int(ldx), sample_ptr, len(n_groups), _ptr_array(group_code_ptrs),
+            _i32_array(n_groups), NORMS[norm], cell_out_ptr or None, _ptr_array(group_sum_ptrs),
+            z_out_ptr or None, u_out_ptr or None, stream or None))
+
+    def distances_device(self, n_cells: int, z_ptr: int, group_code_ptrs: Sequence[int] = (),
+                         n_groups: Sequence[int] = (), norm: str = "l2", cell_out_ptr: int = 0,
+                         group_sum_ptrs: Sequence[int] = (), stream: int = 0):
+        if norm not in NORMS:
+            raise ValueError(f"norm {norm} not supported")
+        _check(load_library().mrvi_distances_device(
+            self._h, int(n_cells), z_ptr, len(n_groups), _ptr_array(group_code_ptrs), _i32_array(n_groups),
+            NORMS[norm], cell_out_ptr or None, _ptr_array(group_sum_ptrs), stream or None))
+
+    # ---- host-buffer pass: numpy arrays in, numpy arrays out
+    def run_host(self, X: np.ndarray, sample_idx: np.ndarray, group_codes: Sequence[np.ndarray] = (),
+                 n_groups: Sequence[int] = (), norm: str = "l2", keep_cell: bool = True, want_z: bool = False,
+                 want_u: bool = False, chunk_cells: int = 0, cell_out: Optional[np.ndarray] = None):
+        if norm not in NORMS:
+            raise ValueError(f"norm {norm} not supported")
+        d = self.dims
+        if X.dtype != np.float32 or X.ndim != 2 or X.strides[1] != 4 or X.strides[0] % 4 != 0:
+            X = np.ascontiguousarray(X, dtype=np.float32)
+        n = X.shape[0]
+        if X.shape[1] != d.n_input:
+            raise ValueError(f"X has {X.shape[1]} genes, model expects {d.n_input}")
+        ldx = X.strides[0] // 4 if n > 1 else d.n_input
+        sid = np.ascontiguousarray(sample_idx, dtype=np.int32).reshape(-1)
+        if sid.shape[0] != n:
+            raise ValueError("sample_idx length does not match X")
+        if n and (sid.min() < 0 or sid.max() >= d.n_sample):
+            raise ValueError("sample_idx outside [0, n_sample)")
+        codes = [np.ascontiguousarray(c, dtype=np.int32).reshape(-1) for c in group_codes]
+        S, L, Lq = d.n_sample, d.n_latent, d.n_latent_q
+        out = {}
+        if keep_cell:
+            if cell_out is None:
+                cell_out = np.empty((n, S, S), dtype=np.float32)
+            elif cell_out.shape != (n, S, S) or cell_out.dtype != np.float32 or not cell_out.flags.c_contiguous:
+                raise ValueError("cell_out must be a C-contiguous float32 array of shape (n, S, S)")
+            out["cell"] = cell_out
+        sums = [np.zeros((g, S, S), dtype=np.float64) for g in n_groups]
+        counts = [np.zeros((g,), dtype=np.int64) for g in n_groups]
+        z = np.empty((n, S, L), dtype=np.float32) if want_z else None
+        u = np.empty((n, Lq), dtype=np.float32) if want_u else None
+        _check(load_library().mrvi_run_host(
+            self._h, n, X.ctypes.data, ldx, sid.ctypes.data, len(codes), _ptr_array([c.ctypes.data for c in codes]),
+            _i32_array(n_groups), NORMS[norm], out["cell"].ctypes.data if keep_cell else None,
+            _ptr_array([s.ctypes.data for s in sums]), _ptr_array([c.ctypes.data for c in counts]),
+            z.ctypes.data if want_z else None, u.ctypes.data if want_u else None, int(chunk_cells)))
+        out["group_sums"] = sums
+        out["group_counts"] = counts
+        if want_z:
+            out["z"] = z
+        if want_u:
+            out["u"] = u
+        return out
+
+    def last_stage_ms(self):
+        buf = (C.c_float * 4)()
+        _check(load_library().mrvi_last_stage_ms(self._h, buf))
+        return {"encoder": buf[0], "qz_chain": buf[1], "distances": buf[2], "total": buf[3]}

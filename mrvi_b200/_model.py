@@ -1,0 +1,296 @@
+"""Host-side mirror of the reference's ``MrVI`` for the local-sample-distance path.
+
+Same method names, arguments, validation, warnings, output layout and quirks as
+``src/mrvi/_model.py`` (``get_local_sample_distances`` :627-714, ``compute_local_statistics``
+:273-506, ``get_local_sample_representation`` :586-625), with the device work
+(``mapped_inference_fn`` :326-365, ``_compute_distances_from_representations`` :542-584 and the
+per-category sums :469-484) replaced by one call into the CUDA library through the C-ABI
+(``mrvi_b200._capi``).  pandas / xarray semantics (group order = ``value_counts()`` order, counts,
+coords, errors) stay on the host, exactly where the reference has them.
+
+There is no CPU fallback: constructing a model without ``libmrvi_b200.so`` and a B200 raises.
+"""
+from __future__ import annotations
+
+import warnings
+from collections import OrderedDict
+from typing import Mapping, Optional, Sequence
+
+import numpy as np
+import pandas as pd
+
+from . import _capi
+from ._data import dense_float32
+from ._params import MrviDims, flatten_params, infer_dims, validate_params
+from ._types import MrVIReduction, _default_fn
+from ._utils import _parse_local_statistics_requirements
+from ._xr import DataArray, Dataset
+
+_PRECISIONS = {"fp32": _capi.PRECISION_FP32, "tc": _capi.PRECISION_TC}
+
+
+def _identity(x):
+    return x
+
+
+def _is_identity_fn(fn) -> bool:
+    return fn is _identity or fn is _default_fn or getattr(fn, "_mrvi_identity", False)
+
+
+class MrVI:
+    """Trained MrVI model restricted to the counterfactual local-sample-distance path.
+
+    Parameters
+    ----------
+    adata
+        AnnData-like object the model was trained on (``.X``, ``.obs``, ``.obs_names``, ``.n_obs``).
+    params
+        The trained flax parameters, nested (``module.params``) or already flat
+        (``{"qu/Dense_0/kernel": ...}``); see :mod:`mrvi_b200._params`.
+    sample_key
+        ``obs`` column holding the sample label of each cell (reference ``setup_anndata(sample_key=...)``).
+    sample_order
+        Category labels in code order (reference ``self.sample_order``, `_model.py:113-115`).  Default:
+        sorted unique labels of ``adata.obs[sample_key]`` -- what scvi's CategoricalObsField registers.
+    precision
+        ``"fp32"`` (FFMA, parity 1e-5) or ``"tc"`` (tcgen05 tensor cores, parity 1e-3).
+    device
+        CUDA device index.
+    """
+
+    def __init__(self, adata, params: Mapping, sample_key: str = "sample", sample_order: Optional[Sequence] = None,
+                 precision: str = "fp32", device: int = 0, dims: Optional[MrviDims] = None):
+        if precision not in _PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(_PRECISIONS)}, not {precision!r}")
+        self.adata = adata
+        self.sample_key = sample_key
+        flat = flatten_params(params)
+        self.dims = infer_dims(flat) if dims is None else dims
+        self.params = validate_params(flat, self.dims)
+        if sample_order is None:
+            col = adata.obs[sample_key]
+            if isinstance(col.dtype, pd.CategoricalDtype):
+                sample_order = np.asarray(col.cat.categories)
+            else:
+                sample_order = np.sort(pd.unique(col))
+        self.sample_order = np.asarray(sample_order)
+        if len(self.sample_order) != self.dims.n_sample:
+            raise ValueError(f"{len(self.sample_order)} sample categories but the parameters were trained with "
+                             f"n_sample={self.dims.n_sample}")
+        if adata.n_vars != self.dims.n_input:
+            raise ValueError(f"adata has {adata.n_vars} genes, parameters expect {self.dims.n_input}")
+        self.precision = precision
+        self.device = int(device)
+        self.is_trained_ = True
+        self._handle = _capi.Handle(self.dims, self.params, device=self.device, precision=_PRECISIONS[precision])
+        self.last_stage_ms: dict = {}
+
+    # ------------------------------------------------------------------ construction helpers
+    @classmethod
+    def from_reference(cls, ref_model, precision: str = "fp32", device: int = 0) -> "MrVI":
+        """Build from a trained reference ``mrvi.MrVI`` instance (reads ``module.params``, ``adata``,
+        ``sample_key``, ``sample_order``)."""
+        return cls(ref_model.adata, ref_model.module.params, sample_key=ref_model.sample_key,
+                   sample_order=ref_model.sample_order, precision=precision, device=device)
+
+    def to_device(self, device):  # reference `_model.py:132-134` is a no-op as well
+        pass
+
+    def close(self):
+        self._handle.close()
+
+    # ------------------------------------------------------------------ host helpers
+    def _check_if_trained(self, warn: bool = False):
+        if not self.is_trained_:
+            raise RuntimeError("Trying to query inferred values from an untrained model. Please train the model first.")
+
+    def _sample_codes(self, adata) -> np.ndarray:
+        """Sample label -> code through the registered mapping (scvi ``_validate_anndata`` + CategoricalObsField)."""
+        col = adata.obs[self.sample_key]
+        codes = pd.Categorical(col, categories=list(self.sample_order)).codes
+        if (codes < 0).any():
+            bad = pd.unique(np.asarray(col)[codes < 0])[:5]
+            raise ValueError(f"Category {list(bad)} not found in source registry for sample key {self.sample_key!r}.")
+        return np.asarray(codes, dtype=np.int32)
+
+    def _group_codes(self, adata, key: str, indices: np.ndarray):
+        """Per-cell int32 group code in ``value_counts()`` order plus (labels, counts)."""
+        vc = adata.obs[key].value_counts()  # reference `_model.py:494-495`
+        cats = list(vc.index)
+        counts = vc.to_numpy().astype(np.int64)
+        # labels come from self.adata, positionally (reference quirk, `_model.py:470`; pandas>=3 needs to_numpy)
+        labels = self.adata.obs[key].to_numpy()[indices]
+        lookup = {c: i for i, c in enumerate(cats)}
+        codes = np.fromiter((lookup.get(l, -1) for l in labels.tolist()), dtype=np.int32, count=len(labels))
+        return codes, cats, counts
+
+    # ------------------------------------------------------------------ reference API
+    def compute_local_statistics(self, reductions: list, adata=None, indices: Optional[Sequence[int]] = None,
+                                 batch_size: Optional[int] = None, use_vmap: bool = True, norm: str = "l2",
+                                 mc_samples: int = 10):
+        """Reference `_model.py:273-506`.  ``batch_size`` / ``use_vmap`` only change memory use in the
+        reference; here ``batch_size`` is accepted for signature compatibility and the device chunking is
+        chosen by the library (results do not depend on either)."""
+        if not reductions or len(reductions) == 0:
+            raise ValueError("At least one reduction must be provided.")
+        adata = self.adata if adata is None else adata
+        self._check_if_trained(warn=False)
+        # Hack to ensure new AnnDatas have indices.  (reference `_model.py:314`)
+        adata.obs["_indices"] = np.arange(adata.n_obs).astype(int)
+        if norm not in _capi.NORMS:
+            raise ValueError(f"norm {norm} not supported")
+
+        reqs = _parse_local_statistics_requirements(reductions)
+        if reqs.needs_sampled_representations or reqs.needs_sampled_distances or reqs.needs_normalized_distances:
+            if reqs.needs_normalized_distances and norm != "l2":
+                raise ValueError(f"Norm must be 'l2' when using normalized distances. Got {norm}.")
+            raise NotImplementedError(
+                "sampled / normalized distances (use_mean=False, normalize_distances=True) depend on the JAX PRNG "
+                "streams of the reference and are not part of the B200 path yet (SURVEY.md section 8(f)-1)")
+
+        idx = np.arange(adata.n_obs) if indices is None else np.asarray(indices).astype(int).reshape(-1)
+        sample_codes = self._sample_codes(adata)[idx]
+        whole = indices is None
+        X = adata.X
+        if whole and isinstance(X, np.ndarray) and X.dtype == np.float32 and X.flags.c_contiguous:
+            Xh = X
+        elif whole:
+            Xh = dense_float32(X)
+        else:
+            Xh = dense_float32(X[idx] if not hasattr(X, "tocsr") else X.tocsr()[idx])
+
+        generic = [r for r in reductions if not _is_identity_fn(r.fn)]
+        if generic:
+            return self._compute_generic(reductions, adata, idx, Xh, sample_codes, batch_size, norm)
+
+        # ---- fused device path: one C-ABI call for everything
+        keys = [r.group_by for r in reqs.grouped_reductions]
+        plans = [self._group_codes(adata, k, idx) for k in keys]
+        keep_cell = any(r.input == "mean_distances" for r in reqs.ungrouped_reductions)
+        want_z = any(r.input == "mean_representations" for r in reductions)
+        if any(r.input == "mean_representations" for r in reqs.grouped_reductions):
+            return self._compute_generic(reductions, adata, idx, Xh, sample_codes, batch_size, norm)
+        res = self._handle.run_host(Xh, sample_codes, [p[0] for p in plans], [len(p[1]) for p in plans], norm=norm,
+                                    keep_cell=keep_cell, want_z=want_z)
+        self.last_stage_ms = self._handle.last_stage_ms()
+        cell_names = self.adata.obs_names[idx].values
+        final = OrderedDict()
+        for ur in reqs.ungrouped_reductions:
+            if ur.input == "mean_distances":
+                final[ur.name] = self._wrap_dists(res["cell"], cell_names)
+            else:
+                final[ur.name] = self._wrap_reps(res["z"], cell_names)
+        for gi, gr in enumerate(reqs.grouped_reductions):
+            codes, cats, counts = plans[gi]
+            present = np.bincount(codes[codes >= 0], minlength=len(cats))
+            for c, p in zip(cats, present):
+                if p == 0:
+                    raise KeyError(c)  # reference: grouped_data_arrs[gr.name][cat] missing (`_model.py:499`)
+            means = (res["group_sums"][gi] / counts[:, None, None].astype(np.float64)).astype(np.float32)
+            final[gr.name] = DataArray(
+                means,
+                dims=[f"{gr.group_by}_name", "sample_x", "sample_y"],
+                coords={f"{gr.group_by}_name": np.asarray(cats), "sample_x": self.sample_order,
+                        "sample_y": self.sample_order},
+                name="sample_distances",
+            )
+        return Dataset(final)
+
+    def _wrap_dists(self, d, cell_names):
+        return DataArray(d, dims=["cell_name", "sample_x", "sample_y"],
+                         coords={"cell_name": cell_names, "sample_x": self.sample_order, "sample_y": self.sample_order},
+                         name="sample_distances")
+
+    def _wrap_reps(self, z, cell_names):
+        return DataArray(z, dims=["cell_name", "sample", "latent_dim"],
+                         coords={"cell_name": cell_names, "sample": self.sample_order}, name="sample_representations")
+
+    def _compute_generic(self, reductions, adata, idx, Xh, sample_codes, batch_size, norm):
+        """Reductions with a user ``fn``: the reference's batch loop (`_model.py:376-504`) on the host,
+        with each batch's z / distances computed on the GPU."""
+        bs = 128 if batch_size is None else int(batch_size)  # scvi.settings.batch_size default
+        reqs = _parse_local_statistics_requirements(reductions)
+        ungrouped = {r.name: [] for r in reqs.ungrouped_reductions}
+        grouped = {r.name: OrderedDict() for r in reqs.grouped_reductions}
+        for lo in range(0, len(idx), bs):
+            hi = min(lo + bs, len(idx))
+            res = self._handle.run_host(Xh[lo:hi], sample_codes[lo:hi], norm=norm, keep_cell=reqs.needs_mean_distances,
+                                        want_z=True)
+            names = self.adata.obs_names[idx[lo:hi]].values
+            mean_zs = self._wrap_reps(res["z"], names)
+            mean_dists = self._wrap_dists(res["cell"], names) if reqs.needs_mean_distances else None
+            for r in reductions:
+                outputs = r.fn(mean_zs if r.input == "mean_representations" else mean_dists)
+                if r.group_by is not None:
+                    group_by = self.adata.obs[r.group_by].to_numpy()[idx[lo:hi]]
+                    for cat in pd.unique(group_by):
+                        sel = outputs.sel(cell_name=names[group_by == cat]).sum(dim="cell_name")
+                        if cat not in grouped[r.name]:
+                            grouped[r.name][cat] = sel
+                        else:
+                            prev = grouped[r.name][cat]
+                            grouped[r.name][cat] = DataArray(np.asarray(prev.values) + np.asarray(sel.values),
+                                                             dims=prev.dims, coords=dict(prev.coords), name=prev.name)
+                else:
+                    ungrouped[r.name].append(outputs)
+        final = OrderedDict()
+        for name, outs in ungrouped.items():
+            first = outs[0]
+            final[name] = DataArray(
+                np.concatenate([np.asarray(o.values) for o in outs], axis=0), dims=first.dims,
+                coords={**{k: v for k, v in dict(first.coords).items() if k != "cell_name"},
+                        "cell_name": np.concatenate([np.asarray(dict(o.coords)["cell_name"]) for o in outs])},
+                name=first.name)
+        for gr in reqs.grouped_reductions:
+            vc = adata.obs[gr.group_by].value_counts()
+            arrs, cats = [], []
+            for cat, count in vc.items():
+                g = grouped[gr.name][cat]  # KeyError for an empty category, as in the reference
+                arrs.append(np.asarray(g.values) / count)
+                cats.append(cat)
+            g0 = grouped[gr.name][cats[0]]
+            final[gr.name] = DataArray(np.stack(arrs, axis=0), dims=[f"{gr.group_by}_name", *g0.dims],
+                                       coords={**dict(g0.coords), f"{gr.group_by}_name": np.asarray(cats)}, name=g0.name)
+        return Dataset(final)
+
+    def get_local_sample_representation(self, adata=None, indices: Optional[Sequence[int]] = None, batch_size: int = 256,
+                                        use_mean: bool = True, use_vmap: bool = True):
+        """Reference `_model.py:586-625`: (cell_name, sample, latent_dim) counterfactual representations."""
+        reductions = [
+            MrVIReduction(
+                name="sample_representations",
+                input="mean_representations" if use_mean else "sampled_representations",
+                fn=_identity,
+                group_by=None,
+            )
+        ]
+        return self.compute_local_statistics(reductions, adata=adata, indices=indices, batch_size=batch_size,
+                                             use_vmap=use_vmap).sample_representations
+
+    def get_local_sample_distances(self, adata=None, batch_size: int = 256, use_mean: bool = True,
+                                   normalize_distances: bool = False, use_vmap: bool = True, groupby=None,
+                                   keep_cell: bool = True, norm: str = "l2", mc_samples: int = 10):
+        """Reference `_model.py:627-714`: per-cell (n_sample x n_sample) distances between counterfactual
+        sample representations as variable ``cell`` and, per ``groupby`` key, their per-category means."""
+        input = "mean_distances" if use_mean else "sampled_distances"
+        if normalize_distances:
+            if use_mean:
+                warnings.warn(
+                    "Normalizing distances uses sampled distances. Ignoring ``use_mean``.",
+                    UserWarning,
+                    stacklevel=2,
+                )
+            input = "normalized_distances"
+        if groupby and not isinstance(groupby, list):
+            groupby = [groupby]
+
+        reductions = []
+        if not keep_cell and not groupby:
+            raise ValueError("Undefined computation because not keep_cell and no groupby.")
+        if keep_cell:
+            reductions.append(MrVIReduction(name="cell", input=input, fn=_identity))
+        if groupby:
+            for groupby_key in groupby:
+                reductions.append(MrVIReduction(name=groupby_key, input=input, group_by=groupby_key))
+        return self.compute_local_statistics(reductions, adata=adata, batch_size=batch_size, use_vmap=use_vmap,
+                                             norm=norm, mc_samples=mc_samples)

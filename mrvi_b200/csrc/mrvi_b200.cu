@@ -1,0 +1,683 @@
+// C-ABI implementation of include/mrvi_b200.h: handle, weight packing, launch orchestration.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
+#include <cub/device/device_radix_sort.cuh>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "fp32_kernels.cuh"
+#include "tc_kernels.cuh"
+
+namespace mrvi {
+
+static thread_local std::string g_last_error;
+static std::atomic<int64_t> g_launches{0};
+
+static int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                          \
+  do {                                                                                          \
+    cudaError_t _e = (expr);                                                                    \
+    if (_e != cudaSuccess)                                                                      \
+      return fail(MRVI_ERR_CUDA, "%s failed at %s:%d: %s", #expr, __FILE__, __LINE__,           \
+                  cudaGetErrorString(_e));                                                      \
+  } while (0)
+
+#define LAUNCH_CHECK()                                                                          \
+  do {                                                                                          \
+    g_launches.fetch_add(1, std::memory_order_relaxed);                                         \
+    cudaError_t _e = cudaGetLastError();                                                        \
+    if (_e != cudaSuccess)                                                                      \
+      return fail(MRVI_ERR_CUDA, "kernel launch failed at %s:%d: %s", __FILE__, __LINE__,       \
+                  cudaGetErrorString(_e));                                                      \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------
+struct DeviceArena {  // owns every device allocation of a handle
+  std::vector<void*> ptrs;
+  ~DeviceArena() { for (void* p : ptrs) cudaFree(p); }
+  cudaError_t alloc(void** out, size_t bytes) {
+    cudaError_t e = cudaMalloc(out, bytes ? bytes : 16);
+    if (e == cudaSuccess) ptrs.push_back(*out);
+    return e;
+  }
+  void release(void* p) {
+    for (size_t i = 0; i < ptrs.size(); ++i)
+      if (ptrs[i] == p) { cudaFree(p); ptrs.erase(ptrs.begin() + i); return; }
+  }
+};
+
+struct HostStage {  // device-side staging of mrvi_run_host, cached across calls
+  int64_t chunk = 0;
+  int n_keys = 0;
+  bool has_cell = false, has_z = false, has_u = false;
+  float* X[2] = {nullptr, nullptr};
+  int32_t* sid[2] = {nullptr, nullptr};
+  int32_t* codes[2][kMaxKeys] = {};
+  float* cell[2] = {nullptr, nullptr};
+  float* z[2] = {nullptr, nullptr};
+  float* u[2] = {nullptr, nullptr};
+  double* sums[kMaxKeys] = {};
+  size_t sums_elems[kMaxKeys] = {};
+  cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_d2h = nullptr;
+  cudaEvent_t ev_h2d[2] = {}, ev_comp[2] = {}, ev_d2h[2] = {};
+  std::vector<void*> owned;
+  void free_buffers() {
+    for (void* p : owned) cudaFree(p);
+    owned.clear();
+  }
+  ~HostStage() {
+    free_buffers();
+    if (s_h2d) cudaStreamDestroy(s_h2d);
+    if (s_comp) cudaStreamDestroy(s_comp);
+    if (s_d2h) cudaStreamDestroy(s_d2h);
+    for (int i = 0; i < 2; ++i) {
+      if (ev_h2d[i]) cudaEventDestroy(ev_h2d[i]);
+      if (ev_comp[i]) cudaEventDestroy(ev_comp[i]);
+      if (ev_d2h[i]) cudaEventDestroy(ev_d2h[i]);
+    }
+  }
+};
+
+}  // namespace mrvi
+
+using namespace mrvi;
+
+struct MrviHandle {
+  MrviDims dims{};
+  int device = 0;
+  int precision = 0;
+  int sm_count = 148;
+  DeviceArena arena;
+  NetW net{};
+  TcNet tc{};
+  // workspace for one chunk of cells
+  int64_t chunk_cells = 0;
+  CellBuf cb{};
+  float* zbuf = nullptr;
+  int32_t *comp_in = nullptr, *idx_in = nullptr, *comp_sorted = nullptr, *order = nullptr;
+  int32_t* n_groups_dev = nullptr;
+  void* cub_tmp = nullptr;
+  size_t cub_tmp_bytes = 0;
+  // launch geometry of the fp32 kernels
+  int enc_ldh = 0, enc_ldhid = 0;
+  size_t enc_smem = 0;
+  int qz_lda = 0, qz_ldhid = 0, qz_ldm = 0, qz_ldc = 0;
+  size_t qz_smem = 0;
+  // stage timing
+  std::vector<cudaEvent_t> ev;  // 4 per chunk: start, after enc, after qz, after dist
+  int ev_used = 0;
+  cudaEvent_t ev_call[2] = {nullptr, nullptr};
+  HostStage hs;
+  ~MrviHandle() {
+    for (cudaEvent_t e : ev) cudaEventDestroy(e);
+    for (int i = 0; i < 2; ++i) if (ev_call[i]) cudaEventDestroy(ev_call[i]);
+  }
+};
+
+namespace mrvi {
+
+// ------------------------------------------------------------------------------------------
+// parameter lookup + packing
+struct ParamTable {
+  std::map<std::string, std::pair<const float*, int64_t>> m;
+  const float* get(const std::string& name, int64_t numel, int* err) const {
+    auto it = m.find(name);
+    if (it == m.end()) {
+      *err = fail(MRVI_ERR_PARAM, "missing parameter '%s' (expected %lld elements)", name.c_str(), (long long)numel);
+      return nullptr;
+    }
+    if (it->second.second != numel) {
+      *err = fail(MRVI_ERR_PARAM, "parameter '%s' has %lld elements, expected %lld", name.c_str(),
+                  (long long)it->second.second, (long long)numel);
+      return nullptr;
+    }
+    return it->second.first;
+  }
+  bool has(const std::string& name) const { return m.count(name) != 0; }
+};
+
+static int upload(MrviHandle* h, const std::vector<float>& host, const float** out) {
+  float* d = nullptr;
+  CUDA_TRY(h->arena.alloc((void**)&d, host.size() * sizeof(float)));
+  if (!host.empty()) CUDA_TRY(cudaMemcpy(d, host.data(), host.size() * sizeof(float), cudaMemcpyHostToDevice));
+  *out = d;
+  return 0;
+}
+
+// kernel [K][N] row-major (+ bias [N]) -> padded [Kpad][ld]
+static int pack_dense(MrviHandle* h, const ParamTable& pt, const std::string& name, int K, int N,
+                      bool has_bias, DenseW* out) {
+  int err = 0;
+  const float* w = pt.get(name + "/kernel", (int64_t)K * N, &err);
+  if (!w) return err;
+  const float* b = nullptr;
+  if (has_bias) { b = pt.get(name + "/bias", N, &err); if (!b) return err; }
+  out->K = K; out->N = N; out->Kpad = round_up(K, 4); out->ld = round_up(N, 4);
+  std::vector<float> wp((size_t)out->Kpad * out->ld, 0.f), bp(out->ld, 0.f);
+  for (int k = 0; k < K; ++k) memcpy(&wp[(size_t)k * out->ld], w + (size_t)k * N, N * sizeof(float));
+  if (b) memcpy(bp.data(), b, N * sizeof(float));
+  if ((err = upload(h, wp, &out->w))) return err;
+  if ((err = upload(h, bp, &out->b))) return err;
+  return 0;
+}
+
+static int pack_vec(MrviHandle* h, const ParamTable& pt, const std::string& name, int64_t n, const float** out) {
+  int err = 0;
+  const float* v = pt.get(name, n, &err);
+  if (!v) return err;
+  std::vector<float> tmp(v, v + n);
+  return upload(h, tmp, out);
+}
+
+static int pack_ln(MrviHandle* h, const ParamTable& pt, const std::string& name, int N, LnW* out) {
+  int err;
+  out->N = N;
+  if ((err = pack_vec(h, pt, name + "/scale", N, &out->scale))) return err;
+  if ((err = pack_vec(h, pt, name + "/bias", N, &out->bias))) return err;
+  return 0;
+}
+
+static int pack_resnet(MrviHandle* h, const ParamTable& pt, const std::string& prefix, int n_in, int n_out, ResnetW* rb) {
+  int err;
+  const int R = kResnetHidden;
+  if ((err = pack_dense(h, pt, prefix + "/Dense_0", n_in, R, true, &rb->d0))) return err;
+  if ((err = pack_ln(h, pt, prefix + "/LayerNorm_0", R, &rb->ln0))) return err;
+  int k = 1;
+  if (n_in != R) {
+    if ((err = pack_dense(h, pt, prefix + "/Dense_1", n_in, R, true, &rb->dskip))) return err;
+    k = 2;
+  } else {
+    rb->dskip = DenseW{};
+  }
+  if ((err = pack_dense(h, pt, prefix + "/Dense_" + std::to_string(k), R, n_out, true, &rb->dout))) return err;
+  if ((err = pack_ln(h, pt, prefix + "/LayerNorm_1", n_out, &rb->ln1))) return err;
+  return 0;
+}
+
+static int build_net(MrviHandle* h, const ParamTable& pt) {
+  const MrviDims& d = h->dims;
+  NetW& n = h->net;
+  int err;
+  const int G = d.n_input, S = d.n_sample, L = d.n_latent, H = d.encoder_n_hidden, E = d.n_latent_sample;
+  const int C = d.n_channels, nh = d.n_heads, M = d.qz_n_hidden;
+  const int Lq = d.n_latent_u > 0 ? d.n_latent_u : L;
+  n.G = G; n.S = S; n.L = L; n.Lq = Lq; n.H = H; n.E = E; n.C = C; n.nh = nh; n.M = M;
+  n.out_dim = d.use_map ? L : 2 * L;
+  n.has_zbase = d.n_latent_u > 0;
+  n.n_enc_blocks = d.encoder_n_layers;
+  n.n_qz_blocks = d.qz_n_layers;
+  if ((err = pack_dense(h, pt, "qu/Dense_0", G, H, true, &n.enc0))) return err;
+  if ((err = pack_dense(h, pt, "qu/Dense_1", H, H, true, &n.enc1))) return err;
+  for (int i = 0; i < 2; ++i) {
+    std::string cn = "qu/ConditionalNormalization_" + std::to_string(i);
+    if ((err = pack_vec(h, pt, cn + "/gamma_conditional/embedding", (int64_t)S * H, &n.gamma[i]))) return err;
+    if ((err = pack_vec(h, pt, cn + "/beta_conditional/embedding", (int64_t)S * H, &n.beta[i]))) return err;
+  }
+  if ((err = pack_vec(h, pt, "qu/Embed_0/embedding", (int64_t)S * H, &n.sample_effect))) return err;
+  for (int b = 0; b < d.encoder_n_layers; ++b)
+    if ((err = pack_resnet(h, pt, "qu/NormalDistOutputNN_0/ResnetBlock_" + std::to_string(b), H, H, &n.enc_blocks[b]))) return err;
+  if ((err = pack_dense(h, pt, "qu/NormalDistOutputNN_0/Dense_0", H, Lq, true, &n.enc_mean))) return err;
+  if ((err = pack_ln(h, pt, "qz/u_ln", Lq, &n.u_ln))) return err;
+  const std::string ab = "qz/AttentionBlock_0";
+  if ((err = pack_dense(h, pt, ab + "/DenseGeneral_0", Lq, E, false, &n.q_tok))) return err;  // kernel (Lq,E,1)
+  if (n.has_zbase) { if ((err = pack_dense(h, pt, "qz/Dense_0", Lq, L, true, &n.zbase))) return err; }
+  const std::string mha = ab + "/MultiHeadDotProductAttention_0";
+  if ((err = pack_vec(h, pt, mha + "/query/kernel", nh * C, &n.wq))) return err;
+  if ((err = pack_vec(h, pt, mha + "/query/bias", nh * C, &n.bq))) return err;
+  if ((err = pack_vec(h, pt, mha + "/out/kernel", (int64_t)nh * C * C, &n.wo))) return err;
+  if ((err = pack_vec(h, pt, mha + "/out/bias", C, &n.bo))) return err;
+  if ((err = pack_resnet(h, pt, ab + "/MLP_0/ResnetBlock_0", E * C, M, &n.mlp0_block))) return err;
+  if ((err = pack_dense(h, pt, ab + "/MLP_0/Dense_0", M, E, true, &n.mlp0_out))) return err;
+  for (int b = 0; b < d.qz_n_layers; ++b)
+    if ((err = pack_resnet(h, pt, ab + "/MLP_1/ResnetBlock_" + std::to_string(b), b == 0 ? Lq + E : M, M, &n.mlp1_blocks[b]))) return err;
+  if ((err = pack_dense(h, pt, ab + "/MLP_1/Dense_0", M, n.out_dim, true, &n.mlp1_out))) return err;
+
+  // per-sample tables on the device
+  const float *embed, *ln_s, *ln_b, *wkv, *wk, *bk, *wv, *bv;
+  if ((err = pack_vec(h, pt, "qz/Embed_0/embedding", (int64_t)S * E, &embed))) return err;
+  if ((err = pack_vec(h, pt, "qz/sample_embed_ln/scale", E, &ln_s))) return err;
+  if ((err = pack_vec(h, pt, "qz/sample_embed_ln/bias", E, &ln_b))) return err;
+  if ((err = pack_vec(h, pt, ab + "/DenseGeneral_1/kernel", (int64_t)E * E, &wkv))) return err;
+  if ((err = pack_vec(h, pt, mha + "/key/kernel", nh * C, &wk))) return err;
+  if ((err = pack_vec(h, pt, mha + "/key/bias", nh * C, &bk))) return err;
+  if ((err = pack_vec(h, pt, mha + "/value/kernel", nh * C, &wv))) return err;
+  if ((err = pack_vec(h, pt, mha + "/value/bias", nh * C, &bv))) return err;
+  float *ktab, *vtab, *kvtok;
+  CUDA_TRY(h->arena.alloc((void**)&ktab, (size_t)S * E * nh * C * sizeof(float)));
+  CUDA_TRY(h->arena.alloc((void**)&vtab, (size_t)S * E * nh * C * sizeof(float)));
+  CUDA_TRY(h->arena.alloc((void**)&kvtok, (size_t)S * E * sizeof(float)));
+  k_sample_tables<<<(S + 127) / 128, 128>>>(embed, ln_s, ln_b, wkv, wk, bk, wv, bv, S, E, nh, C, ktab, vtab, kvtok);
+  LAUNCH_CHECK();
+  CUDA_TRY(cudaDeviceSynchronize());
+  n.ktab = ktab; n.vtab = vtab;
+  h->tc.kvtok = kvtok;
+  return 0;
+}
+
+static int setup_workspace(MrviHandle* h) {
+  const NetW& n = h->net;
+  // chunk: z buffer <= 256 MiB, <= 65536 cells, multiple of 128 cells
+  int64_t per_cell = (int64_t)n.S * n.L * sizeof(float);
+  int64_t ch = (256ll << 20) / per_cell;
+  if (ch > 65536) ch = 65536;
+  ch = ch / 128 * 128;
+  if (ch < 128) ch = 128;
+  h->chunk_cells = ch;
+  CUDA_TRY(h->arena.alloc((void**)&h->cb.u, ch * n.Lq * sizeof(float)));
+  CUDA_TRY(h->arena.alloc((void**)&h->cb.u_ln, ch * n.Lq * sizeof(float)));
+  CUDA_TRY(h->arena.alloc((void**)&h->cb.q_tok, ch * n.E * sizeof(float)));
+  CUDA_TRY(h->arena.alloc((void**)&h->cb.zbase, ch * n.L * sizeof(float)));
+  CUDA_TRY(h->arena.alloc((void**)&h->zbuf, ch * per_cell));
+  CUDA_TRY(h->arena.alloc((void**)&h->comp_in, ch * sizeof(int32_t)));
+  CUDA_TRY(h->arena.alloc((void**)&h->idx_in, ch * sizeof(int32_t)));
+  CUDA_TRY(h->arena.alloc((void**)&h->comp_sorted, ch * sizeof(int32_t)));
+  CUDA_TRY(h->arena.alloc((void**)&h->order, ch * sizeof(int32_t)));
+  CUDA_TRY(h->arena.alloc((void**)&h->n_groups_dev, kMaxKeys * sizeof(int32_t)));
+  size_t tmp = 0;
+  CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp, h->comp_in, h->comp_sorted, h->idx_in, h->order, (int)ch));
+  h->cub_tmp_bytes = tmp;
+  CUDA_TRY(h->arena.alloc(&h->cub_tmp, tmp));
+
+  // fp32 kernel geometry
+  const int Hld = round_up(n.H, 4);
+  bool enc_skip = false;
+  for (int b = 0; b < n.n_enc_blocks; ++b) enc_skip |= (n.enc_blocks[b].dskip.w != nullptr);
+  h->enc_ldh = std::max(Hld, kResnetHidden) + 4;
+  h->enc_ldhid = std::max((enc_skip ? 2 * kResnetHidden : kResnetHidden), 64 + round_up(n.L, 4)) + 4;
+  h->enc_smem = ((size_t)kTM * 36 + 2 * (size_t)kTM * h->enc_ldh + (size_t)kTM * h->enc_ldhid) * sizeof(float) +
+                3 * kTM * sizeof(float*) + kTM * sizeof(int);
+  h->qz_lda = std::max(round_up(n.E * n.C, 4), round_up(n.M, 4)) + 4;
+  h->qz_ldhid = std::max(2 * kResnetHidden, round_up(n.out_dim, 4)) + 4;
+  h->qz_ldm = round_up(n.M, 4) + 4;
+  h->qz_ldc = round_up(n.Lq + n.E, 4) + 4;
+  h->qz_smem = (size_t)kTM * (h->qz_lda + h->qz_ldhid + h->qz_ldm + h->qz_ldc) * sizeof(float);
+  if (h->enc_smem > 227 * 1024 || h->qz_smem > 227 * 1024)
+    return fail(MRVI_ERR_UNSUPPORTED, "hyper-parameters need %zu / %zu bytes of shared memory (> 227 KiB)",
+                h->enc_smem, h->qz_smem);
+  CUDA_TRY(cudaFuncSetAttribute(k_encoder_fp32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->enc_smem));
+  CUDA_TRY(cudaFuncSetAttribute(k_qz_fp32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->qz_smem));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// stage launches (all on `st`)
+static int launch_encoder(MrviHandle* h, const float* X, int64_t ldx, const int32_t* sid, int64_t n, cudaStream_t st) {
+  const int grid = (int)((n + kTM - 1) / kTM);
+  const int vec_ok = ((ldx % 4) == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
+  k_encoder_fp32<<<grid, kThreads, h->enc_smem, st>>>(h->net, X, ldx, sid, n, h->cb, h->enc_ldh, h->enc_ldhid, vec_ok);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+static int launch_qz(MrviHandle* h, int64_t n, float* z, cudaStream_t st) {
+  const int64_t rows = n * h->net.S;
+  const int grid = (int)((rows + kTM - 1) / kTM);
+  k_qz_fp32<<<grid, kThreads, h->qz_smem, st>>>(h->net, h->cb, n, z, h->qz_lda, h->qz_ldhid, h->qz_ldm, h->qz_ldc);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+template <int NORM>
+static int launch_dist_t(MrviHandle* h, const float* z, int64_t n, float* cell_out, const GroupPlan& gp, cudaStream_t st) {
+  const int S = h->net.S, L = h->net.L;
+  if (S * S <= 1024) {
+    const int warps = kThreads / 32;
+    // enough warps to fill the GPU, but keep runs long when grouping
+    int64_t target_warps = (int64_t)h->sm_count * 4 * warps;
+    int cpw = (int)std::max<int64_t>(1, (n + target_warps - 1) / target_warps);
+    const int64_t n_warps = (n + cpw - 1) / cpw;
+    const int grid = (int)((n_warps + warps - 1) / warps);
+    const size_t smem = (size_t)warps * S * (L | 1) * sizeof(float);
+    k_dist_small<NORM><<<grid, kThreads, smem, st>>>(z, n, S, L, cell_out, gp, cpw);
+  } else {
+    const int nb = (S + kDB - 1) / kDB;
+    int64_t target = std::max<int64_t>(1, (int64_t)h->sm_count * 4 / (nb * nb));
+    int cpc = (int)std::max<int64_t>(1, (n + target - 1) / target);
+    dim3 grid((unsigned)((n + cpc - 1) / cpc), (unsigned)(nb * nb));
+    const int Lp = round_up(L, 4);
+    const size_t smem = (size_t)2 * kDB * Lp * sizeof(float);
+    k_dist_tiled<NORM><<<grid, kThreads, smem, st>>>(z, n, S, L, cell_out, gp, cpc);
+  }
+  LAUNCH_CHECK();
+  return 0;
+}
+
+static int launch_dist(MrviHandle* h, const float* z, int64_t n, int norm, float* cell_out, const GroupPlan& gp, cudaStream_t st) {
+  if (cell_out == nullptr && gp.n_keys == 0) return 0;
+  switch (norm) {
+    case MRVI_NORM_L2: return launch_dist_t<0>(h, z, n, cell_out, gp, st);
+    case MRVI_NORM_L1: return launch_dist_t<1>(h, z, n, cell_out, gp, st);
+    case MRVI_NORM_LINF: return launch_dist_t<2>(h, z, n, cell_out, gp, st);
+  }
+  return fail(MRVI_ERR_INVALID_ARG, "norm %d not supported", norm);
+}
+
+// builds the sorted order of one chunk for the group reductions
+static int plan_groups(MrviHandle* h, int64_t n, int n_keys, const int32_t* const* codes, int64_t offset,
+                       const int32_t* n_groups, double* const* sums, GroupPlan* gp, cudaStream_t st) {
+  memset(gp, 0, sizeof(*gp));
+  gp->n_keys = n_keys;
+  if (n_keys == 0) return 0;
+  int64_t prod = 1;
+  for (int k = 0; k < n_keys; ++k) {
+    gp->codes[k] = codes[k] + offset;
+    gp->sums[k] = sums[k];
+    prod *= (int64_t)n_groups[k] + 1;
+    if (prod > (1ll << 30)) return fail(MRVI_ERR_UNSUPPORTED, "too many group combinations across keys");
+  }
+  int bits = 1;
+  while ((1ll << bits) < prod) ++bits;
+  k_composite_codes<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(*gp, h->n_groups_dev, n, h->comp_in, h->idx_in);
+  LAUNCH_CHECK();
+  size_t tmp = h->cub_tmp_bytes;
+  CUDA_TRY(cub::DeviceRadixSort::SortPairs(h->cub_tmp, tmp, h->comp_in, h->comp_sorted, h->idx_in, h->order, (int)n, 0, bits, st));
+  g_launches.fetch_add(2, std::memory_order_relaxed);  // cub: histogram + onesweep (at least)
+  gp->order = h->order;
+  gp->comp_sorted = h->comp_sorted;
+  return 0;
+}
+
+static cudaEvent_t next_event(MrviHandle* h) {
+  if (h->ev_used == (int)h->ev.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    h->ev.push_back(e);
+  }
+  return h->ev[h->ev_used++];
+}
+
+static int validate_run(MrviHandle* h, int64_t n, const void* X, int64_t ldx, const void* sid, int n_keys,
+                        const int32_t* const* codes, const int32_t* n_groups, int norm, double* const* sums) {
+  if (!h) return fail(MRVI_ERR_INVALID_ARG, "null handle");
+  if (n < 0) return fail(MRVI_ERR_INVALID_ARG, "n_cells < 0");
+  if (n > 0 && (!X || !sid)) return fail(MRVI_ERR_INVALID_ARG, "X / sample_idx is null");
+  if (ldx < h->dims.n_input) return fail(MRVI_ERR_INVALID_ARG, "ldx (%lld) < n_input (%d)", (long long)ldx, h->dims.n_input);
+  if (n_keys < 0 || n_keys > kMaxKeys) return fail(MRVI_ERR_INVALID_ARG, "n_keys must be in [0, %d]", kMaxKeys);
+  if (norm < 0 || norm > 2) return fail(MRVI_ERR_INVALID_ARG, "norm %d not supported", norm);
+  for (int k = 0; k < n_keys; ++k) {
+    if (!codes || !codes[k] || !n_groups || !sums || !sums[k]) return fail(MRVI_ERR_INVALID_ARG, "group key %d: null pointer", k);
+    if (n_groups[k] <= 0) return fail(MRVI_ERR_INVALID_ARG, "group key %d: n_groups must be > 0", k);
+  }
+  return 0;
+}
+
+// core: device buffers, one stream, chunked over cells
+static int run_device_impl(MrviHandle* h, int64_t n, const float* X, int64_t ldx, const int32_t* sid, int n_keys,
+                           const int32_t* const* codes, const int32_t* n_groups, int norm, float* cell_out,
+                           double* const* sums, float* z_out, float* u_out, cudaStream_t st, bool time_stages) {
+  const NetW& net = h->net;
+  if (n_keys > 0)
+    CUDA_TRY(cudaMemcpyAsync(h->n_groups_dev, n_groups, n_keys * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  const bool need_dist = cell_out != nullptr || n_keys > 0;
+  const bool need_z = need_dist || z_out != nullptr;
+  for (int64_t lo = 0; lo < n; lo += h->chunk_cells) {
+    const int64_t m = std::min(h->chunk_cells, n - lo);
+    cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr, e3 = nullptr;
+    if (time_stages) { e0 = next_event(h); e1 = next_event(h); e2 = next_event(h); e3 = next_event(h); cudaEventRecord(e0, st); }
+    int err;
+    float* z = z_out ? z_out + lo * net.S * net.L : h->zbuf;
+    if (h->precision == MRVI_PRECISION_TC) {
+      if ((err = tc_launch_chain(h->tc, h->net, X + lo * ldx, ldx, sid + lo, m, h->cb, need_z ? z : nullptr, st, e1))) return err;
+    } else {
+      if ((err = launch_encoder(h, X + lo * ldx, ldx, sid + lo, m, st))) return err;
+      if (time_stages) cudaEventRecord(e1, st);
+      if (need_z) { if ((err = launch_qz(h, m, z, st))) return err; }
+    }
+    if (time_stages) cudaEventRecord(e2, st);
+    if (u_out) CUDA_TRY(cudaMemcpyAsync(u_out + lo * net.Lq, h->cb.u, m * net.Lq * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (need_dist) {
+      GroupPlan gp;
+      if ((err = plan_groups(h, m, n_keys, codes, lo, n_groups, sums, &gp, st))) return err;
+      if ((err = launch_dist(h, z, m, norm, cell_out ? cell_out + lo * net.S * net.S : nullptr, gp, st))) return err;
+    }
+    if (time_stages) cudaEventRecord(e3, st);
+  }
+  return 0;
+}
+
+}  // namespace mrvi
+
+// ==========================================================================================
+extern "C" {
+
+int mrvi_abi_version(void) { return MRVI_B200_ABI_VERSION; }
+
+const char* mrvi_last_error(void) { return g_last_error.c_str(); }
+
+int64_t mrvi_kernel_launch_count(void) { return g_launches.load(); }
+
+int mrvi_create(const MrviDims* dims, int32_t n_params, const char* const* names, const float* const* values,
+                const int64_t* numels, int32_t device, int32_t precision, MrviHandle** out) {
+  if (!dims || !out || (n_params > 0 && (!names || !values || !numels)))
+    return fail(MRVI_ERR_INVALID_ARG, "mrvi_create: null argument");
+  *out = nullptr;
+  const MrviDims& d = *dims;
+  if (d.n_input <= 0 || d.n_sample <= 0 || d.n_latent <= 0 || d.n_latent_u < 0 || d.encoder_n_hidden <= 0)
+    return fail(MRVI_ERR_INVALID_ARG, "mrvi_create: non-positive dimension");
+  if (d.n_latent_sample <= 0 || d.n_latent_sample > kMaxE)
+    return fail(MRVI_ERR_UNSUPPORTED, "n_latent_sample=%d outside [1, %d]", d.n_latent_sample, kMaxE);
+  if (d.n_channels <= 0 || d.n_channels > kMaxHeadDim || d.n_heads <= 0 || d.n_heads > kMaxHeads)
+    return fail(MRVI_ERR_UNSUPPORTED, "n_channels=%d / n_heads=%d outside supported range (<= %d / <= %d)",
+                d.n_channels, d.n_heads, kMaxHeadDim, kMaxHeads);
+  if (d.encoder_n_layers < 0 || d.encoder_n_layers > kMaxBlocks || d.qz_n_layers < 0 || d.qz_n_layers > kMaxBlocks)
+    return fail(MRVI_ERR_UNSUPPORTED, "more than %d ResnetBlocks per MLP", kMaxBlocks);
+  if (d.encoder_n_hidden > 512 || d.qz_n_hidden > 128 || d.n_latent > 96)
+    return fail(MRVI_ERR_UNSUPPORTED, "encoder_n_hidden<=512, qz_n_hidden<=128, n_latent<=96 required");
+  if (d.n_latent_u == d.n_latent)
+    return fail(MRVI_ERR_INVALID_ARG, "n_latent_u must be 0 when equal to n_latent (isomorphic)");
+  if (precision != MRVI_PRECISION_FP32 && precision != MRVI_PRECISION_TC)
+    return fail(MRVI_ERR_INVALID_ARG, "unknown precision %d", precision);
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
+    cudaGetLastError();
+    return fail(MRVI_ERR_NO_DEVICE, "no CUDA device visible");
+  }
+  if (device < 0 || device >= n_dev) return fail(MRVI_ERR_NO_DEVICE, "device %d out of range (%d visible)", device, n_dev);
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(MRVI_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+  CUDA_TRY(cudaSetDevice(device));
+
+  std::unique_ptr<MrviHandle> h(new MrviHandle());
+  h->dims = d;
+  h->device = device;
+  h->precision = precision;
+  h->sm_count = prop.multiProcessorCount;
+  ParamTable pt;
+  for (int i = 0; i < n_params; ++i) {
+    if (!names[i] || !values[i]) return fail(MRVI_ERR_INVALID_ARG, "parameter %d: null name or value", i);
+    pt.m[names[i]] = {values[i], numels[i]};
+  }
+  int err;
+  if ((err = build_net(h.get(), pt))) return err;
+  if ((err = setup_workspace(h.get()))) return err;
+  if (precision == MRVI_PRECISION_TC) {
+    if ((err = tc_build(h->tc, h->net, h->dims, pt.m, h->arena, h->sm_count))) return fail(err, "%s", tc_error());
+  }
+  CUDA_TRY(cudaEventCreate(&h->ev_call[0]));
+  CUDA_TRY(cudaEventCreate(&h->ev_call[1]));
+  *out = h.release();
+  return 0;
+}
+
+int mrvi_destroy(MrviHandle* h) {
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  delete h;
+  return 0;
+}
+
+int mrvi_run_device(MrviHandle* h, int64_t n_cells, const float* X, int64_t ldx, const int32_t* sample_idx,
+                    int32_t n_keys, const int32_t* const* group_codes, const int32_t* n_groups, int32_t norm,
+                    float* cell_out, double* const* group_sums, float* z_out, float* u_out, void* stream) {
+  int err;
+  if ((err = validate_run(h, n_cells, X, ldx, sample_idx, n_keys, group_codes, n_groups, norm, group_sums))) return err;
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  h->ev_used = 0;
+  CUDA_TRY(cudaEventRecord(h->ev_call[0], st));
+  if ((err = run_device_impl(h, n_cells, X, ldx, sample_idx, n_keys, group_codes, n_groups, norm, cell_out,
+                             group_sums, z_out, u_out, st, true))) return err;
+  CUDA_TRY(cudaEventRecord(h->ev_call[1], st));
+  return 0;
+}
+
+int mrvi_distances_device(MrviHandle* h, int64_t n_cells, const float* z, int32_t n_keys,
+                          const int32_t* const* group_codes, const int32_t* n_groups, int32_t norm,
+                          float* cell_out, double* const* group_sums, void* stream) {
+  if (!h) return fail(MRVI_ERR_INVALID_ARG, "null handle");
+  if (n_cells > 0 && !z) return fail(MRVI_ERR_INVALID_ARG, "z is null");
+  int err;
+  if ((err = validate_run(h, n_cells, z, h->dims.n_input, z, n_keys, group_codes, n_groups, norm, group_sums))) return err;
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const NetW& net = h->net;
+  if (n_keys > 0)
+    CUDA_TRY(cudaMemcpyAsync(h->n_groups_dev, n_groups, n_keys * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  for (int64_t lo = 0; lo < n_cells; lo += h->chunk_cells) {
+    const int64_t m = std::min(h->chunk_cells, n_cells - lo);
+    GroupPlan gp;
+    if ((err = plan_groups(h, m, n_keys, group_codes, lo, n_groups, group_sums, &gp, st))) return err;
+    if ((err = launch_dist(h, z + lo * net.S * net.L, m, norm, cell_out ? cell_out + lo * net.S * net.S : nullptr, gp, st))) return err;
+  }
+  return 0;
+}
+
+int mrvi_run_host(MrviHandle* h, int64_t n_cells, const float* X, int64_t ldx, const int32_t* sample_idx,
+                  int32_t n_keys, const int32_t* const* group_codes, const int32_t* n_groups, int32_t norm,
+                  float* cell_out, double* const* group_sums, int64_t* const* group_counts, float* z_out,
+                  float* u_out, int64_t chunk_cells) {
+  int err;
+  if ((err = validate_run(h, n_cells, X, ldx, sample_idx, n_keys, group_codes, n_groups, norm, group_sums))) return err;
+  CUDA_TRY(cudaSetDevice(h->device));
+  const NetW& net = h->net;
+  const int S = net.S, L = net.L, G = net.G, Lq = net.Lq;
+  // ---- group counts: host integer bookkeeping
+  for (int k = 0; k < n_keys; ++k) {
+    for (int64_t i = 0; i < n_cells; ++i) {
+      const int g = group_codes[k][i];
+      if (g < -1 || g >= n_groups[k])
+        return fail(MRVI_ERR_INVALID_ARG, "group key %d: code %d of cell %lld outside [-1, %d)", k, g, (long long)i, n_groups[k]);
+    }
+    if (group_counts && group_counts[k]) {
+      for (int g = 0; g < n_groups[k]; ++g) group_counts[k][g] = 0;
+      for (int64_t i = 0; i < n_cells; ++i) if (group_codes[k][i] >= 0) group_counts[k][group_codes[k][i]]++;
+    }
+  }
+  // ---- chunk size: bound device staging (2 buffers) to ~1 GiB per buffer set
+  int64_t per_cell = (int64_t)G * 4 + 4 + 4 * n_keys + (cell_out ? (int64_t)S * S * 4 : 0) + (z_out ? (int64_t)S * L * 4 : 0) + (u_out ? Lq * 4 : 0);
+  int64_t ch = chunk_cells > 0 ? chunk_cells : std::max<int64_t>(256, std::min<int64_t>(16384, (768ll << 20) / per_cell));
+  ch = std::min<int64_t>(ch, std::max<int64_t>(n_cells, 1));
+  HostStage& hs = h->hs;
+  if (!hs.s_h2d) {
+    CUDA_TRY(cudaStreamCreateWithFlags(&hs.s_h2d, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&hs.s_comp, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&hs.s_d2h, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      CUDA_TRY(cudaEventCreateWithFlags(&hs.ev_h2d[i], cudaEventDisableTiming));
+      CUDA_TRY(cudaEventCreateWithFlags(&hs.ev_comp[i], cudaEventDisableTiming));
+      CUDA_TRY(cudaEventCreateWithFlags(&hs.ev_d2h[i], cudaEventDisableTiming));
+    }
+  }
+  bool sums_ok = true;
+  for (int k = 0; k < n_keys; ++k) sums_ok &= hs.sums_elems[k] >= (size_t)n_groups[k] * S * S;
+  if (hs.chunk < ch || hs.n_keys < n_keys || (cell_out && !hs.has_cell) || (z_out && !hs.has_z) || (u_out && !hs.has_u) || !sums_ok) {
+    CUDA_TRY(cudaDeviceSynchronize());
+    hs.free_buffers();
+    auto A = [&](void** p, size_t bytes) -> cudaError_t {
+      cudaError_t e = cudaMalloc(p, bytes ? bytes : 16);
+      if (e == cudaSuccess) hs.owned.push_back(*p);
+      return e;
+    };
+    for (int b = 0; b < 2; ++b) {
+      CUDA_TRY(A((void**)&hs.X[b], ch * G * sizeof(float)));
+      CUDA_TRY(A((void**)&hs.sid[b], ch * sizeof(int32_t)));
+      for (int k = 0; k < n_keys; ++k) CUDA_TRY(A((void**)&hs.codes[b][k], ch * sizeof(int32_t)));
+      hs.cell[b] = nullptr; hs.z[b] = nullptr; hs.u[b] = nullptr;
+      if (cell_out) CUDA_TRY(A((void**)&hs.cell[b], ch * S * S * sizeof(float)));
+      if (z_out) CUDA_TRY(A((void**)&hs.z[b], ch * S * L * sizeof(float)));
+      if (u_out) CUDA_TRY(A((void**)&hs.u[b], ch * Lq * sizeof(float)));
+    }
+    for (int k = 0; k < kMaxKeys; ++k) { hs.sums[k] = nullptr; hs.sums_elems[k] = 0; }
+    for (int k = 0; k < n_keys; ++k) {
+      hs.sums_elems[k] = (size_t)n_groups[k] * S * S;
+      CUDA_TRY(A((void**)&hs.sums[k], hs.sums_elems[k] * sizeof(double)));
+    }
+    hs.chunk = ch; hs.n_keys = n_keys; hs.has_cell = cell_out != nullptr; hs.has_z = z_out != nullptr; hs.has_u = u_out != nullptr;
+  }
+  ch = std::min(ch, hs.chunk);
+  for (int k = 0; k < n_keys; ++k)
+    CUDA_TRY(cudaMemsetAsync(hs.sums[k], 0, (size_t)n_groups[k] * S * S * sizeof(double), hs.s_comp));
+  h->ev_used = 0;
+  CUDA_TRY(cudaEventRecord(h->ev_call[0], hs.s_comp));
+  int64_t c = 0;
+  for (int64_t lo = 0; lo < n_cells; lo += ch, ++c) {
+    const int b = (int)(c & 1);
+    const int64_t m = std::min(ch, n_cells - lo);
+    // H2D (wait until the kernels of chunk c-2 released input buffers b)
+    if (c >= 2) CUDA_TRY(cudaStreamWaitEvent(hs.s_h2d, hs.ev_comp[b], 0));
+    CUDA_TRY(cudaMemcpy2DAsync(hs.X[b], (size_t)G * sizeof(float), X + lo * ldx, (size_t)ldx * sizeof(float),
+                               (size_t)G * sizeof(float), (size_t)m, cudaMemcpyHostToDevice, hs.s_h2d));
+    CUDA_TRY(cudaMemcpyAsync(hs.sid[b], sample_idx + lo, m * sizeof(int32_t), cudaMemcpyHostToDevice, hs.s_h2d));
+    for (int k = 0; k < n_keys; ++k)
+      CUDA_TRY(cudaMemcpyAsync(hs.codes[b][k], group_codes[k] + lo, m * sizeof(int32_t), cudaMemcpyHostToDevice, hs.s_h2d));
+    CUDA_TRY(cudaEventRecord(hs.ev_h2d[b], hs.s_h2d));
+    // compute (wait for inputs, and for the D2H of chunk c-2 to release output buffers b)
+    CUDA_TRY(cudaStreamWaitEvent(hs.s_comp, hs.ev_h2d[b], 0));
+    if (c >= 2) CUDA_TRY(cudaStreamWaitEvent(hs.s_comp, hs.ev_d2h[b], 0));
+    if ((err = run_device_impl(h, m, hs.X[b], G, hs.sid[b], n_keys, hs.codes[b], n_groups, norm,
+                               cell_out ? hs.cell[b] : nullptr, hs.sums, z_out ? hs.z[b] : nullptr,
+                               u_out ? hs.u[b] : nullptr, hs.s_comp, false))) return err;
+    CUDA_TRY(cudaEventRecord(hs.ev_comp[b], hs.s_comp));
+    // D2H
+    if (cell_out || z_out || u_out) {
+      CUDA_TRY(cudaStreamWaitEvent(hs.s_d2h, hs.ev_comp[b], 0));
+      if (cell_out) CUDA_TRY(cudaMemcpyAsync(cell_out + lo * S * S, hs.cell[b], m * S * S * sizeof(float), cudaMemcpyDeviceToHost, hs.s_d2h));
+      if (z_out) CUDA_TRY(cudaMemcpyAsync(z_out + lo * S * L, hs.z[b], m * S * L * sizeof(float), cudaMemcpyDeviceToHost, hs.s_d2h));
+      if (u_out) CUDA_TRY(cudaMemcpyAsync(u_out + lo * Lq, hs.u[b], m * Lq * sizeof(float), cudaMemcpyDeviceToHost, hs.s_d2h));
+    }
+    CUDA_TRY(cudaEventRecord(hs.ev_d2h[b], hs.s_d2h));
+  }
+  CUDA_TRY(cudaEventRecord(h->ev_call[1], hs.s_comp));
+  for (int k = 0; k < n_keys; ++k)
+    CUDA_TRY(cudaMemcpyAsync(group_sums[k], hs.sums[k], (size_t)n_groups[k] * S * S * sizeof(double), cudaMemcpyDeviceToHost, hs.s_comp));
+  CUDA_TRY(cudaStreamSynchronize(hs.s_h2d));
+  CUDA_TRY(cudaStreamSynchronize(hs.s_comp));
+  CUDA_TRY(cudaStreamSynchronize(hs.s_d2h));
+  return 0;
+}
+
+int mrvi_last_stage_ms(MrviHandle* h, float out_ms[4]) {
+  if (!h || !out_ms) return fail(MRVI_ERR_INVALID_ARG, "null argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  out_ms[0] = out_ms[1] = out_ms[2] = out_ms[3] = 0.f;
+  for (int i = 0; i + 3 < h->ev_used; i += 4) {
+    float a = 0, b = 0, c = 0;
+    CUDA_TRY(cudaEventElapsedTime(&a, h->ev[i], h->ev[i + 1]));
+    CUDA_TRY(cudaEventElapsedTime(&b, h->ev[i + 1], h->ev[i + 2]));
+    CUDA_TRY(cudaEventElapsedTime(&c, h->ev[i + 2], h->ev[i + 3]));
+    out_ms[0] += a; out_ms[1] += b; out_ms[2] += c;
+  }
+  CUDA_TRY(cudaEventElapsedTime(&out_ms[3], h->ev_call[0], h->ev_call[1]));
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,257 @@
+"""CPU oracle for MrVI's counterfactual local-sample-distance path.  TEST INFRASTRUCTURE ONLY.
+
+This file is the checker, never the product: only ``tests/``, ``__graft_entry__.smoke()`` and
+``bench.py``'s ``cpu_baseline`` / ``--impl reference`` legs may import it.  The shipped path
+(``mrvi_b200``) never imports ``oracle`` and raises if its CUDA library is missing.
+
+It restates, operation by operation and in numpy, the reference's
+``MrVI.get_local_sample_distances`` (``use_mean=True``, eval mode).  Every function cites the
+reference ``file:line`` it follows (paths relative to the reference repo root,
+``src/mrvi/...``).
+
+PARITY UNPINNED at the third-party boundary.  The reference executes its arithmetic through
+flax.linen / jax / numpyro / scvi-tools, none of which is installed here (no wheel, no network),
+and its own tests hold no numeric golden vectors for this path (``tests/test_model.py:233-241``
+check only shapes and symmetry).  So the semantics of the flax primitives below
+(``LayerNorm`` eps=1e-6 with fast variance, tanh-``gelu``, ``DenseGeneral``, ``Embed``,
+``MultiHeadDotProductAttention`` with 1/sqrt(head_dim) query scaling, no mask, dropout off) are
+restated from their published definitions, not checked against a run of the reference.  What IS
+pinned: (i) the composition of those primitives is cross-checked by executing the reference's own
+``_components.py`` / ``_module.py`` source on a numpy shim of the flax API
+(``oracle/flax_shim`` + ``oracle/gen_golden.py``; fixtures in ``tests/golden``), (ii) two
+independent restatements (this sequential-over-samples numpy one and the vectorised torch one in
+``oracle/mrvi_oracle_torch.py``) agree, (iii) the invariants of SURVEY.md section 8(c).
+
+Arithmetic dtype is a parameter: float64 is the numeric oracle, float32 mirrors the reference's
+JAX default (x64 disabled).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+LN_EPS = 1e-6  # flax.linen.LayerNorm default epsilon
+R_HIDDEN = 128  # ResnetBlock.n_hidden default, `_components.py:31`
+
+
+# --------------------------------------------------------------------------- primitives (flax)
+def layer_norm(v, scale=None, bias=None, eps=LN_EPS):
+    """flax.linen.LayerNorm over the last axis, ``use_fast_variance=True``:
+    mean = E[v], var = max(0, E[v^2] - mean^2), y = (v - mean) * rsqrt(var + eps) [* scale] [+ bias]."""
+    mu = v.mean(axis=-1, keepdims=True)
+    var = np.maximum((v * v).mean(axis=-1, keepdims=True) - mu * mu, 0)
+    mul = 1.0 / np.sqrt(var + v.dtype.type(eps))
+    if scale is not None:
+        mul = mul * scale
+    y = (v - mu) * mul
+    if bias is not None:
+        y = y + bias
+    return y
+
+
+def gelu(v):
+    """jax.nn.gelu(approximate=True) == flax ``nn.gelu`` default (`_module.py:56,128,178`; `_components.py:178`)."""
+    t = v.dtype.type
+    c = t(np.sqrt(2.0 / np.pi))
+    return t(0.5) * v * (t(1.0) + np.tanh(c * (v + t(0.044715) * v * v * v)))
+
+
+def relu(v):
+    return np.maximum(v, 0)
+
+
+def dense(v, p, name):
+    """``Dense`` / ``nn.Dense``: v @ kernel + bias (`_components.py:15-24`)."""
+    return v @ p[f"{name}/kernel"] + p[f"{name}/bias"]
+
+
+def softmax(v, axis=-1):
+    m = v.max(axis=axis, keepdims=True)
+    e = np.exp(v - m)
+    return e / e.sum(axis=axis, keepdims=True)
+
+
+# --------------------------------------------------------------------------- building blocks
+def resnet_block(h, p, prefix, act_internal, act_output):
+    """ResnetBlock `_components.py:36-51`."""
+    n_in = h.shape[-1]
+    t = dense(h, p, f"{prefix}/Dense_0")
+    t = layer_norm(t, p[f"{prefix}/LayerNorm_0/scale"], p[f"{prefix}/LayerNorm_0/bias"])
+    t = act_internal(t)
+    if n_in != R_HIDDEN:
+        t = t + dense(h, p, f"{prefix}/Dense_1")
+        k = 2
+    else:
+        t = t + h
+        k = 1
+    t = dense(t, p, f"{prefix}/Dense_{k}")
+    t = layer_norm(t, p[f"{prefix}/LayerNorm_1/scale"], p[f"{prefix}/LayerNorm_1/bias"])
+    return act_output(t)
+
+
+def mlp(h, p, prefix, act):
+    """MLP `_components.py:63-75`: ResnetBlock_* then a final Dense."""
+    i = 0
+    while f"{prefix}/ResnetBlock_{i}/Dense_0/kernel" in p:
+        h = resnet_block(h, p, f"{prefix}/ResnetBlock_{i}", act, act)
+        i += 1
+    return dense(h, p, f"{prefix}/Dense_0")
+
+
+def conditional_normalization(h, sid, p, prefix):
+    """ConditionalNormalization `_components.py:130-162` (normalization_type="layer")."""
+    h = layer_norm(h)  # use_bias=False, use_scale=False
+    gamma = p[f"{prefix}/gamma_conditional/embedding"][sid]
+    beta = p[f"{prefix}/beta_conditional/embedding"][sid]
+    return gamma * h + beta
+
+
+def encoder_xu_mean(p, x, sid):
+    """_EncoderXU `_module.py:182-202` + NormalDistOutputNN mean head `_components.py:86-97`.
+    Returns qu.mean, i.e. u under use_mean=True (`_module.py:312-314`)."""
+    h = np.log1p(x)
+    for i in range(2):
+        h = dense(h, p, f"qu/Dense_{i}")
+        h = conditional_normalization(h, sid, p, f"qu/ConditionalNormalization_{i}")
+        h = gelu(h)
+    h = h + p["qu/Embed_0/embedding"][sid]
+    i = 0
+    nd = "qu/NormalDistOutputNN_0"
+    while f"{nd}/ResnetBlock_{i}/Dense_0/kernel" in p:
+        h = resnet_block(h, p, f"{nd}/ResnetBlock_{i}", relu, relu)
+        i += 1
+    return dense(h, p, f"{nd}/Dense_0")
+
+
+def multi_head_attention(q_in, kv_in, p, prefix):
+    """flax MultiHeadDotProductAttention as called at `_components.py:199-205`
+    (inputs (B, E, 1); no mask; deterministic)."""
+    q = np.einsum("bti,ihd->bthd", q_in, p[f"{prefix}/query/kernel"]) + p[f"{prefix}/query/bias"]
+    k = np.einsum("bti,ihd->bthd", kv_in, p[f"{prefix}/key/kernel"]) + p[f"{prefix}/key/bias"]
+    v = np.einsum("bti,ihd->bthd", kv_in, p[f"{prefix}/value/kernel"]) + p[f"{prefix}/value/bias"]
+    depth = q.shape[-1]
+    q = q / np.sqrt(depth).astype(q.dtype)
+    w = np.einsum("bqhd,bkhd->bhqk", q, k)
+    w = softmax(w, axis=-1)
+    a = np.einsum("bhqk,bkhd->bqhd", w, v)
+    return np.einsum("bqhd,hdc->bqc", a, p[f"{prefix}/out/kernel"]) + p[f"{prefix}/out/bias"]
+
+
+def attention_block(u_, e_s, p, prefix="qz/AttentionBlock_0"):
+    """AttentionBlock `_components.py:181-230` without MC axis."""
+    q_tok = np.einsum("bl,lei->bei", u_, p[f"{prefix}/DenseGeneral_0/kernel"])  # (B,E,1)  :195-197
+    kv_tok = np.einsum("bl,lei->bei", e_s, p[f"{prefix}/DenseGeneral_1/kernel"])  # (B,E,1)  :198
+    o = multi_head_attention(q_tok, kv_tok, p, f"{prefix}/MultiHeadDotProductAttention_0")  # (B,E,C)
+    a = o.reshape(o.shape[0], o.shape[1] * o.shape[2])  # :209-210
+    eps_ = mlp(a, p, f"{prefix}/MLP_0", gelu)  # :216-221
+    c = np.concatenate([u_, eps_], axis=-1)  # :222
+    return mlp(c, p, f"{prefix}/MLP_1", gelu)  # :223-229
+
+
+def encoder_uz(p, u, s_idx):
+    """EncoderUZ `_module.py:131-170`: returns (z_base, residual)."""
+    u_ = layer_norm(u, p["qz/u_ln/scale"], p["qz/u_ln/bias"])
+    e = p["qz/Embed_0/embedding"][s_idx]
+    e = layer_norm(e, p["qz/sample_embed_ln/scale"], p["qz/sample_embed_ln/bias"])
+    residual = attention_block(u_, e, p)
+    if "qz/Dense_0/kernel" in p:
+        z_base = dense(u, p, "qz/Dense_0")  # raw u, `_module.py:166-168`
+    else:
+        z_base = u
+    return z_base, residual
+
+
+def inference_z(p, x, sid, cf_sample):
+    """MrVAE.inference(...)["z"] with use_mean=True (`_module.py:308-343`)."""
+    u = encoder_xu_mean(p, x, sid)
+    z_base, eps = encoder_uz(p, u, cf_sample)
+    L = z_base.shape[-1]
+    if eps.shape[-1] == 2 * L:  # use_map=False: qeps.mean = first half (`_module.py:326-329`)
+        eps = eps[..., :L]
+    return z_base + eps
+
+
+def cast_params(flat, dtype):
+    return {k: np.asarray(v, dtype=dtype) for k, v in flat.items()}
+
+
+def counterfactual_z(flat, x, sid, dtype=np.float64):
+    """mapped_inference_fn `_model.py:326-365` (the sequential ``lax.map`` form): z[b, s, :] for every
+    counterfactual sample s, output axes (cell, sample, latent) (`out_axes=-2`, `:352`)."""
+    p = cast_params(flat, dtype)
+    x = np.asarray(x, dtype=dtype)
+    sid = np.asarray(sid).astype(np.int64).reshape(-1)
+    S = p["qz/Embed_0/embedding"].shape[0]
+    zs = []
+    for s in range(S):
+        cf = np.full(x.shape[0], s, dtype=np.int64)
+        zs.append(inference_z(p, x, sid, cf))
+    return np.stack(zs, axis=1)
+
+
+def pairwise_distances(z, norm="l2"):
+    """_compute_distances_from_representations `_model.py:545-560` (vmap over cells)."""
+    delta = z[:, None, :, :] - z[:, :, None, :]  # [b, i, j] = rep[j] - rep[i]
+    if norm == "l2":
+        return np.sqrt((delta ** 2).sum(-1))
+    if norm == "l1":
+        return np.abs(delta).sum(-1)
+    if norm == "linf":
+        return np.abs(delta).max(-1)
+    raise ValueError(f"norm {norm} not supported")
+
+
+def local_sample_distances(flat, X, sample_idx, group_labels=None, keep_cell=True, batch_size=256,
+                           norm="l2", dtype=np.float64, return_z=False):
+    """The hot loop of ``compute_local_statistics`` (`_model.py:376-504`) on plain arrays.
+
+    ``group_labels``: dict key -> array of labels (any hashable), one per cell.  Per batch, per
+    category present, the (B,S,S) blocks are summed and added to a running sum (`:469-484`); at
+    the end every running sum is divided by the category's count and categories are emitted in
+    ``value_counts()`` order (`:493-504`) -- the caller passes that order in via pandas; here we
+    return sums keyed by label plus counts, and ``group_means`` in descending-count order with
+    first-appearance tie-break (what ``pd.Series.value_counts`` does for object dtype).
+    """
+    n = X.shape[0]
+    out = {}
+    cell_blocks, z_blocks = [], []
+    sums = {k: {} for k in (group_labels or {})}
+    for lo in range(0, n, batch_size):
+        hi = min(lo + batch_size, n)
+        z = counterfactual_z(flat, X[lo:hi], sample_idx[lo:hi], dtype=dtype)
+        if return_z:
+            z_blocks.append(z)
+        d = pairwise_distances(z, norm)
+        if keep_cell:
+            cell_blocks.append(d)
+        for key, labels in (group_labels or {}).items():
+            lab = np.asarray(labels)[lo:hi]
+            seen = []
+            for c in lab:  # unique(), order of first appearance
+                if c not in seen:
+                    seen.append(c)
+            for c in seen:
+                part = d[lab == c].sum(axis=0)
+                if c not in sums[key]:
+                    sums[key][c] = part
+                else:
+                    sums[key][c] = sums[key][c] + part
+    if keep_cell:
+        out["cell"] = np.concatenate(cell_blocks, axis=0) if cell_blocks else np.zeros((0, 0, 0), dtype)
+    if return_z:
+        out["z"] = np.concatenate(z_blocks, axis=0)
+    for key, labels in (group_labels or {}).items():
+        lab = list(np.asarray(labels))
+        cats, counts = [], {}
+        for c in lab:
+            if c not in counts:
+                counts[c] = 0
+                cats.append(c)
+            counts[c] += 1
+        order = sorted(range(len(cats)), key=lambda i: -counts[cats[i]])  # stable
+        cats = [cats[i] for i in order]
+        out[key] = {
+            "labels": cats,
+            "counts": np.array([counts[c] for c in cats], dtype=np.int64),
+            "means": np.stack([sums[key][c] / dtype(counts[c]) for c in cats], axis=0),
+        }
+    return out

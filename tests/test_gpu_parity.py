@@ -1,0 +1,135 @@
+"""GPU parity tests proper: the CUDA path, called through the C-ABI, against the oracle.
+
+Tolerances (normwise, per test): fp32-FFMA mode 1e-5 of the largest distance (north_star's fp32 bar);
+tensor-core mode 1e-3.  Group assignment, counts and cell order must be exact.
+"""
+import numpy as np
+import pytest
+
+import mrvi_b200
+from mrvi_b200 import _capi
+from oracle import mrvi_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"fp32": 1e-5, "tc": 1e-3}
+
+
+def _model(dims, seed=0, precision="fp32", **kw):
+    params = mrvi_b200.init_params(dims, seed=seed, **kw)
+    return params, _capi.Handle(dims, params, device=0, precision=_capi.PRECISION_FP32 if precision == "fp32" else _capi.PRECISION_TC)
+
+
+def _inputs(n, G, S, seed=0):
+    X = mrvi_b200.synthetic_counts(n, G, seed=seed)
+    sid = np.random.default_rng(seed + 7).integers(0, S, size=n).astype(np.int32)
+    return X, sid
+
+
+def _relerr(got, ref):
+    return float(np.abs(got.astype(np.float64) - ref).max() / np.abs(ref).max())
+
+
+CASES = [
+    # (name, dims kwargs, n_cells)
+    ("c1_400x100_S4", dict(n_input=100, n_sample=4), 400),
+    ("tests_S15", dict(n_input=100, n_sample=15), 300),
+    ("isomorphic_L10", dict(n_input=100, n_sample=15, n_latent=10, n_latent_u=10), 200),
+    ("latent_u5", dict(n_input=100, n_sample=6, n_latent=10, n_latent_u=5), 200),
+    ("use_map_false", dict(n_input=60, n_sample=5, use_map=False), 130),
+    ("S32_G2000", dict(n_input=2000, n_sample=32), 192),
+    ("S128", dict(n_input=333, n_sample=128), 70),
+    ("S256_L50", dict(n_input=128, n_sample=256, n_latent=50), 20),
+    ("H64_skip", dict(n_input=50, n_sample=7, encoder_n_hidden=64), 100),
+    ("qz_layers2", dict(n_input=50, n_sample=9, qz_n_layers=2), 100),
+    ("odd_G", dict(n_input=101, n_sample=3), 65),
+]
+
+
+@pytest.mark.parametrize("name,dk,n", CASES, ids=[c[0] for c in CASES])
+def test_fp32_matches_oracle(built_library, name, dk, n):
+    dims = mrvi_b200.MrviDims(**dk)
+    params, h = _model(dims, seed=3)
+    X, sid = _inputs(n, dims.n_input, dims.n_sample, seed=5)
+    rng = np.random.default_rng(11)
+    codes = [rng.integers(0, 3, size=n).astype(np.int32), rng.integers(0, 2, size=n).astype(np.int32)]
+    res = h.run_host(X, sid, codes, [3, 2], keep_cell=True, want_z=True, want_u=True)
+    zref = orc.counterfactual_z(params, X, sid, dtype=np.float64)
+    uref = orc.encoder_xu_mean(orc.cast_params(params, np.float64), X.astype(np.float64), sid)
+    dref = orc.pairwise_distances(zref)
+    assert _relerr(res["u"], uref) < 1e-5
+    assert _relerr(res["z"], zref) < 1e-5
+    assert _relerr(res["cell"], dref) < TOL["fp32"]
+    # exact structural properties of the direct-difference kernel
+    assert np.all(np.diagonal(res["cell"], axis1=1, axis2=2) == 0)
+    assert np.array_equal(res["cell"], np.swapaxes(res["cell"], 1, 2))
+    for k, ng in enumerate([3, 2]):
+        assert np.array_equal(res["group_counts"][k], np.bincount(codes[k], minlength=ng))
+        ref_sum = np.stack([dref[codes[k] == g].sum(0) for g in range(ng)])
+        assert _relerr(res["group_sums"][k], ref_sum) < TOL["fp32"]
+    h.close()
+
+
+@pytest.mark.parametrize("norm", ["l1", "linf", "l2"])
+def test_norms(built_library, norm):
+    dims = mrvi_b200.MrviDims(n_input=40, n_sample=70)
+    params, h = _model(dims, seed=1)
+    X, sid = _inputs(50, 40, 70, seed=2)
+    res = h.run_host(X, sid, norm=norm, keep_cell=True, want_z=True)
+    dref = orc.pairwise_distances(res["z"].astype(np.float64), norm)
+    assert _relerr(res["cell"], dref) < 1e-6
+    h.close()
+
+
+def test_chunking_and_ragged(built_library):
+    """Results do not depend on the host chunk size; ragged final chunk; n smaller than a tile."""
+    dims = mrvi_b200.MrviDims(n_input=64, n_sample=12)
+    params, h = _model(dims, seed=2)
+    X, sid = _inputs(1000, 64, 12, seed=9)
+    codes = [np.random.default_rng(0).integers(0, 5, size=1000).astype(np.int32)]
+    a = h.run_host(X, sid, codes, [5], keep_cell=True)
+    b = h.run_host(X, sid, codes, [5], keep_cell=True, chunk_cells=137)
+    assert np.array_equal(a["cell"], b["cell"])
+    assert np.allclose(a["group_sums"][0], b["group_sums"][0], rtol=1e-6)
+    c = h.run_host(X[:3], sid[:3], [codes[0][:3]], [5], keep_cell=True)
+    assert np.array_equal(c["cell"], a["cell"][:3])
+    e = h.run_host(X[:0], sid[:0], [codes[0][:0]], [5], keep_cell=True)
+    assert e["cell"].shape == (0, 12, 12) and np.all(e["group_sums"][0] == 0)
+    h.close()
+
+
+def test_drop_in_api_matches_reference_layout(built_library):
+    """The reference's own grouped-distance test (`tests/test_model.py:221-241`): shapes, symmetry, both
+    outputs in one Dataset -- plus values against the oracle and value_counts() group order."""
+    ad = mrvi_b200.synthetic_iid(n_obs=400, n_vars=100, n_sample=15, seed=4)
+    dims = mrvi_b200.MrviDims(n_input=100, n_sample=15, n_latent=10, n_latent_u=10)
+    params = mrvi_b200.init_params(dims, seed=8)
+    model = mrvi_b200.MrVI(ad, params, sample_key="sample_str")
+    dists = model.get_local_sample_distances(groupby=["labels", "label_2"])
+    cell = dists["cell"]
+    assert cell.shape == (400, 15, 15)
+    assert dists["labels"].shape == (3, 15, 15)
+    assert dists["label_2"].shape == (2, 15, 15)
+    for key in ("labels", "label_2"):
+        g0 = np.asarray(dists[key][0].values)
+        assert np.allclose(g0, g0.T, atol=1e-6)
+    assert "_indices" in ad.obs
+    sid = model._sample_codes(ad)
+    ref = orc.local_sample_distances(params, ad.X, sid, {k: ad.obs[k].to_numpy() for k in ("labels", "label_2")},
+                                     keep_cell=True, dtype=np.float64)
+    assert _relerr(np.asarray(cell.values), ref["cell"]) < 1e-5
+    for key in ("labels", "label_2"):
+        vc = ad.obs[key].value_counts()
+        assert list(np.asarray(dists[key].coords[f"{key}_name"])) == list(vc.index)
+        assert _relerr(np.asarray(dists[key].values), ref[key]["means"]) < 1e-5
+        assert np.asarray(dists[key].values).dtype == np.float32
+    assert list(np.asarray(cell.coords["cell_name"])) == list(ad.obs_names)
+    assert list(np.asarray(cell.coords["sample_x"])) == list(model.sample_order)
+    # group-only call returns no "cell"
+    g = model.get_local_sample_distances(groupby="labels", keep_cell=False)
+    assert "cell" not in g and np.array_equal(np.asarray(g["labels"].values), np.asarray(dists["labels"].values))
+    with pytest.raises(ValueError, match="Undefined computation"):
+        model.get_local_sample_distances(keep_cell=False)
+    z = model.get_local_sample_representation()
+    assert z.shape == (400, 15, 10)
+    model.close()
