@@ -152,6 +152,14 @@ struct ParamTable {
   bool has(const std::string& name) const { return m.count(name) != 0; }
 };
 
+int tc_upload(DeviceArena& arena, const void* host, size_t bytes, const void** dev) {
+  void* d = nullptr;
+  CUDA_TRY(arena.alloc(&d, bytes));
+  if (bytes) CUDA_TRY(cudaMemcpy(d, host, bytes, cudaMemcpyHostToDevice));
+  *dev = d;
+  return 0;
+}
+
 static int upload(MrviHandle* h, const std::vector<float>& host, const float** out) {
   float* d = nullptr;
   CUDA_TRY(h->arena.alloc((void**)&d, host.size() * sizeof(float)));
@@ -432,12 +440,15 @@ static int run_device_impl(MrviHandle* h, int64_t n, const float* X, int64_t ldx
     if (time_stages) { e0 = next_event(h); e1 = next_event(h); e2 = next_event(h); e3 = next_event(h); cudaEventRecord(e0, st); }
     int err;
     float* z = z_out ? z_out + lo * net.S * net.L : h->zbuf;
-    if (h->precision == MRVI_PRECISION_TC) {
-      if ((err = tc_launch_chain(h->tc, h->net, X + lo * ldx, ldx, sid + lo, m, h->cb, need_z ? z : nullptr, st, e1))) return err;
-    } else {
-      if ((err = launch_encoder(h, X + lo * ldx, ldx, sid + lo, m, st))) return err;
-      if (time_stages) cudaEventRecord(e1, st);
-      if (need_z) { if ((err = launch_qz(h, m, z, st))) return err; }
+    if ((err = launch_encoder(h, X + lo * ldx, ldx, sid + lo, m, st))) return err;
+    if (time_stages) cudaEventRecord(e1, st);
+    if (need_z) {
+      if (h->precision == MRVI_PRECISION_TC) {
+        if ((err = tc_launch_qz(h->tc, h->net, m, h->cb, z, st))) return err;
+        LAUNCH_CHECK();
+      } else {
+        if ((err = launch_qz(h, m, z, st))) return err;
+      }
     }
     if (time_stages) cudaEventRecord(e2, st);
     if (u_out) CUDA_TRY(cudaMemcpyAsync(u_out + lo * net.Lq, h->cb.u, m * net.Lq * sizeof(float), cudaMemcpyDeviceToDevice, st));

@@ -1,29 +1,685 @@
-// tcgen05 tensor-core path (MRVI_PRECISION_TC).  Placeholder until the kernels land: creating a
-// handle with MRVI_PRECISION_TC fails loudly with MRVI_ERR_UNSUPPORTED (no silent fallback).
+// tcgen05 tensor-core path of the q(z|u,s) chain (MRVI_PRECISION_TC), sm_100a only.
+//
+// One CTA = 128 threads = one 128-row tile of (cell, sample) rows; thread r owns row r, which is
+// TMEM lane r, so LayerNorm statistics are thread-local.  The chain of the reference
+// (_components.py:181-230) is executed as five GEMMs on the 5th-gen tensor cores
+// (tcgen05.mma, kind::f16, fp32 accumulators in TMEM) with CUDA-core epilogues in between:
+//
+//   attention  -> m[h,i] = softmax_j(t[h,i] kv_s[j]) . kv_s        (exact collapse of the 16x16x2 MHA;
+//                 score is rank-1 in the scalar tokens, value/out projections fold into GEMM1)
+//   GEMM1  D1[128x128] = A1[m | 1]            x B1      (MLP_0 Dense_0, attention out-proj folded in)
+//   epi1   T = gelu(LN(D1))                              (fp32, thread-local row statistics)
+//   GEMM2  D2[128x32]  = T x B2t + A1 x B2a              (Dense_2; the skip Dense_1 folded: (a Ws) Wout)
+//   epi2   t2 = gelu(LN(D2))
+//   GEMM3  D3[128x128] = A3[t2 | u_ln | 1]    x B3      (MLP_0 Dense_0(out) and MLP_1 Dense_0 fused)
+//   epi3   T = gelu(LN(D3))
+//   GEMM4  D4[128x32]  = T x B4t + A3 x B4a
+//   epi4   t4 = gelu(LN(D4))
+//   GEMM5  D5[128xN5]  = A5[t4 | 1]           x B5      (MLP_1 final Dense, first L outputs)
+//
+// Every A operand is written as an (hi, lo) pair of f16 values (hi = 11 leading bits, lo = the
+// remainder) and multiplied against the same f16 weights twice, which keeps the activation
+// rounding at 2^-21; weights are rounded to f16 once (systematic 3e-4 normwise effect on the
+// distances, measured in oracle/tc_emulation.py).  All folding of weights is done in float64 on the
+// host at create time (tc_build).
+//
+// Operands use the canonical no-swizzle K-major UMMA layout: 16-byte chunk kc of row r of an
+// [R x K] operand lives at  base + kc * (R * 16) + r * 16  (LBO = R*16 bytes between K chunks,
+// SBO = 128 bytes between groups of 8 rows), so thread r writes its row with conflict-free
+// 16-byte shared stores.
 #pragma once
+#include <cuda_fp16.h>
+
+#include <cmath>
 #include <map>
 #include <string>
+#include <vector>
 
 #include "common.cuh"
 
 namespace mrvi {
 
-struct DeviceArena;
+constexpr int kTcThreads = 128;
+constexpr int kTcRows = 128;
+constexpr float kLog2e = 1.4426950408889634f;
 
-struct TcNet {
-  const float* kvtok = nullptr;  // [S][E] per-sample kv tokens (filled by build_net)
+// epilogue vectors, passed by value so they are read as constant-bank operands
+struct TcLn {
+  float g1[128], b1[128];  // MLP_0 ResnetBlock LayerNorm_0
+  float g2[32], b2[32];    // MLP_0 ResnetBlock LayerNorm_1
+  float g3[128], b3[128];  // MLP_1 ResnetBlock LayerNorm_0
+  float g4[32], b4[32];    // MLP_1 ResnetBlock LayerNorm_1
 };
 
-inline const char* tc_error() { return "MRVI_PRECISION_TC is not built into this library yet"; }
+struct TcNet {
+  const float* kvtok = nullptr;   // [S][16] per-sample kv tokens (fp32)
+  const float* kvl = nullptr;     // [S][16] kv * log2(e)
+  const float* kvref = nullptr;   // [S][2]  (max_j kv, min_j kv) * log2(e)
+  const uint8_t* wimg = nullptr;  // packed f16 operand image (device), copied verbatim to smem
+  uint32_t wimg_bytes = 0;
+  uint32_t off_b1 = 0, off_b2t = 0, off_b2a = 0, off_b3 = 0, off_b4t = 0, off_b4a = 0, off_b5 = 0;
+  int K1 = 48, K3 = 48, K5 = 48, N5 = 32;
+  float alpha[2] = {0, 0}, beta[2] = {0, 0};  // t[h,i] = alpha[h] * q_tok[i] + beta[h]
+  TcLn ln;
+  int sm_count = 148;
+  size_t smem_bytes = 0;
+  bool ready = false;
+};
 
-inline int tc_build(TcNet&, const NetW&, const MrviDims&,
-                    const std::map<std::string, std::pair<const float*, int64_t>>&, DeviceArena&, int) {
-  return MRVI_ERR_UNSUPPORTED;
+static std::string g_tc_error;
+inline const char* tc_error() { return g_tc_error.c_str(); }
+
+// ------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 
-inline int tc_launch_chain(const TcNet&, const NetW&, const float*, int64_t, const int32_t*, int64_t,
-                           const CellBuf&, float*, cudaStream_t, cudaEvent_t) {
-  return MRVI_ERR_UNSUPPORTED;
+// SMEM matrix descriptor, K-major, no swizzle: LBO = byte distance between 16-byte K chunks,
+// SBO = byte distance between 8-row groups.  (cute::UMMA::SmemDescriptor bit layout, version 1.)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+  return d;                // base_offset = 0, lbo_mode = 0, layout_type = SWIZZLE_NONE (0)
+}
+
+// instruction descriptor for kind::f16: A = B = f16, D = f32, both K-major, M = 128
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int N) {
+  return (1u << 4)                     // c_format = F32
+         | (0u << 7) | (0u << 10)      // a_format = b_format = F16
+         | (0u << 15) | (0u << 16)     // a_major = b_major = K
+         | ((uint32_t)(N >> 3) << 17)  // n_dim
+         | ((uint32_t)(128 >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// 32 lanes x 32 consecutive 32-bit columns -> 32 registers per thread
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rsqrt_approx(float x) {
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// gelu(tanh) with MUFU.TANH (measured max abs error 7.6e-6 on B200, tools/microbench.cu)
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float c1 = 0.7978845608028654f, c2 = 0.7978845608028654f * 0.044715f;
+  const float u = x * x;
+  const float p = fmaf(u, c2, c1);
+  const float t = tanh_approx(x * p);
+  const float hx = 0.5f * x;
+  return fmaf(hx, t, hx);
+}
+// (hi, lo) f16 split of two floats: hi = leading 11 significant bits (exact in f16 when the
+// exponent is in range), lo = remainder rounded to f16.  Returns packed f16x2 words.
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const float ah = __uint_as_float(__float_as_uint(a) & 0xFFFFE000u);
+  const float bh = __uint_as_float(__float_as_uint(b) & 0xFFFFE000u);
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(bh), "f"(ah));  // upper half = first source
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(b - bh), "f"(a - ah));
+}
+
+// ------------------------------------------------------------------------------------------
+// shared memory map (bytes, from a 1024-aligned base)
+// ------------------------------------------------------------------------------------------
+struct TcSmemMap {
+  uint32_t w;        // weight image
+  uint32_t a1h, a1l; // [128 x K1]   (also A5 = [t4 | 1])
+  uint32_t a3h, a3l; // [128 x K3]
+  uint32_t th, tl;   // [128 x 128]
+  uint32_t bars;     // 2 mbarriers + tmem slot
+  uint32_t total;
+};
+__host__ __device__ inline TcSmemMap tc_smem_map(uint32_t wimg_bytes, int K1, int K3) {
+  TcSmemMap m;
+  uint32_t o = 0;
+  auto take = [&](uint32_t bytes) { uint32_t r = o; o += (bytes + 1023u) & ~1023u; return r; };
+  m.w = take(wimg_bytes);
+  m.a1h = take(128 * K1 * 2); m.a1l = take(128 * K1 * 2);
+  m.a3h = take(128 * K3 * 2); m.a3l = take(128 * K3 * 2);
+  m.th = take(128 * 128 * 2); m.tl = take(128 * 128 * 2);
+  m.bars = take(64);
+  m.total = o;
+  return m;
+}
+
+// LayerNorm + gelu of NV = 32*NCH accumulator columns held in registers; writes (hi, lo) f16 chunks.
+// dst_h / dst_l: this row's first 16-byte chunk; chunk stride = 128 rows * 16 B = 2048 B.
+template <int NCH>
+__device__ __forceinline__ void ln_gelu_store(float (&v)[NCH * 32], const float* __restrict__ g,
+                                              const float* __restrict__ b, uint8_t* dst_h, uint8_t* dst_l) {
+  constexpr int NV = NCH * 32;
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) { s1 += v[i]; s2 = fmaf(v[i], v[i], s2); }
+  const float mean = s1 * (1.0f / NV);
+  const float var = fmaxf(fmaf(s2, 1.0f / NV, -mean * mean), 0.f);
+  const float rstd = rsqrt_approx(var + kLnEps);
+  const float nb = -mean * rstd;
+#pragma unroll
+  for (int c = 0; c < NV / 8; ++c) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int i0 = c * 8 + 2 * j, i1 = i0 + 1;
+      const float y0 = gelu_fast(fmaf(fmaf(v[i0], rstd, nb), g[i0], b[i0]));
+      const float y1 = gelu_fast(fmaf(fmaf(v[i1], rstd, nb), g[i1], b[i1]));
+      split2(y0, y1, h[j], l[j]);
+    }
+    *reinterpret_cast<uint4*>(dst_h + c * 2048) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(dst_l + c * 2048) = make_uint4(l[0], l[1], l[2], l[3]);
+  }
+}
+
+// issue the MMAs of one [128 x K] x [K x N] product for both the hi and lo copy of A
+__device__ __forceinline__ void issue_gemm(uint32_t d_tmem, uint32_t a_h, uint32_t a_l, uint32_t b, int K, int N,
+                                           uint32_t idesc, bool first_clears) {
+  const uint32_t a_lbo = 128 * 16, b_lbo = (uint32_t)N * 16;
+  for (int ks = 0; ks < K / 16; ++ks) {
+    const uint64_t bd = umma_desc(b + ks * 2 * b_lbo, b_lbo, 128);
+    umma_f16(d_tmem, umma_desc(a_h + ks * 2 * a_lbo, a_lbo, 128), bd, idesc, (first_clears && ks == 0) ? 0u : 1u);
+    umma_f16(d_tmem, umma_desc(a_l + ks * 2 * a_lbo, a_lbo, 128), bd, idesc, 1u);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// the chain kernel: persistent over 128-row tiles
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kTcThreads, 1)
+k_chain_tc(const __grid_constant__ TcNet tc, CellBuf cb, int64_t n_cells, int S, int L, int Lq,
+           float* __restrict__ z_out, int64_t n_tiles, int cells_per_tile, int tiles_per_cell) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const TcSmemMap sm = tc_smem_map(tc.wimg_bytes, tc.K1, tc.K3);
+  uint64_t* bar_w = reinterpret_cast<uint64_t*>(smem + sm.bars);
+  uint64_t* bar_mma = bar_w + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_w + 2);
+  const int tid = threadIdx.x, warp = tid >> 5;
+
+  if (tid == 0) {
+    mbar_init(bar_w, 1);
+    mbar_init(bar_mma, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 128);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (tid == 0) {
+    mbar_expect_tx(bar_w, tc.wimg_bytes);
+    bulk_g2s(smem + sm.w, tc.wimg, tc.wimg_bytes, bar_w);
+  }
+  const uint32_t s_w = smem_u32(smem + sm.w);
+  const uint32_t s_a1h = smem_u32(smem + sm.a1h), s_a1l = smem_u32(smem + sm.a1l);
+  const uint32_t s_a3h = smem_u32(smem + sm.a3h), s_a3l = smem_u32(smem + sm.a3l);
+  const uint32_t s_th = smem_u32(smem + sm.th), s_tl = smem_u32(smem + sm.tl);
+  uint8_t* row_a1h = smem + sm.a1h + tid * 16;
+  uint8_t* row_a1l = smem + sm.a1l + tid * 16;
+  uint8_t* row_a3h = smem + sm.a3h + tid * 16;
+  uint8_t* row_a3l = smem + sm.a3l + tid * 16;
+  uint8_t* row_th = smem + sm.th + tid * 16;
+  uint8_t* row_tl = smem + sm.tl + tid * 16;
+  const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16);  // this warp's TMEM lane quarter
+  const uint32_t idesc128 = umma_idesc_f16(128), idesc32 = umma_idesc_f16(32), idescN5 = umma_idesc_f16(tc.N5);
+  uint32_t phase = 0;
+  mbar_wait(bar_w, 0);  // weights landed (async proxy wrote them; MMA reads them through the same proxy)
+
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    // ---- row -> (cell, s)
+    int64_t cell;
+    int s;
+    bool valid;
+    if (tiles_per_cell == 1) {
+      const int lc = tid / S;
+      cell = tile * cells_per_tile + lc;
+      s = tid - lc * S;
+      valid = lc < cells_per_tile && cell < n_cells;
+    } else {
+      cell = tile / tiles_per_cell;
+      s = (int)(tile % tiles_per_cell) * kTcRows + tid;
+      valid = s < S;
+    }
+    const int64_t cc = valid ? cell : 0;
+    const int ss = valid ? s : 0;
+
+    // ---- attention features m[h*16+i] -> A1 = [m | 1 | 0...], A3 static part = [.. | u_ln | 1 | 0..]
+    {
+      float kvl[16];
+      const float4* kp = reinterpret_cast<const float4*>(tc.kvl + (size_t)ss * 16);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 t4 = __ldg(kp + q);
+        kvl[4 * q] = t4.x; kvl[4 * q + 1] = t4.y; kvl[4 * q + 2] = t4.z; kvl[4 * q + 3] = t4.w;
+      }
+      const float rmax = __ldg(tc.kvref + ss * 2), rmin = __ldg(tc.kvref + ss * 2 + 1);
+      float qt[16];
+      const float4* qp = reinterpret_cast<const float4*>(cb.q_tok + cc * 16);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 t4 = __ldg(qp + q);
+        qt[4 * q] = t4.x; qt[4 * q + 1] = t4.y; qt[4 * q + 2] = t4.z; qt[4 * q + 3] = t4.w;
+      }
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {  // 8 features per 16-byte chunk
+          uint32_t hw[4], lw[4];
+#pragma unroll
+          for (int j2 = 0; j2 < 4; ++j2) {
+            float mm[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int i = c * 8 + j2 * 2 + e;
+              const float t = fmaf(tc.alpha[h], qt[i], tc.beta[h]);
+              const float off = -t * (t >= 0.f ? rmax : rmin);  // exponent <= 0 for every j
+              float den = 0.f, num = 0.f;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const float ex = ex2_approx(fmaf(t, kvl[j], off));
+                den += ex;
+                num = fmaf(ex, kvl[j], num);
+              }
+              mm[e] = num * rcp_approx(den);  // = log2(e) * m[h,i]; the 1/log2(e) is folded into B1 / B2a
+            }
+            split2(mm[0], mm[1], hw[j2], lw[j2]);
+          }
+          *reinterpret_cast<uint4*>(row_a1h + (h * 2 + c) * 2048) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+          *reinterpret_cast<uint4*>(row_a1l + (h * 2 + c) * 2048) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+        }
+      }
+      // constant-one column (k = 32) and zero padding of A1
+      const uint32_t one_h = 0x00003C00u;  // f16 1.0 in the low half
+      for (int c = 4; c < tc.K1 / 8; ++c) {
+        *reinterpret_cast<uint4*>(row_a1h + c * 2048) = make_uint4(c == 4 ? one_h : 0u, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(row_a1l + c * 2048) = make_uint4(0u, 0u, 0u, 0u);
+      }
+      // A3 static part: columns 32.. = u_ln[0..Lq), then 1.0, then zeros
+      const float* ul = cb.u_ln + cc * Lq;
+      for (int c = 4; c < tc.K3 / 8; ++c) {
+        uint32_t hw[4], lw[4];
+#pragma unroll
+        for (int j2 = 0; j2 < 4; ++j2) {
+          const int k0 = (c - 4) * 8 + 2 * j2, k1 = k0 + 1;
+          const float a = k0 < Lq ? __ldg(ul + k0) : (k0 == Lq ? 1.0f : 0.f);
+          const float b = k1 < Lq ? __ldg(ul + k1) : (k1 == Lq ? 1.0f : 0.f);
+          split2(a, b, hw[j2], lw[j2]);
+        }
+        *reinterpret_cast<uint4*>(row_a3h + c * 2048) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+        *reinterpret_cast<uint4*>(row_a3l + c * 2048) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+      }
+    }
+    fence_proxy_async();
+    __syncthreads();
+
+    // ---- GEMM1
+    if (tid == 0) {
+      tc_fence_after();
+      issue_gemm(tmem_base, s_a1h, s_a1l, s_w + tc.off_b1, tc.K1, 128, idesc128, true);
+      umma_commit(bar_mma);
+    }
+    mbar_wait(bar_mma, phase); phase ^= 1;
+    tc_fence_after();
+    {
+      float v[128];
+      tmem_ld32(t_lane + 0, v); tmem_ld32(t_lane + 32, v + 32); tmem_ld32(t_lane + 64, v + 64); tmem_ld32(t_lane + 96, v + 96);
+      tmem_ld_wait();
+      ln_gelu_store<4>(v, tc.ln.g1, tc.ln.b1, row_th, row_tl);
+    }
+    tc_fence_before();
+    fence_proxy_async();
+    __syncthreads();
+
+    // ---- GEMM2: D2 = T x B2t + A1 x B2a
+    if (tid == 0) {
+      tc_fence_after();
+      issue_gemm(tmem_base, s_th, s_tl, s_w + tc.off_b2t, 128, 32, idesc32, true);
+      issue_gemm(tmem_base, s_a1h, s_a1l, s_w + tc.off_b2a, tc.K1, 32, idesc32, false);
+      umma_commit(bar_mma);
+    }
+    mbar_wait(bar_mma, phase); phase ^= 1;
+    tc_fence_after();
+    {
+      float v[32];
+      tmem_ld32(t_lane, v);
+      tmem_ld_wait();
+      ln_gelu_store<1>(v, tc.ln.g2, tc.ln.b2, row_a3h, row_a3l);
+    }
+    tc_fence_before();
+    fence_proxy_async();
+    __syncthreads();
+
+    // ---- GEMM3
+    if (tid == 0) {
+      tc_fence_after();
+      issue_gemm(tmem_base, s_a3h, s_a3l, s_w + tc.off_b3, tc.K3, 128, idesc128, true);
+      umma_commit(bar_mma);
+    }
+    mbar_wait(bar_mma, phase); phase ^= 1;
+    tc_fence_after();
+    {
+      float v[128];
+      tmem_ld32(t_lane + 0, v); tmem_ld32(t_lane + 32, v + 32); tmem_ld32(t_lane + 64, v + 64); tmem_ld32(t_lane + 96, v + 96);
+      tmem_ld_wait();
+      ln_gelu_store<4>(v, tc.ln.g3, tc.ln.b3, row_th, row_tl);
+    }
+    tc_fence_before();
+    fence_proxy_async();
+    __syncthreads();
+
+    // ---- GEMM4: D4 = T x B4t + A3 x B4a
+    if (tid == 0) {
+      tc_fence_after();
+      issue_gemm(tmem_base, s_th, s_tl, s_w + tc.off_b4t, 128, 32, idesc32, true);
+      issue_gemm(tmem_base, s_a3h, s_a3l, s_w + tc.off_b4a, tc.K3, 32, idesc32, false);
+      umma_commit(bar_mma);
+    }
+    mbar_wait(bar_mma, phase); phase ^= 1;
+    tc_fence_after();
+    {
+      float v[32];
+      tmem_ld32(t_lane, v);
+      tmem_ld_wait();
+      // A5 = [t4 | 1 | 0] reuses the A1 buffers (GEMM2 was their last reader); the one / zero columns are still in place
+      ln_gelu_store<1>(v, tc.ln.g4, tc.ln.b4, row_a1h, row_a1l);
+    }
+    tc_fence_before();
+    fence_proxy_async();
+    __syncthreads();
+
+    // ---- GEMM5
+    if (tid == 0) {
+      tc_fence_after();
+      issue_gemm(tmem_base, s_a1h, s_a1l, s_w + tc.off_b5, tc.K5, tc.N5, idescN5, true);
+      umma_commit(bar_mma);
+    }
+    mbar_wait(bar_mma, phase); phase ^= 1;
+    tc_fence_after();
+    {
+      float v[64];
+      tmem_ld32(t_lane, v);
+      if (tc.N5 > 32) tmem_ld32(t_lane + 32, v + 32);
+      tmem_ld_wait();
+      if (valid && z_out != nullptr) {
+        const float* zb = cb.zbase + cell * L;
+        float* dst = z_out + (cell * S + s) * (int64_t)L;
+#pragma unroll
+        for (int l = 0; l < 64; ++l)
+          if (l < L) dst[l] = __ldg(zb + l) + v[l];
+      }
+    }
+    tc_fence_before();
+    __syncthreads();  // every thread has read D5 before the next tile's GEMM1 overwrites TMEM
+  }
+
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 128);
+}
+
+// ------------------------------------------------------------------------------------------
+// host side: weight folding (float64) and packing into the f16 operand image
+// ------------------------------------------------------------------------------------------
+struct DeviceArena;
+
+namespace tc_detail {
+using PMap = std::map<std::string, std::pair<const float*, int64_t>>;
+using Mat = std::vector<double>;  // row-major
+
+inline const float* P(const PMap& m, const std::string& k) { return m.at(k).first; }
+
+// C[K x N] = A[K x J] * B[J x N]
+inline Mat matmul(const Mat& A, const Mat& B, int K, int J, int N) {
+  Mat C((size_t)K * N, 0.0);
+  for (int k = 0; k < K; ++k)
+    for (int j = 0; j < J; ++j) {
+      const double a = A[(size_t)k * J + j];
+      for (int n = 0; n < N; ++n) C[(size_t)k * N + n] += a * B[(size_t)j * N + n];
+    }
+  return C;
+}
+inline Mat load(const float* p, size_t n) { return Mat(p, p + n); }
+
+// append a [N x Kpad] K-major canonical f16 operand built from B[K x N] (rows >= K are zero)
+inline uint32_t append_operand(std::vector<uint8_t>& img, const Mat& B, int K, int N, int Npad, int Kpad) {
+  const uint32_t off = (uint32_t)img.size();
+  img.resize(off + (size_t)Npad * Kpad * 2, 0);
+  __half* base = reinterpret_cast<__half*>(img.data() + off);
+  for (int k = 0; k < K; ++k)
+    for (int n = 0; n < N; ++n) {
+      const size_t e = (size_t)(k / 8) * ((size_t)Npad * 8) + (size_t)n * 8 + (k % 8);
+      base[e] = __float2half_rn((float)B[(size_t)k * N + n]);
+    }
+  while (img.size() % 1024) img.push_back(0);
+  return off;
+}
+}  // namespace tc_detail
+
+int tc_upload(DeviceArena& arena, const void* host, size_t bytes, const void** dev);  // defined in mrvi_b200.cu
+
+inline int tc_build(TcNet& tc, const NetW& net, const MrviDims& d, const tc_detail::PMap& pm, DeviceArena& arena, int sm_count) {
+  using namespace tc_detail;
+  const int E = d.n_latent_sample, C = d.n_channels, nh = d.n_heads, M = d.qz_n_hidden, L = d.n_latent;
+  const int Lq = d.n_latent_u > 0 ? d.n_latent_u : L;
+  if (E != 16 || C != 4 || nh != 2 || M != 32 || d.qz_n_layers != 1 || Lq > 31 || L > 64) {
+    g_tc_error = "MRVI_PRECISION_TC supports n_latent_sample=16, n_channels=4, n_heads=2, qz n_hidden=32, qz n_layers=1, "
+                 "n_latent_u<=31, n_latent<=64 (use MRVI_PRECISION_FP32 for other hyper-parameters)";
+    return MRVI_ERR_UNSUPPORTED;
+  }
+  const int R = kResnetHidden, hd = C, S = d.n_sample;
+  const std::string ab = "qz/AttentionBlock_0", mha = ab + "/MultiHeadDotProductAttention_0";
+  const float *wq = P(pm, mha + "/query/kernel"), *bq = P(pm, mha + "/query/bias");
+  const float *wk = P(pm, mha + "/key/kernel"), *wv = P(pm, mha + "/value/kernel"), *bv = P(pm, mha + "/value/bias");
+  const float *wo = P(pm, mha + "/out/kernel"), *bo = P(pm, mha + "/out/bias");
+  const double inv = 1.0 / std::sqrt((double)hd), ln2 = std::log(2.0);
+  for (int h = 0; h < nh; ++h) {
+    double a = 0, b = 0;
+    for (int dd = 0; dd < hd; ++dd) { a += (double)wq[h * hd + dd] * wk[h * hd + dd]; b += (double)bq[h * hd + dd] * wk[h * hd + dd]; }
+    tc.alpha[h] = (float)(a * inv);
+    tc.beta[h] = (float)(b * inv);
+  }
+  // o[i,c] = sum_h m[h,i] pv[h,c] + ro[c]
+  Mat pv((size_t)nh * C, 0.0), ro(C, 0.0);
+  for (int c = 0; c < C; ++c) {
+    ro[c] = bo[c];
+    for (int h = 0; h < nh; ++h)
+      for (int dd = 0; dd < hd; ++dd) {
+        pv[h * C + c] += (double)wv[h * hd + dd] * wo[(h * hd + dd) * C + c];
+        ro[c] += (double)bv[h * hd + dd] * wo[(h * hd + dd) * C + c];
+      }
+  }
+  const std::string b0 = ab + "/MLP_0/ResnetBlock_0", b1 = ab + "/MLP_1/ResnetBlock_0";
+  const int K1r = nh * E + 1;  // [m (scaled by log2e in the kernel) | 1]
+  auto fold_first = [&](const std::string& dense) {  // [K1r x R]: rows (h,i) then the bias row
+    const float *W = P(pm, dense + "/kernel"), *bb = P(pm, dense + "/bias");
+    Mat B((size_t)K1r * R, 0.0);
+    for (int n = 0; n < R; ++n) {
+      double bias = bb[n];
+      for (int i = 0; i < E; ++i)
+        for (int c = 0; c < C; ++c) {
+          const double w = W[(size_t)(i * C + c) * R + n];
+          bias += ro[c] * w;
+          for (int h = 0; h < nh; ++h) B[(size_t)(h * E + i) * R + n] += pv[h * C + c] * w * ln2;  // kernel feeds log2e * m
+        }
+      B[(size_t)(K1r - 1) * R + n] = bias;
+    }
+    return B;
+  };
+  Mat B1 = fold_first(b0 + "/Dense_0");
+  Mat Bs = fold_first(b0 + "/Dense_1");
+  Mat Wout0 = load(P(pm, b0 + "/Dense_2/kernel"), (size_t)R * M);
+  Mat B2a = matmul(Bs, Wout0, K1r, R, M);
+  { const float* bb = P(pm, b0 + "/Dense_2/bias"); for (int n = 0; n < M; ++n) B2a[(size_t)(K1r - 1) * M + n] += bb[n]; }
+  // A3 = [t2 (M) | u_ln (Lq) | 1]
+  const int K3r = M + Lq + 1;
+  Mat Wfin0 = load(P(pm, ab + "/MLP_0/Dense_0/kernel"), (size_t)M * E);
+  const float* bfin0 = P(pm, ab + "/MLP_0/Dense_0/bias");
+  auto fold_second = [&](const std::string& dense) {  // [K3r x R]
+    const float *W = P(pm, dense + "/kernel"), *bb = P(pm, dense + "/bias");  // (Lq+E, R)
+    Mat We = load(W + (size_t)Lq * R, (size_t)E * R);
+    Mat top = matmul(Wfin0, We, M, E, R);
+    Mat B((size_t)K3r * R, 0.0);
+    std::copy(top.begin(), top.end(), B.begin());
+    for (int k = 0; k < Lq; ++k)
+      for (int n = 0; n < R; ++n) B[(size_t)(M + k) * R + n] = W[(size_t)k * R + n];
+    for (int n = 0; n < R; ++n) {
+      double bias = bb[n];
+      for (int e = 0; e < E; ++e) bias += (double)bfin0[e] * We[(size_t)e * R + n];
+      B[(size_t)(K3r - 1) * R + n] = bias;
+    }
+    return B;
+  };
+  Mat B3 = fold_second(b1 + "/Dense_0");
+  Mat S3 = fold_second(b1 + "/Dense_1");
+  Mat Wout1 = load(P(pm, b1 + "/Dense_2/kernel"), (size_t)R * M);
+  Mat B4a = matmul(S3, Wout1, K3r, R, M);
+  { const float* bb = P(pm, b1 + "/Dense_2/bias"); for (int n = 0; n < M; ++n) B4a[(size_t)(K3r - 1) * M + n] += bb[n]; }
+  // A5 = [t4 | 1]; only the first L output columns are kept (use_map=False keeps the mean half)
+  const int out_dim = d.use_map ? L : 2 * L;
+  const float *Wf1 = P(pm, ab + "/MLP_1/Dense_0/kernel"), *bf1 = P(pm, ab + "/MLP_1/Dense_0/bias");
+  const int K5r = M + 1;
+  Mat B5((size_t)K5r * L, 0.0);
+  for (int k = 0; k < M; ++k)
+    for (int n = 0; n < L; ++n) B5[(size_t)k * L + n] = Wf1[(size_t)k * out_dim + n];
+  for (int n = 0; n < L; ++n) B5[(size_t)M * L + n] = bf1[n];
+
+  tc.K1 = 48; tc.K5 = 48;
+  tc.K3 = round_up(K3r, 16);
+  tc.N5 = round_up(L, 16) <= 32 ? 32 : 64;
+  std::vector<uint8_t> img;
+  tc.off_b1 = append_operand(img, B1, K1r, R, R, tc.K1);
+  tc.off_b2t = append_operand(img, Wout0, R, M, M, R);
+  tc.off_b2a = append_operand(img, B2a, K1r, M, M, tc.K1);
+  tc.off_b3 = append_operand(img, B3, K3r, R, R, tc.K3);
+  tc.off_b4t = append_operand(img, Wout1, R, M, M, R);
+  tc.off_b4a = append_operand(img, B4a, K3r, M, M, tc.K3);
+  tc.off_b5 = append_operand(img, B5, K5r, L, tc.N5, tc.K5);
+  tc.wimg_bytes = (uint32_t)img.size();
+  int err;
+  if ((err = tc_upload(arena, img.data(), img.size(), (const void**)&tc.wimg))) return err;
+
+  auto cp = [&](float* dst, const std::string& name, int n) { const float* s = P(pm, name); for (int i = 0; i < n; ++i) dst[i] = s[i]; };
+  cp(tc.ln.g1, b0 + "/LayerNorm_0/scale", R); cp(tc.ln.b1, b0 + "/LayerNorm_0/bias", R);
+  cp(tc.ln.g2, b0 + "/LayerNorm_1/scale", M); cp(tc.ln.b2, b0 + "/LayerNorm_1/bias", M);
+  cp(tc.ln.g3, b1 + "/LayerNorm_0/scale", R); cp(tc.ln.b3, b1 + "/LayerNorm_0/bias", R);
+  cp(tc.ln.g4, b1 + "/LayerNorm_1/scale", M); cp(tc.ln.b4, b1 + "/LayerNorm_1/bias", M);
+
+  // per-sample tables from the fp32 kv tokens (already on the device, computed by k_sample_tables)
+  std::vector<float> kv((size_t)S * E);
+  if (cudaMemcpy(kv.data(), tc.kvtok, kv.size() * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess) {
+    g_tc_error = "cudaMemcpy of kv tokens failed";
+    return MRVI_ERR_CUDA;
+  }
+  std::vector<float> kvl((size_t)S * E), kvref((size_t)S * 2);
+  for (int s = 0; s < S; ++s) {
+    float mx = -INFINITY, mn = INFINITY;
+    for (int j = 0; j < E; ++j) {
+      const float v = kv[(size_t)s * E + j] * kLog2e;
+      kvl[(size_t)s * E + j] = v;
+      mx = std::max(mx, v); mn = std::min(mn, v);
+    }
+    kvref[s * 2] = mx; kvref[s * 2 + 1] = mn;
+  }
+  if ((err = tc_upload(arena, kvl.data(), kvl.size() * sizeof(float), (const void**)&tc.kvl))) return err;
+  if ((err = tc_upload(arena, kvref.data(), kvref.size() * sizeof(float), (const void**)&tc.kvref))) return err;
+
+  tc.sm_count = sm_count;
+  tc.smem_bytes = tc_smem_map(tc.wimg_bytes, tc.K1, tc.K3).total + 1024;
+  if (tc.smem_bytes > 227 * 1024) {
+    g_tc_error = "tensor-core chain needs more than 227 KiB of shared memory";
+    return MRVI_ERR_UNSUPPORTED;
+  }
+  if (cudaFuncSetAttribute(k_chain_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc.smem_bytes) != cudaSuccess) {
+    g_tc_error = "cudaFuncSetAttribute(k_chain_tc) failed";
+    return MRVI_ERR_CUDA;
+  }
+  tc.ready = true;
+  return 0;
+}
+
+// launches the chain for n cells; per-cell inputs (q_tok, u_ln, zbase) must already be in cb
+inline int tc_launch_qz(const TcNet& tc, const NetW& net, int64_t n, const CellBuf& cb, float* z, cudaStream_t st) {
+  const int S = net.S;
+  int cpt = 1, tpc = 1;
+  int64_t n_tiles;
+  if (S <= kTcRows) { cpt = kTcRows / S; n_tiles = (n + cpt - 1) / cpt; }
+  else { tpc = (S + kTcRows - 1) / kTcRows; n_tiles = n * tpc; }
+  const int grid = (int)std::min<int64_t>(n_tiles, tc.sm_count);
+  if (grid == 0) return 0;
+  k_chain_tc<<<grid, kTcThreads, tc.smem_bytes, st>>>(tc, cb, n, S, net.L, net.Lq, z, n_tiles, cpt, tpc);
+  return 0;
 }
 
 }  // namespace mrvi

@@ -133,3 +133,47 @@ def test_drop_in_api_matches_reference_layout(built_library):
     z = model.get_local_sample_representation()
     assert z.shape == (400, 15, 10)
     model.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# tensor-core mode (tcgen05): parity bar 1e-3 normwise; and agreement with the numpy emulation of the
+# exact TC arithmetic (oracle/tc_emulation.py), which isolates kernel bugs from rounding effects.
+TC_CASES = [
+    ("S32", dict(n_input=200, n_sample=32), 300),
+    ("S128", dict(n_input=200, n_sample=128), 150),
+    ("S15_iso_L10", dict(n_input=100, n_sample=15, n_latent=10, n_latent_u=10), 200),
+    ("S4", dict(n_input=100, n_sample=4), 400),
+    ("S256_L50", dict(n_input=64, n_sample=256, n_latent=50), 12),
+    ("S48_usemapF", dict(n_input=64, n_sample=48, use_map=False), 77),
+    ("S200_Lu5", dict(n_input=64, n_sample=200, n_latent=10, n_latent_u=5), 9),
+]
+
+
+@pytest.mark.parametrize("name,dk,n", TC_CASES, ids=[c[0] for c in TC_CASES])
+def test_tc_matches_oracle(built_library, name, dk, n):
+    from oracle import tc_emulation as tce
+
+    dims = mrvi_b200.MrviDims(**dk)
+    params, h = _model(dims, seed=4, precision="tc")
+    X, sid = _inputs(n, dims.n_input, dims.n_sample, seed=6)
+    codes = [np.random.default_rng(3).integers(0, 4, size=n).astype(np.int32)]
+    res = h.run_host(X, sid, codes, [4], keep_cell=True, want_z=True, want_u=True)
+    p64 = orc.cast_params(params, np.float64)
+    uref = orc.encoder_xu_mean(p64, X.astype(np.float64), sid)
+    zref = orc.counterfactual_z(params, X, sid, dtype=np.float64)
+    dref = orc.pairwise_distances(zref)
+    L = dims.n_latent
+    zb = orc.dense(uref, p64, "qz/Dense_0") if dims.n_latent_u is not None else uref
+    # (a) kernel == emulation of its own arithmetic (f16 weights, split activations ~ exact)
+    emu = tce.tc_chain_residual(params, res["u"].astype(np.float64), fmt_act=None, fmt_w="f16")[..., :L]
+    got_res = res["z"].astype(np.float64) - zb[:, None, :]
+    assert _relerr(got_res, emu) < 5e-5, "kernel deviates from the emulated tensor-core arithmetic"
+    # (b) parity with the oracle
+    scale = dref.max(axis=(1, 2), keepdims=True)
+    err = float((np.abs(res["cell"] - dref) / scale).max())
+    assert err < TOL["tc"], err
+    assert np.all(np.diagonal(res["cell"], axis1=1, axis2=2) == 0)
+    assert np.array_equal(res["group_counts"][0], np.bincount(codes[0], minlength=4))
+    ref_sum = np.stack([dref[codes[0] == g].sum(0) for g in range(4)])
+    assert _relerr(res["group_sums"][0], ref_sum) < TOL["tc"]
+    h.close()
