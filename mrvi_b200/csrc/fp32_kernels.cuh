@@ -165,7 +165,7 @@ struct EncSmem {
 __global__ void __launch_bounds__(kThreads)
 k_encoder_fp32(const __grid_constant__ NetW net, const float* __restrict__ X, int64_t ldx,
                const int32_t* __restrict__ sample_idx, int64_t n_cells, CellBuf cb, int ldh,
-               int ldhid, int x_vec_ok) {
+               int ldhid, int x_vec_ok, const float* __restrict__ h1_in) {
   extern __shared__ __align__(16) float smem[];
   const int H = net.H;
   float* xs = smem;                       // [kTM][36]
@@ -189,7 +189,16 @@ k_encoder_fp32(const __grid_constant__ NetW net, const float* __restrict__ X, in
   // ---- Dense_0 over K = G in chunks of 32, accumulators in registers (8 rows x 4 cols / thread,
   //      column passes of 128)
   const int Hld = net.enc0.ld;  // roundup(H,4)
-  for (int c0 = 0; c0 < Hld; c0 += 128) {
+  if (h1_in != nullptr) {
+    // Dense_0 (+ bias) was computed by the tensor-core GEMM (k_enc_gemm_tc): load this tile's rows
+    for (int idx = tid; idx < kTM * (Hld / 4); idx += kThreads) {
+      const int r = idx / (Hld / 4), c4 = idx % (Hld / 4);
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < TM) v = __ldg(reinterpret_cast<const float4*>(h1_in + (cell0 + r) * Hld) + c4);
+      *reinterpret_cast<float4*>(ha + (size_t)r * ldh + 4 * c4) = v;
+    }
+  }
+  for (int c0 = 0; h1_in == nullptr && c0 < Hld; c0 += 128) {
     const int ncols = min(128, Hld - c0);
     const int ncg = ncols >> 2;
     const int nrg = kThreads / ncg;

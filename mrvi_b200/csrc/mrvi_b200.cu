@@ -106,6 +106,8 @@ struct MrviHandle {
   DeviceArena arena;
   NetW net{};
   TcNet tc{};
+  EncTc enc_tc{};
+  float* h1buf = nullptr;  // [chunk][128] Dense_0 output of the tensor-core encoder GEMM
   // workspace for one chunk of cells
   int64_t chunk_cells = 0;
   CellBuf cb{};
@@ -328,7 +330,13 @@ static int setup_workspace(MrviHandle* h) {
 static int launch_encoder(MrviHandle* h, const float* X, int64_t ldx, const int32_t* sid, int64_t n, cudaStream_t st) {
   const int grid = (int)((n + kTM - 1) / kTM);
   const int vec_ok = ((ldx % 4) == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
-  k_encoder_fp32<<<grid, kThreads, h->enc_smem, st>>>(h->net, X, ldx, sid, n, h->cb, h->enc_ldh, h->enc_ldhid, vec_ok);
+  const float* h1 = nullptr;
+  if (h->precision == MRVI_PRECISION_TC && h->enc_tc.ready) {
+    enc_tc_launch(h->enc_tc, X, ldx, n, h->net.G, h->h1buf, st);
+    LAUNCH_CHECK();
+    h1 = h->h1buf;
+  }
+  k_encoder_fp32<<<grid, kThreads, h->enc_smem, st>>>(h->net, X, ldx, sid, n, h->cb, h->enc_ldh, h->enc_ldhid, vec_ok, h1);
   LAUNCH_CHECK();
   return 0;
 }
@@ -521,6 +529,8 @@ int mrvi_create(const MrviDims* dims, int32_t n_params, const char* const* names
   if ((err = setup_workspace(h.get()))) return err;
   if (precision == MRVI_PRECISION_TC) {
     if ((err = tc_build(h->tc, h->net, h->dims, pt.m, h->arena, h->sm_count))) return fail(err, "%s", tc_error());
+    if ((err = enc_tc_build(h->enc_tc, h->net, pt.m, h->arena))) return fail(err, "%s", tc_error());
+    if (h->enc_tc.ready) CUDA_TRY(h->arena.alloc((void**)&h->h1buf, (size_t)h->chunk_cells * 128 * sizeof(float)));
   }
   CUDA_TRY(cudaEventCreate(&h->ev_call[0]));
   CUDA_TRY(cudaEventCreate(&h->ev_call[1]));

@@ -682,4 +682,221 @@ inline int tc_launch_qz(const TcNet& tc, const NetW& net, int64_t n, const CellB
   return 0;
 }
 
+
+// ==========================================================================================
+// Encoder first layer on the tensor cores:  H1[n x H] = log1p(X)[n x G] . W0[G x H] + b0   (H = 128)
+// (reference _module.py:189-190, the only large-K contraction of the path; HBM-bound on reading X).
+//
+// Warp-specialised, 3-stage mbarrier pipeline, one CTA = 128 cells:
+//   warps 0-3  producers: coalesced LDG.128 of X, log1p (MUFU.LG2), (hi, lo) f16 split, conflict-free
+//              16-byte shared stores in the K-major UMMA layout; afterwards the epilogue (TMEM -> H1)
+//   warp 4     one elected thread issues tcgen05.mma:  per 16-wide K slice  Ah.Wh + Al.Wh + Ah.Wl
+//              (f16 operands, fp32 accumulate: ~21 significant bits, see oracle/tc_emulation.py)
+//   warp 5     one elected thread streams the pre-packed W0 image (hi|lo, 16 KiB per 32-wide K block)
+//              with cp.async.bulk (TMA) into the stage's B buffer
+// W0 is scaled by 2^8 before the split so that the lo halves stay in the f16 normal range; the
+// epilogue multiplies by 2^-8 (exact).
+// ==========================================================================================
+constexpr int kEncBK = 32;
+constexpr int kEncStages = 3;
+constexpr int kEncALbo = 129 * 16;                       // 16-byte row pad per K-chunk plane: conflict-free stores
+constexpr int kEncAHalf = 4 * kEncALbo;                  // one of (hi, lo): 4 K-chunks
+constexpr int kEncBBytes = 2 * 4 * 128 * 16;             // hi | lo, 4 K-chunks x 128 n x 16 B
+constexpr int kEncStageBytes = ((2 * kEncAHalf + kEncBBytes + 1023) / 1024) * 1024;
+constexpr int kEncThreads = 192;
+constexpr float kEncWScale = 256.0f;
+
+struct EncTc {
+  const uint8_t* w0img = nullptr;  // [n_kblocks][kEncBBytes]
+  const float* b0 = nullptr;       // [128]
+  int n_kblocks = 0;
+  size_t smem_bytes = 0;
+  bool ready = false;
+};
+
+__device__ __forceinline__ float log1p_fast(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(1.0f + x));
+  return y * 0.6931471805599453f;
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(kEncThreads, 2)
+k_enc_gemm_tc(const float* __restrict__ X, int64_t ldx, int64_t n_cells, int G, EncTc enc, float* __restrict__ H1,
+              int x_vec_ok) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kEncStages * kEncStageBytes);
+  uint64_t* full = bars;                    // [stages] producers (128) + B expect_tx (1)
+  uint64_t* empty = bars + kEncStages;      // [stages] tcgen05.commit
+  uint64_t* acc_bar = bars + 2 * kEncStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kEncStages + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nkb = enc.n_kblocks;
+  const int64_t cell0 = (int64_t)blockIdx.x * 128;
+
+  if (tid == 0) {
+    for (int s = 0; s < kEncStages; ++s) { mbar_init(full + s, 129); mbar_init(empty + s, 1); }
+    mbar_init(acc_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 4) tmem_alloc(tmem_slot, 128);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    // ------------------------------------------------------------ producers
+    const int rsub = lane >> 2, chunk = lane & 3;
+    float4 cur[8], nxt[8];
+    auto load = [&](int kb, float4 (&dst)[8]) {
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        const int row = warp * 32 + p * 8 + rsub;
+        const int64_t cell = cell0 + row;
+        const int k = kb * kEncBK + chunk * 8;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+        if (cell < n_cells) {
+          const float* src = X + cell * ldx + k;
+          if (x_vec_ok && k + 8 <= G) {
+            a = __ldg(reinterpret_cast<const float4*>(src));
+            b = __ldg(reinterpret_cast<const float4*>(src) + 1);
+          } else {
+            float t[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) t[j] = (k + j < G) ? __ldg(src + j) : 0.f;
+            a = make_float4(t[0], t[1], t[2], t[3]);
+            b = make_float4(t[4], t[5], t[6], t[7]);
+          }
+        }
+        dst[2 * p] = a;
+        dst[2 * p + 1] = b;
+      }
+    };
+    load(0, cur);
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % kEncStages;
+      if (kb + 1 < nkb) load(kb + 1, nxt);
+      if (kb >= kEncStages) mbar_wait(empty + s, ((kb / kEncStages) - 1) & 1);
+      uint8_t* stage = smem + s * kEncStageBytes;
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        const int row = warp * 32 + p * 8 + rsub;
+        const float4 a = cur[2 * p], b = cur[2 * p + 1];
+        uint32_t h[4], l[4];
+        split2(log1p_fast(a.x), log1p_fast(a.y), h[0], l[0]);
+        split2(log1p_fast(a.z), log1p_fast(a.w), h[1], l[1]);
+        split2(log1p_fast(b.x), log1p_fast(b.y), h[2], l[2]);
+        split2(log1p_fast(b.z), log1p_fast(b.w), h[3], l[3]);
+        *reinterpret_cast<uint4*>(stage + chunk * kEncALbo + row * 16) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4*>(stage + kEncAHalf + chunk * kEncALbo + row * 16) = make_uint4(l[0], l[1], l[2], l[3]);
+      }
+      fence_proxy_async();
+      mbar_arrive(full + s);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) cur[j] = nxt[j];
+    }
+    // ------------------------------------------------------------ epilogue: TMEM -> H1 (+ bias, unscale)
+    mbar_wait(acc_bar, 0);
+    tc_fence_after();
+    const int row = tid;  // == TMEM lane
+    const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const int64_t cell = cell0 + row;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      float v[32];
+      tmem_ld32(t_lane + c * 32, v);
+      tmem_ld_wait();
+      if (cell < n_cells) {
+        float4* dst = reinterpret_cast<float4*>(H1 + cell * 128 + c * 32);
+        const float4* bb = reinterpret_cast<const float4*>(enc.b0 + c * 32);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 b4 = __ldg(bb + q);
+          dst[q] = make_float4(fmaf(v[4 * q], 1.0f / kEncWScale, b4.x), fmaf(v[4 * q + 1], 1.0f / kEncWScale, b4.y),
+                               fmaf(v[4 * q + 2], 1.0f / kEncWScale, b4.z), fmaf(v[4 * q + 3], 1.0f / kEncWScale, b4.w));
+        }
+      }
+    }
+    tc_fence_before();
+  } else if (warp == 4) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_f16(128);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % kEncStages;
+        mbar_wait(full + s, (kb / kEncStages) & 1);
+        tc_fence_after();
+        const uint32_t a_h = smem_u32(smem + s * kEncStageBytes), a_l = a_h + kEncAHalf;
+        const uint32_t b_h = a_h + 2 * kEncAHalf, b_l = b_h + 4 * 2048;
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+          const uint64_t ah = umma_desc(a_h + ks * 2 * kEncALbo, kEncALbo, 128);
+          const uint64_t al = umma_desc(a_l + ks * 2 * kEncALbo, kEncALbo, 128);
+          const uint64_t bh = umma_desc(b_h + ks * 2 * 2048, 2048, 128);
+          const uint64_t bl = umma_desc(b_l + ks * 2 * 2048, 2048, 128);
+          umma_f16(tmem_base, ah, bh, idesc, (kb | ks) ? 1u : 0u);
+          umma_f16(tmem_base, al, bh, idesc, 1u);
+          umma_f16(tmem_base, ah, bl, idesc, 1u);
+        }
+        umma_commit(empty + s);
+      }
+      umma_commit(acc_bar);
+    }
+  } else {
+    // ------------------------------------------------------------ W0 loader (TMA bulk copies)
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % kEncStages;
+        if (kb >= kEncStages) mbar_wait(empty + s, ((kb / kEncStages) - 1) & 1);
+        mbar_expect_tx(full + s, kEncBBytes);
+        bulk_g2s(smem + s * kEncStageBytes + 2 * kEncAHalf, enc.w0img + (size_t)kb * kEncBBytes, kEncBBytes, full + s);
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem_base, 128);
+}
+
+// pack W0 [G x 128] (+ scale 2^8) into per-K-block (hi | lo) canonical f16 images
+inline int enc_tc_build(EncTc& enc, const NetW& net, const tc_detail::PMap& pm, DeviceArena& arena) {
+  if (net.H != 128) return 0;  // fp32 encoder is used for other widths
+  const int G = net.G;
+  const float* W = tc_detail::P(pm, "qu/Dense_0/kernel");
+  const int nkb = (G + kEncBK - 1) / kEncBK;
+  std::vector<uint8_t> img((size_t)nkb * kEncBBytes, 0);
+  for (int k = 0; k < G; ++k) {
+    const int kb = k / kEncBK, kk = k % kEncBK;
+    __half* hi = reinterpret_cast<__half*>(img.data() + (size_t)kb * kEncBBytes);
+    __half* lo = hi + 4 * 128 * 8;
+    for (int n = 0; n < 128; ++n) {
+      const float w = W[(size_t)k * 128 + n] * kEncWScale;
+      const __half h = __float2half_rn(w);
+      const size_t e = (size_t)(kk / 8) * (128 * 8) + (size_t)n * 8 + (kk % 8);
+      hi[e] = h;
+      lo[e] = __float2half_rn(w - __half2float(h));
+    }
+  }
+  int err;
+  if ((err = tc_upload(arena, img.data(), img.size(), (const void**)&enc.w0img))) return err;
+  enc.b0 = net.enc0.b;
+  enc.n_kblocks = nkb;
+  enc.smem_bytes = (size_t)kEncStages * kEncStageBytes + 256 + 1024;
+  if (cudaFuncSetAttribute(k_enc_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)enc.smem_bytes) != cudaSuccess) {
+    g_tc_error = "cudaFuncSetAttribute(k_enc_gemm_tc) failed";
+    return MRVI_ERR_CUDA;
+  }
+  enc.ready = true;
+  return 0;
+}
+
+inline void enc_tc_launch(const EncTc& enc, const float* X, int64_t ldx, int64_t n, int G, float* H1, cudaStream_t st) {
+  const int grid = (int)((n + 127) / 128);
+  const int vec_ok = ((ldx % 4) == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
+  k_enc_gemm_tc<<<grid, kEncThreads, enc.smem_bytes, st>>>(X, ldx, n, G, enc, H1, vec_ok);
+}
+
 }  // namespace mrvi
