@@ -153,6 +153,28 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
       : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// registers -> 32 lanes x 32 consecutive 32-bit columns
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+      "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// A operand from TMEM (lane = row, 32-bit column = two consecutive K values), B from shared memory
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
@@ -199,7 +221,6 @@ struct TcSmemMap {
   uint32_t w;        // weight image
   uint32_t a1h, a1l; // [128 x K1]   (also A5 = [t4 | 1])
   uint32_t a3h, a3l; // [128 x K3]
-  uint32_t th, tl;   // [128 x 128]
   uint32_t bars;     // 2 mbarriers + tmem slot
   uint32_t total;
 };
@@ -210,7 +231,6 @@ __host__ __device__ inline TcSmemMap tc_smem_map(uint32_t wimg_bytes, int K1, in
   m.w = take(wimg_bytes);
   m.a1h = take(128 * K1 * 2); m.a1l = take(128 * K1 * 2);
   m.a3h = take(128 * K3 * 2); m.a3l = take(128 * K3 * 2);
-  m.th = take(128 * 128 * 2); m.tl = take(128 * 128 * 2);
   m.bars = take(64);
   m.total = o;
   return m;
@@ -244,6 +264,46 @@ __device__ __forceinline__ void ln_gelu_store(float (&v)[NCH * 32], const float*
   }
 }
 
+// LayerNorm + gelu of the 128 accumulator columns of this row, written back IN PLACE to TMEM as the
+// A operand of the next GEMM: f16 pairs, hi copy in columns [0, 64), lo copy in columns [64, 128).
+// (The row's accumulators are all in registers before the first store, and a lane is private to
+// its thread, so overwriting is safe.)
+__device__ __forceinline__ void ln_gelu_store_tmem(float (&v)[128], const float* __restrict__ g,
+                                                   const float* __restrict__ b, uint32_t t_lane) {
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < 128; ++i) { s1 += v[i]; s2 = fmaf(v[i], v[i], s2); }
+  const float mean = s1 * (1.0f / 128);
+  const float var = fmaxf(fmaf(s2, 1.0f / 128, -mean * mean), 0.f);
+  const float rstd = rsqrt_approx(var + kLnEps);
+  const float nb = -mean * rstd;
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {  // 64 values -> 32 hi words + 32 lo words
+    uint32_t h[32], l[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int i0 = c * 64 + 2 * j, i1 = i0 + 1;
+      const float y0 = gelu_fast(fmaf(fmaf(v[i0], rstd, nb), g[i0], b[i0]));
+      const float y1 = gelu_fast(fmaf(fmaf(v[i1], rstd, nb), g[i1], b[i1]));
+      split2(y0, y1, h[j], l[j]);
+    }
+    tmem_st32(t_lane + c * 32, h);
+    tmem_st32(t_lane + 64 + c * 32, l);
+  }
+  tmem_st_wait();
+}
+
+// [128 x 128] (A in TMEM: hi at a_tmem, lo at a_tmem + 64 columns) x [128 x N]
+__device__ __forceinline__ void issue_gemm_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t b, int N, uint32_t idesc) {
+  const uint32_t b_lbo = (uint32_t)N * 16;
+#pragma unroll
+  for (int ks = 0; ks < 8; ++ks) {
+    const uint64_t bd = umma_desc(b + ks * 2 * b_lbo, b_lbo, 128);
+    umma_f16_ts(d_tmem, a_tmem + ks * 8, bd, idesc, ks == 0 ? 0u : 1u);
+    umma_f16_ts(d_tmem, a_tmem + 64 + ks * 8, bd, idesc, 1u);
+  }
+}
+
 // issue the MMAs of one [128 x K] x [K x N] product for both the hi and lo copy of A
 __device__ __forceinline__ void issue_gemm(uint32_t d_tmem, uint32_t a_h, uint32_t a_l, uint32_t b, int K, int N,
                                            uint32_t idesc, bool first_clears) {
@@ -258,7 +318,7 @@ __device__ __forceinline__ void issue_gemm(uint32_t d_tmem, uint32_t a_h, uint32
 // ------------------------------------------------------------------------------------------
 // the chain kernel: persistent over 128-row tiles
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kTcThreads, 1)
+__global__ void __launch_bounds__(kTcThreads, 2)
 k_chain_tc(const __grid_constant__ TcNet tc, CellBuf cb, int64_t n_cells, int S, int L, int Lq,
            float* __restrict__ z_out, int64_t n_tiles, int cells_per_tile, int tiles_per_cell) {
   extern __shared__ uint8_t smem_raw[];
@@ -274,7 +334,7 @@ k_chain_tc(const __grid_constant__ TcNet tc, CellBuf cb, int64_t n_cells, int S,
     mbar_init(bar_mma, 1);
     fence_mbar_init();
   }
-  if (warp == 0) tmem_alloc(tmem_slot, 128);
+  if (warp == 0) tmem_alloc(tmem_slot, 256);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -286,13 +346,10 @@ k_chain_tc(const __grid_constant__ TcNet tc, CellBuf cb, int64_t n_cells, int S,
   const uint32_t s_w = smem_u32(smem + sm.w);
   const uint32_t s_a1h = smem_u32(smem + sm.a1h), s_a1l = smem_u32(smem + sm.a1l);
   const uint32_t s_a3h = smem_u32(smem + sm.a3h), s_a3l = smem_u32(smem + sm.a3l);
-  const uint32_t s_th = smem_u32(smem + sm.th), s_tl = smem_u32(smem + sm.tl);
   uint8_t* row_a1h = smem + sm.a1h + tid * 16;
   uint8_t* row_a1l = smem + sm.a1l + tid * 16;
   uint8_t* row_a3h = smem + sm.a3h + tid * 16;
   uint8_t* row_a3l = smem + sm.a3l + tid * 16;
-  uint8_t* row_th = smem + sm.th + tid * 16;
-  uint8_t* row_tl = smem + sm.tl + tid * 16;
   const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16);  // this warp's TMEM lane quarter
   const uint32_t idesc128 = umma_idesc_f16(128), idesc32 = umma_idesc_f16(32), idescN5 = umma_idesc_f16(tc.N5);
   uint32_t phase = 0;
@@ -397,24 +454,23 @@ k_chain_tc(const __grid_constant__ TcNet tc, CellBuf cb, int64_t n_cells, int S,
       float v[128];
       tmem_ld32(t_lane + 0, v); tmem_ld32(t_lane + 32, v + 32); tmem_ld32(t_lane + 64, v + 64); tmem_ld32(t_lane + 96, v + 96);
       tmem_ld_wait();
-      ln_gelu_store<4>(v, tc.ln.g1, tc.ln.b1, row_th, row_tl);
+      ln_gelu_store_tmem(v, tc.ln.g1, tc.ln.b1, t_lane);
     }
     tc_fence_before();
-    fence_proxy_async();
     __syncthreads();
 
     // ---- GEMM2: D2 = T x B2t + A1 x B2a
     if (tid == 0) {
       tc_fence_after();
-      issue_gemm(tmem_base, s_th, s_tl, s_w + tc.off_b2t, 128, 32, idesc32, true);
-      issue_gemm(tmem_base, s_a1h, s_a1l, s_w + tc.off_b2a, tc.K1, 32, idesc32, false);
+      issue_gemm_ts(tmem_base + 128, tmem_base, s_w + tc.off_b2t, 32, idesc32);
+      issue_gemm(tmem_base + 128, s_a1h, s_a1l, s_w + tc.off_b2a, tc.K1, 32, idesc32, false);
       umma_commit(bar_mma);
     }
     mbar_wait(bar_mma, phase); phase ^= 1;
     tc_fence_after();
     {
       float v[32];
-      tmem_ld32(t_lane, v);
+      tmem_ld32(t_lane + 128, v);
       tmem_ld_wait();
       ln_gelu_store<1>(v, tc.ln.g2, tc.ln.b2, row_a3h, row_a3l);
     }
@@ -434,24 +490,23 @@ k_chain_tc(const __grid_constant__ TcNet tc, CellBuf cb, int64_t n_cells, int S,
       float v[128];
       tmem_ld32(t_lane + 0, v); tmem_ld32(t_lane + 32, v + 32); tmem_ld32(t_lane + 64, v + 64); tmem_ld32(t_lane + 96, v + 96);
       tmem_ld_wait();
-      ln_gelu_store<4>(v, tc.ln.g3, tc.ln.b3, row_th, row_tl);
+      ln_gelu_store_tmem(v, tc.ln.g3, tc.ln.b3, t_lane);
     }
     tc_fence_before();
-    fence_proxy_async();
     __syncthreads();
 
     // ---- GEMM4: D4 = T x B4t + A3 x B4a
     if (tid == 0) {
       tc_fence_after();
-      issue_gemm(tmem_base, s_th, s_tl, s_w + tc.off_b4t, 128, 32, idesc32, true);
-      issue_gemm(tmem_base, s_a3h, s_a3l, s_w + tc.off_b4a, tc.K3, 32, idesc32, false);
+      issue_gemm_ts(tmem_base + 128, tmem_base, s_w + tc.off_b4t, 32, idesc32);
+      issue_gemm(tmem_base + 128, s_a3h, s_a3l, s_w + tc.off_b4a, tc.K3, 32, idesc32, false);
       umma_commit(bar_mma);
     }
     mbar_wait(bar_mma, phase); phase ^= 1;
     tc_fence_after();
     {
       float v[32];
-      tmem_ld32(t_lane, v);
+      tmem_ld32(t_lane + 128, v);
       tmem_ld_wait();
       // A5 = [t4 | 1 | 0] reuses the A1 buffers (GEMM2 was their last reader); the one / zero columns are still in place
       ln_gelu_store<1>(v, tc.ln.g4, tc.ln.b4, row_a1h, row_a1l);
@@ -486,7 +541,7 @@ k_chain_tc(const __grid_constant__ TcNet tc, CellBuf cb, int64_t n_cells, int S,
   }
 
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, 128);
+  if (warp == 0) tmem_dealloc(tmem_base, 256);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -676,7 +731,7 @@ inline int tc_launch_qz(const TcNet& tc, const NetW& net, int64_t n, const CellB
   int64_t n_tiles;
   if (S <= kTcRows) { cpt = kTcRows / S; n_tiles = (n + cpt - 1) / cpt; }
   else { tpc = (S + kTcRows - 1) / kTcRows; n_tiles = n * tpc; }
-  const int grid = (int)std::min<int64_t>(n_tiles, tc.sm_count);
+  const int grid = (int)std::min<int64_t>(n_tiles, 2 * (int64_t)tc.sm_count);
   if (grid == 0) return 0;
   k_chain_tc<<<grid, kTcThreads, tc.smem_bytes, st>>>(tc, cb, n, S, net.L, net.Lq, z, n_tiles, cpt, tpc);
   return 0;
