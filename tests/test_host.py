@@ -1,0 +1,139 @@
+"""CPU tests of the host-side logic: parameter schema, reduction planner, output containers, the
+C-ABI library (loads, exports every symbol of include/mrvi_b200.h, fails loudly without a GPU)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pandas as pd
+import pytest
+
+import mrvi_b200
+from mrvi_b200 import _capi, _params
+from mrvi_b200._types import MrVIReduction
+from mrvi_b200._utils import _parse_local_statistics_requirements
+from mrvi_b200._xr import _LiteDataArray, _LiteDataset
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_param_schema_roundtrip(tmp_path):
+    dims = mrvi_b200.MrviDims(n_input=37, n_sample=5, n_latent=12, n_latent_u=4, qz_n_layers=2, use_map=False)
+    p = mrvi_b200.init_params(dims, seed=3)
+    assert list(p) == list(mrvi_b200.expected_param_shapes(dims))
+    assert mrvi_b200.infer_dims(p) == dims
+    nested = {}
+    for k, v in p.items():
+        node = nested
+        parts = k.split("/")
+        for part in parts[:-1]:
+            node = node.setdefault(part, {})
+        node[parts[-1]] = v
+    nested["px"] = {"Dense_0": {"kernel": np.zeros((3, 3))}}  # decoder params are ignored by the path
+    flat = mrvi_b200.flatten_params({"params": nested})
+    assert all(np.array_equal(flat[k], p[k]) for k in p)
+    mrvi_b200.save_params(str(tmp_path / "m.npz"), p, dims)
+    p2, d2 = mrvi_b200.load_params(str(tmp_path / "m.npz"))
+    assert d2 == dims and all(np.array_equal(p2[k], p[k]) for k in p)
+
+
+def test_isomorphic_dims_and_validation():
+    dims = mrvi_b200.MrviDims(n_input=20, n_sample=3, n_latent=10, n_latent_u=10)
+    assert dims.n_latent_u is None and dims.n_latent_q == 10
+    p = mrvi_b200.init_params(dims)
+    assert "qz/Dense_0/kernel" not in p
+    bad = dict(p)
+    bad["qz/u_ln/scale"] = np.ones(3, np.float32)
+    with pytest.raises(ValueError, match="shape"):
+        mrvi_b200.validate_params(bad, dims)
+    del bad["qz/u_ln/scale"]
+    with pytest.raises(KeyError, match="missing parameter"):
+        mrvi_b200.validate_params(bad, dims)
+
+
+def test_requirements_parser_truth_table():
+    f = lambda x: x
+    r = _parse_local_statistics_requirements([
+        MrVIReduction("cell", "mean_distances", f), MrVIReduction("ct", "mean_distances", f, "ct")])
+    assert r.needs_mean_representations and r.needs_mean_distances
+    assert not (r.needs_sampled_representations or r.needs_sampled_distances or r.needs_normalized_distances)
+    assert [x.name for x in r.ungrouped_reductions] == ["cell"] and [x.name for x in r.grouped_reductions] == ["ct"]
+    r = _parse_local_statistics_requirements([MrVIReduction("n", "normalized_distances", f)])
+    assert r.needs_sampled_representations and r.needs_normalized_distances and not r.needs_sampled_distances
+    r = _parse_local_statistics_requirements([MrVIReduction("s", "sampled_distances", f)])
+    assert r.needs_sampled_representations and r.needs_sampled_distances
+    with pytest.raises(ValueError, match="Unknown reduction input"):
+        _parse_local_statistics_requirements([MrVIReduction("x", "nope", f)])
+
+
+def test_lite_xarray_layout():
+    d = _LiteDataArray(np.arange(24.0).reshape(2, 3, 4), dims=["cell_name", "sample_x", "sample_y"],
+                       coords={"cell_name": np.array(["a", "b"]), "sample_x": np.arange(3), "sample_y": np.arange(4)},
+                       name="sample_distances")
+    assert d.shape == (2, 3, 4) and d[0].shape == (3, 4) and d[0].dims == ("sample_x", "sample_y")
+    assert np.array_equal(d.sel(cell_name=np.array(["b"])).values[0], d.values[1])
+    assert np.array_equal(d.sum("cell_name").values, d.values.sum(0))
+    assert np.array_equal(np.asarray(d[1].values.T), np.asarray(d[1].T.values))
+    ds = _LiteDataset({"cell": d})
+    assert "cell" in ds and ds.cell is d and list(ds.keys()) == ["cell"]
+    with pytest.raises(ValueError):
+        _LiteDataArray(np.zeros((2, 2)), dims=["a"])
+
+
+def test_synthetic_iid_recipe():
+    ad = mrvi_b200.synthetic_iid()
+    assert ad.X.shape == (400, 100) and ad.X.dtype == np.float32 and ad.n_obs == 400 and ad.n_vars == 100
+    assert (ad.X >= 0).all() and np.array_equal(ad.X, np.round(ad.X))
+    assert 0.2 < (ad.X == 0).mean() < 0.4  # Bernoulli(0.7) dropout mask
+    assert {"sample", "sample_str", "batch", "labels", "label_2"} <= set(ad.obs.columns)
+    assert isinstance(ad.obs["labels"].dtype, pd.CategoricalDtype)
+
+
+def test_capi_library_loads_and_exports_header_symbols(built_library):
+    header = open(os.path.join(ROOT, "include", "mrvi_b200.h")).read()
+    declared = set(re.findall(r"\b(mrvi_[a-z_0-9]+)\s*\(", header))
+    assert declared == set(_capi.EXPORTED_SYMBOLS)
+    for sym in declared:
+        assert hasattr(built_library, sym), sym
+    assert built_library.mrvi_abi_version() == _capi.ABI_VERSION
+    assert int(re.search(r"#define MRVI_B200_ABI_VERSION (\d+)", header).group(1)) == _capi.ABI_VERSION
+    assert built_library.mrvi_last_error() is not None
+    assert _capi.kernel_launch_count() >= 0
+
+
+def test_capi_argument_validation_without_gpu(built_library):
+    """Error paths that never reach a kernel: null / bad dims return a negative status with a message;
+    without a B200 mrvi_create fails loudly (no CPU fallback)."""
+    out = ctypes.c_void_p()
+    assert built_library.mrvi_create(None, 0, None, None, None, 0, 0, ctypes.byref(out)) == -1
+    assert b"null" in built_library.mrvi_last_error()
+    dims = mrvi_b200.MrviDims(n_input=10, n_sample=2)
+    p = mrvi_b200.init_params(dims)
+    import torch
+
+    if not torch.cuda.is_available():
+        with pytest.raises(_capi.MrviError) as e:
+            _capi.Handle(dims, p)
+        assert e.value.status in (-4, -3)
+    bad = mrvi_b200.MrviDims(n_input=10, n_sample=2, n_latent_sample=64)
+    with pytest.raises(_capi.MrviError) as e:
+        _capi.Handle(bad, mrvi_b200.init_params(bad))
+    assert e.value.status in (-5, -4)
+
+
+def test_model_fails_loudly_without_library(monkeypatch, tmp_path):
+    monkeypatch.setattr(_capi, "_lib", None)
+    monkeypatch.setattr(_capi, "library_path", lambda: str(tmp_path / "missing.so"))
+    ad = mrvi_b200.synthetic_iid(n_obs=20, n_vars=10, n_sample=2)
+    dims = mrvi_b200.MrviDims(n_input=10, n_sample=2)
+    with pytest.raises(_capi.MrviError, match="no CPU fallback"):
+        mrvi_b200.MrVI(ad, mrvi_b200.init_params(dims), sample_key="sample")
+
+
+def test_product_never_imports_oracle():
+    """The shipped package must not route through the oracle (parity contract)."""
+    pkg = os.path.join(ROOT, "mrvi_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), fn
