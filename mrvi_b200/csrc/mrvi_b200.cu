@@ -14,6 +14,7 @@
 #include "common.cuh"
 #include "fp32_kernels.cuh"
 #include "tc_kernels.cuh"
+#include "tc_fused.cuh"
 
 namespace mrvi {
 
@@ -450,6 +451,16 @@ static int run_device_impl(MrviHandle* h, int64_t n, const float* X, int64_t ldx
     float* z = z_out ? z_out + lo * net.S * net.L : h->zbuf;
     if ((err = launch_encoder(h, X + lo * ldx, ldx, sid + lo, m, st))) return err;
     if (time_stages) cudaEventRecord(e1, st);
+    if (h->precision == MRVI_PRECISION_TC && need_dist && h->tc.fused_smem_bytes && tc_fused_supported(h->tc, net.S, norm)) {
+      // fused: chain + distances + group sums in one kernel; z never leaves the SM unless asked for
+      GroupPlan gp;
+      if ((err = plan_groups(h, m, n_keys, codes, lo, n_groups, sums, &gp, st))) return err;
+      tc_launch_fused(h->tc, h->net, m, h->cb, z_out ? z : nullptr, cell_out ? cell_out + lo * net.S * net.S : nullptr, gp, st);
+      LAUNCH_CHECK();
+      if (time_stages) { cudaEventRecord(e2, st); cudaEventRecord(e3, st); }
+      if (u_out) CUDA_TRY(cudaMemcpyAsync(u_out + lo * net.Lq, h->cb.u, m * net.Lq * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      continue;
+    }
     if (need_z) {
       if (h->precision == MRVI_PRECISION_TC) {
         if ((err = tc_launch_qz(h->tc, h->net, m, h->cb, z, st))) return err;
@@ -531,6 +542,7 @@ int mrvi_create(const MrviDims* dims, int32_t n_params, const char* const* names
     if ((err = tc_build(h->tc, h->net, h->dims, pt.m, h->arena, h->sm_count))) return fail(err, "%s", tc_error());
     if ((err = enc_tc_build(h->enc_tc, h->net, pt.m, h->arena))) return fail(err, "%s", tc_error());
     if (h->enc_tc.ready) CUDA_TRY(h->arena.alloc((void**)&h->h1buf, (size_t)h->chunk_cells * 128 * sizeof(float)));
+    if ((err = tc_fused_prepare(h->tc, h->dims.n_latent))) return fail(err, "%s", tc_error());
   }
   CUDA_TRY(cudaEventCreate(&h->ev_call[0]));
   CUDA_TRY(cudaEventCreate(&h->ev_call[1]));

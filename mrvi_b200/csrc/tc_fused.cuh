@@ -1,0 +1,659 @@
+// Fused tensor-core kernel: q(z|u,s) chain + pairwise distances + group reduction, 4 <= S <= 128.
+//
+// The S x L tile of counterfactual representations of a cell never leaves the SM (north_star):
+// after GEMM5 the residuals (z_base cancels in every distance, reference _module.py:166-170, 331) are
+// centred per cell, split into (hi, lo) f16 and fed back to the tensor cores as BOTH operands of a
+// Gram product  G = Zh Zh^T + Zh Zl^T + Zl Zh^T  (fp32 accumulate in TMEM).  Row r of G gives
+// d[r][j] = sqrt(n_r + n_j - 2 G[r][j]) with fp32 norms; pairs whose squared distance is cancellation
+// dominated (< 2^-12 of n_r + n_j; the Gram error is ~2^-20 of it) are recomputed by direct
+// differences, the diagonal is forced to zero.  Rows are stored per cell (keep_cell) and/or added to
+// a [128 x 128] fp32 accumulator that lives in TMEM while consecutive tiles carry the same composite
+// group code (cells arrive sorted by it) and is flushed with float64 atomics when the code changes.
+//
+// Shape of the kernel (what the ncu profile of the first version asked for: its fully unrolled
+// 718 KB body spent 48 % of the samples in instruction-fetch stalls with 2 warps per scheduler):
+//   * one CTA per SM, 512 threads = 2 warpgroups x 256; each warpgroup owns one 128-row tile in
+//     flight (own A buffers, own 160 TMEM columns, own mbarrier); the 50 KB weight image and the TMEM
+//     accumulator are shared (the accumulator behind a shared-memory lock, taken once per tile);
+//   * TWO threads per row: thread (r, half) owns the column half `half` of every epilogue (the
+//     LayerNorm partial sums are exchanged through shared memory), so a tile's latency halves;
+//   * every epilogue is a loop over 32-column chunks (re-loaded from TMEM), which keeps the hot code
+//     in the instruction cache and the kernel at <= 128 registers.
+// The 128-wide hidden activations are written back in place into TMEM, per 32-column chunk as
+// [16 words hi | 16 words lo] (f16 pairs), and read by the next GEMM as its A operand (TS-mode MMA).
+#pragma once
+#include "tc_kernels.cuh"
+
+namespace mrvi {
+
+constexpr int kFusedThreads = 512;
+
+struct FusedSmemMap {
+  uint32_t w;            // weight image
+  uint32_t wg[2];        // per-warpgroup scratch: [a1h a1l a3h a3l] overlaid later by [zf | zh zl]
+  uint32_t off_a1l, off_a3h, off_a3l;   // offsets inside the scratch (a1h at 0)
+  uint32_t off_zf, off_zh, off_zl;      // overlay offsets
+  uint32_t mean[2];      // [32 cells][Kz] fp32
+  uint32_t nrm[2];       // [128] fp32
+  uint32_t xch[2];       // [2 halves][128] float2: partial row statistics
+  uint32_t lnv;          // TcLn copy (640 floats)
+  uint32_t ctrl;         // barriers, tmem slot, lock, run state
+  uint32_t total;
+  int zf_ld;             // row stride (floats) of the fp32 z tile, odd
+  int Kz;                // padded K of the Gram operands (32 or 64)
+};
+
+__host__ __device__ inline FusedSmemMap fused_smem_map(uint32_t wimg_bytes, int K1, int K3, int L) {
+  FusedSmemMap m;
+  uint32_t o = 0;
+  auto up = [](uint32_t b) { return (b + 1023u) & ~1023u; };
+  m.w = o; o += up(wimg_bytes);
+  const uint32_t a1 = up(128 * K1 * 2), a3 = up(128 * K3 * 2);
+  m.off_a1l = a1; m.off_a3h = 2 * a1; m.off_a3l = 2 * a1 + a3;
+  const uint32_t abytes = 2 * a1 + 2 * a3;
+  m.Kz = L <= 32 ? 32 : 64;
+  m.zf_ld = m.Kz + 1;
+  const uint32_t zf = up(128 * m.zf_ld * 4), zk = up(128 * m.Kz * 2);
+  m.off_zf = 0; m.off_zh = zf; m.off_zl = zf + zk;
+  const uint32_t scratch = abytes > zf + 2 * zk ? abytes : zf + 2 * zk;
+  m.wg[0] = o; o += scratch;
+  m.wg[1] = o; o += scratch;
+  m.mean[0] = o; o += up(32 * m.Kz * 4);
+  m.mean[1] = o; o += up(32 * m.Kz * 4);
+  m.nrm[0] = o; o += 512;
+  m.nrm[1] = o; o += 512;
+  m.xch[0] = o; o += 2048;
+  m.xch[1] = o; o += 2048;
+  m.lnv = o; o += up(sizeof(TcLn));
+  m.ctrl = o; o += 128;
+  m.total = o;
+  return m;
+}
+
+struct FusedCtrl {
+  uint64_t bar_w;
+  uint64_t bar_mma[2];
+  uint32_t tmem_slot;
+  int lock;
+  int cur_code;       // composite group code currently held in the TMEM accumulator
+  int cur_valid;
+  long long cur_cell; // a cell of that run (to look up its per-key group ids at flush time)
+};
+
+__device__ __forceinline__ void wg_sync(int wg) { asm volatile("bar.sync %0, 256;" ::"r"(wg + 1) : "memory"); }
+// warpgroup-wide AND of a predicate (bar.red on the warpgroup's named barrier)
+__device__ __forceinline__ int wg_all(int wg, int pred) {
+  int out;
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 q, %2, 0;\n\t"
+      "bar.red.and.pred p, %1, 256, q;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(out)
+      : "r"(wg + 1), "r"(pred)
+      : "memory");
+  return out;
+}
+__device__ __forceinline__ float sqrt_approx(float x) {
+  float y;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float h2f_lo(uint32_t w) { return __half2float(__ushort_as_half((unsigned short)(w & 0xFFFFu))); }
+__device__ __forceinline__ float h2f_hi(uint32_t w) { return __half2float(__ushort_as_half((unsigned short)(w >> 16))); }
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+
+// exact squared distance of tile rows a and b from the K-major (hi, lo) f16 operand buffers
+__device__ __noinline__ float exact_d2(const uint8_t* zh, const uint8_t* zl, int a, int b, int L) {
+  float e = 0.f;
+  for (int k = 0; k < L; ++k) {
+    const uint32_t ko = (uint32_t)(k >> 3) * 2048u + (uint32_t)(k & 7) * 2u;
+    const float za = __half2float(*reinterpret_cast<const __half*>(zh + ko + a * 16)) +
+                     __half2float(*reinterpret_cast<const __half*>(zl + ko + a * 16));
+    const float zb = __half2float(*reinterpret_cast<const __half*>(zh + ko + b * 16)) +
+                     __half2float(*reinterpret_cast<const __half*>(zl + ko + b * 16));
+    const float df = zb - za;
+    e = fmaf(df, df, e);
+  }
+  return e;
+}
+
+// LayerNorm + gelu of the 128-column accumulator row, this thread's 64-column half, written back in
+// place per 32-column chunk as [16 hi words | 16 lo words].  g_s / b_s: shared-memory LN vectors.
+__device__ __forceinline__ void ep128(uint32_t t_lane, int half, int r, int wg, const float* g_s, const float* b_s,
+                                      float2* xch) {
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+  for (int pp = 0; pp < 2; ++pp) {
+    float v[32];
+    tmem_ld32(t_lane + (2 * half + pp) * 32, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) { s1 += v[i]; s2 = fmaf(v[i], v[i], s2); }
+  }
+  xch[half * 128 + r] = make_float2(s1, s2);
+  wg_sync(wg);
+  const float2 o = xch[(half ^ 1) * 128 + r];
+  s1 += o.x; s2 += o.y;
+  const float mean = s1 * (1.0f / 128);
+  const float var = fmaxf(fmaf(s2, 1.0f / 128, -mean * mean), 0.f);
+  const float rstd = rsqrt_approx(var + kLnEps);
+  const float nb = -mean * rstd;
+#pragma unroll 1
+  for (int pp = 0; pp < 2; ++pp) {
+    const int p = 2 * half + pp;
+    float v[32];
+    tmem_ld32(t_lane + p * 32, v);
+    tmem_ld_wait();
+    uint32_t out[32];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 g4 = *reinterpret_cast<const float4*>(g_s + p * 32 + 4 * q);
+      const float4 b4 = *reinterpret_cast<const float4*>(b_s + p * 32 + 4 * q);
+      const float y0 = gelu_fast(fmaf(fmaf(v[4 * q], rstd, nb), g4.x, b4.x));
+      const float y1 = gelu_fast(fmaf(fmaf(v[4 * q + 1], rstd, nb), g4.y, b4.y));
+      const float y2 = gelu_fast(fmaf(fmaf(v[4 * q + 2], rstd, nb), g4.z, b4.z));
+      const float y3 = gelu_fast(fmaf(fmaf(v[4 * q + 3], rstd, nb), g4.w, b4.w));
+      split2(y0, y1, out[2 * q], out[16 + 2 * q]);
+      split2(y2, y3, out[2 * q + 1], out[16 + 2 * q + 1]);
+    }
+    tmem_st32(t_lane + p * 32, out);
+  }
+  tmem_st_wait();
+}
+
+// LayerNorm + gelu of the 32-column accumulator row, this thread's 16 columns -> two 16-byte K chunks
+// (hi and lo) of the next A operand in shared memory.
+__device__ __forceinline__ void ep32(uint32_t t_lane32, int half, int r, int wg, const float* g_s, const float* b_s,
+                                     float2* xch, uint8_t* row_h, uint8_t* row_l) {
+  float v[16];
+  tmem_ld16(t_lane32 + half * 16, v);
+  tmem_ld_wait();
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) { s1 += v[i]; s2 = fmaf(v[i], v[i], s2); }
+  xch[half * 128 + r] = make_float2(s1, s2);
+  wg_sync(wg);
+  const float2 o = xch[(half ^ 1) * 128 + r];
+  s1 += o.x; s2 += o.y;
+  const float mean = s1 * (1.0f / 32);
+  const float var = fmaxf(fmaf(s2, 1.0f / 32, -mean * mean), 0.f);
+  const float rstd = rsqrt_approx(var + kLnEps);
+  const float nb = -mean * rstd;
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int i0 = c * 8 + 2 * j, i1 = i0 + 1;
+      const float y0 = gelu_fast(fmaf(fmaf(v[i0], rstd, nb), g_s[half * 16 + i0], b_s[half * 16 + i0]));
+      const float y1 = gelu_fast(fmaf(fmaf(v[i1], rstd, nb), g_s[half * 16 + i1], b_s[half * 16 + i1]));
+      split2(y0, y1, h[j], l[j]);
+    }
+    *reinterpret_cast<uint4*>(row_h + (half * 2 + c) * 2048) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(row_l + (half * 2 + c) * 2048) = make_uint4(l[0], l[1], l[2], l[3]);
+  }
+}
+
+// [128 x 128] (A in TMEM, chunked [hi16|lo16] layout) x [128 x N]
+__device__ __forceinline__ void issue_gemm_ts2(uint32_t d_tmem, uint32_t a_tmem, uint32_t b, int N, uint32_t idesc) {
+  const uint32_t b_lbo = (uint32_t)N * 16;
+#pragma unroll
+  for (int ks = 0; ks < 8; ++ks) {
+    const uint64_t bd = umma_desc(b + ks * 2 * b_lbo, b_lbo, 128);
+    const uint32_t a = a_tmem + (ks >> 1) * 32 + (ks & 1) * 8;
+    umma_f16_ts(d_tmem, a, bd, idesc, ks == 0 ? 0u : 1u);
+    umma_f16_ts(d_tmem, a + 16, bd, idesc, 1u);
+  }
+}
+
+// flush this thread's two chunks of its accumulator lane into the float64 group sums and clear them
+__device__ __forceinline__ void flush_acc(uint32_t t_acc_lane, int half, const GroupPlan& gp, long long rep_cell, int S,
+                                          int c0, bool lane_valid, int r) {
+#pragma unroll 1
+  for (int pp = 0; pp < 2; ++pp) {
+    const int c = 2 * half + pp;
+    float a[32];
+    tmem_ld32(t_acc_lane + c * 32, a);
+    tmem_ld_wait();
+    if (lane_valid) {
+#pragma unroll 1
+      for (int k = 0; k < gp.n_keys; ++k) {
+        const int g = gp.codes[k][rep_cell];
+        if (g < 0) continue;
+        double* base = gp.sums[k] + ((size_t)g * S + (r - c0)) * S;
+#pragma unroll
+        for (int q = 0; q < 32; ++q) {
+          const int j = c * 32 + q - c0;
+          if (j >= 0 && j < S && j != r - c0) atomicAdd(base + j, (double)a[q]);
+        }
+      }
+    }
+    uint32_t z[32];
+#pragma unroll
+    for (int q = 0; q < 32; ++q) z[q] = 0u;
+    tmem_st32(t_acc_lane + c * 32, z);
+  }
+  tmem_st_wait();
+}
+
+__global__ void __launch_bounds__(kFusedThreads, 1)
+k_chain_fused_tc(const __grid_constant__ TcNet tc, CellBuf cb, int64_t n_cells, int S, int L, int Lq,
+                 float* __restrict__ z_out, float* __restrict__ cell_out, GroupPlan gp, int64_t n_tiles,
+                 int cells_per_tile, int64_t tiles_per_cta) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const FusedSmemMap sm = fused_smem_map(tc.wimg_bytes, tc.K1, tc.K3, L);
+  FusedCtrl* ctrl = reinterpret_cast<FusedCtrl*>(smem + sm.ctrl);
+  const int tid = threadIdx.x, wg = tid >> 8, wt = tid & 255, half = wt >> 7, r = wt & 127, warp_q = (wt >> 5) & 3;
+  const int Kz = sm.Kz, zld = sm.zf_ld;
+  float* lnv = reinterpret_cast<float*>(smem + sm.lnv);
+
+  if (tid == 0) {
+    mbar_init(&ctrl->bar_w, 1);
+    mbar_init(&ctrl->bar_mma[0], 1);
+    mbar_init(&ctrl->bar_mma[1], 1);
+    ctrl->lock = 0; ctrl->cur_code = -1; ctrl->cur_valid = 0; ctrl->cur_cell = 0;
+    fence_mbar_init();
+  }
+  for (int i = tid; i < (int)(sizeof(TcLn) / sizeof(float)); i += kFusedThreads) lnv[i] = reinterpret_cast<const float*>(&tc.ln)[i];
+  if (tid < 32) tmem_alloc(&ctrl->tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = ctrl->tmem_slot;
+  if (tid == 0) {
+    mbar_expect_tx(&ctrl->bar_w, tc.wimg_bytes);
+    bulk_g2s(smem + sm.w, tc.wimg, tc.wimg_bytes, &ctrl->bar_w);
+  }
+  const float *g1 = lnv, *b1 = lnv + 128, *g2 = lnv + 256, *b2 = lnv + 288, *g3 = lnv + 320, *b3 = lnv + 448,
+              *g4 = lnv + 576, *b4 = lnv + 608;
+  // TMEM columns: warpgroup g: [g*160, +128) = D1/T/D3/T/D5/Gram, [g*160+128, +32) = D2/D4; accumulator [320, 448)
+  const uint32_t t_r0 = tmem_base + wg * 160, t_d2 = t_r0 + 128;
+  const uint32_t lane_off = (uint32_t)(warp_q * 32) << 16;
+  const uint32_t t_lane = t_r0 + lane_off, t_d2_lane = t_d2 + lane_off, t_acc_lane = tmem_base + 320 + lane_off;
+  uint8_t* scratch = smem + sm.wg[wg];
+  const uint32_t s_w = smem_u32(smem + sm.w);
+  const uint32_t s_a1h = smem_u32(scratch), s_a1l = s_a1h + sm.off_a1l, s_a3h = s_a1h + sm.off_a3h, s_a3l = s_a1h + sm.off_a3l;
+  const uint32_t s_zh = s_a1h + sm.off_zh, s_zl = s_a1h + sm.off_zl;
+  uint8_t* row_a1h = scratch + r * 16;
+  uint8_t* row_a1l = scratch + sm.off_a1l + r * 16;
+  uint8_t* row_a3h = scratch + sm.off_a3h + r * 16;
+  uint8_t* row_a3l = scratch + sm.off_a3l + r * 16;
+  float* zf = reinterpret_cast<float*>(scratch + sm.off_zf);
+  uint8_t* zh = scratch + sm.off_zh;
+  uint8_t* zl = scratch + sm.off_zl;
+  float* mean_s = reinterpret_cast<float*>(smem + sm.mean[wg]);
+  float* nrm_s = reinterpret_cast<float*>(smem + sm.nrm[wg]);
+  float2* xch = reinterpret_cast<float2*>(smem + sm.xch[wg]);
+  uint64_t* bar_mma = &ctrl->bar_mma[wg];
+  const uint32_t idesc128 = umma_idesc_f16(128), idesc32 = umma_idesc_f16(32), idescN5 = umma_idesc_f16(tc.N5);
+  uint32_t phase = 0;
+  const bool need_dist = (cell_out != nullptr) || (gp.n_keys > 0);
+  const bool issuer = wt == 0;
+
+  // static row -> (local cell, sample) map of this thread
+  const int lc = r / S, s = r - lc * S, c0 = lc * S;
+  const bool row_in_tile = lc < cells_per_tile;
+  // warp-uniform Gram column chunks this warp needs (rows of a warp may straddle cells)
+  int cmin = row_in_tile ? c0 : 128, cmax = row_in_tile ? c0 + S : 0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    cmin = min(cmin, __shfl_xor_sync(0xffffffffu, cmin, o));
+    cmax = max(cmax, __shfl_xor_sync(0xffffffffu, cmax, o));
+  }
+  const int ch_lo = max(cmin >> 5, 2 * half), ch_hi = min((cmax + 31) >> 5, 2 * half + 2);  // this thread's chunks
+
+  if (gp.n_keys > 0 && wg == 0) {  // clear the accumulator once
+    uint32_t z[32];
+#pragma unroll
+    for (int q = 0; q < 32; ++q) z[q] = 0u;
+    tmem_st32(t_acc_lane + (2 * half) * 32, z);
+    tmem_st32(t_acc_lane + (2 * half + 1) * 32, z);
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  mbar_wait(&ctrl->bar_w, 0);
+  const float a_h = half ? tc.alpha[1] : tc.alpha[0], b_h = half ? tc.beta[1] : tc.beta[0];
+
+  const int64_t tile_begin = (int64_t)blockIdx.x * tiles_per_cta;
+  const int64_t tile_end = min(n_tiles, tile_begin + tiles_per_cta);
+  for (int64_t tile = tile_begin + wg; tile < tile_end; tile += 2) {
+    const int64_t pos = tile * cells_per_tile + lc;  // sorted position of this row's cell
+    const bool valid = row_in_tile && pos < n_cells;
+    const int64_t cell = valid ? (gp.order ? (int64_t)gp.order[pos] : pos) : 0;
+    const int code = (valid && gp.n_keys) ? gp.comp_sorted[pos] : -2;
+    const int ss = valid ? s : 0;
+
+    // ================= attention features of head `half` -> A1 chunks 2*half, 2*half+1 =================
+    {
+      float kvl[16];
+      const float4* kp = reinterpret_cast<const float4*>(tc.kvl + (size_t)ss * 16);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 t4 = __ldg(kp + q);
+        kvl[4 * q] = t4.x; kvl[4 * q + 1] = t4.y; kvl[4 * q + 2] = t4.z; kvl[4 * q + 3] = t4.w;
+      }
+      const float rmax = __ldg(tc.kvref + ss * 2), rmin = __ldg(tc.kvref + ss * 2 + 1);
+      const float* qp = cb.q_tok + cell * 16;
+#pragma unroll 1
+      for (int it = 0; it < 8; ++it) {  // one packed word (two features) per iteration
+        float mm[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const float t = fmaf(a_h, __ldg(qp + it * 2 + e), b_h);
+          const float off = -t * (t >= 0.f ? rmax : rmin);  // exponent <= 0 for every j
+          float den = 0.f, num = 0.f;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float ex = ex2_approx(fmaf(t, kvl[j], off));
+            den += ex;
+            num = fmaf(ex, kvl[j], num);
+          }
+          mm[e] = num * rcp_approx(den);  // = log2(e) * m[h,i]; 1/log2(e) is folded into B1 / B2a
+        }
+        uint32_t hw, lw;
+        split2(mm[0], mm[1], hw, lw);
+        const int off = (half * 2 + (it >> 2)) * 2048 + (it & 3) * 4;
+        *reinterpret_cast<uint32_t*>(row_a1h + off) = hw;
+        *reinterpret_cast<uint32_t*>(row_a1l + off) = lw;
+      }
+      if (half == 0) {  // constant-one column (k = 32) and zero padding of A1
+        for (int c = 4; c < tc.K1 / 8; ++c) {
+          *reinterpret_cast<uint4*>(row_a1h + c * 2048) = make_uint4(c == 4 ? 0x00003C00u : 0u, 0u, 0u, 0u);
+          *reinterpret_cast<uint4*>(row_a1l + c * 2048) = make_uint4(0u, 0u, 0u, 0u);
+        }
+      } else {          // A3 static part: columns 32.. = u_ln[0..Lq), then 1.0, then zeros
+        const float* ul = cb.u_ln + cell * Lq;
+        for (int c = 4; c < tc.K3 / 8; ++c) {
+          uint32_t hw[4], lw[4];
+#pragma unroll
+          for (int j2 = 0; j2 < 4; ++j2) {
+            const int k0 = (c - 4) * 8 + 2 * j2, k1 = k0 + 1;
+            const float a = k0 < Lq ? __ldg(ul + k0) : (k0 == Lq ? 1.0f : 0.f);
+            const float b = k1 < Lq ? __ldg(ul + k1) : (k1 == Lq ? 1.0f : 0.f);
+            split2(a, b, hw[j2], lw[j2]);
+          }
+          *reinterpret_cast<uint4*>(row_a3h + c * 2048) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+          *reinterpret_cast<uint4*>(row_a3l + c * 2048) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+        }
+      }
+    }
+    fence_proxy_async();
+    wg_sync(wg);
+
+    // ================= GEMM1 / epilogue 1 =================
+    if (issuer) {
+      tc_fence_after();
+      issue_gemm(t_r0, s_a1h, s_a1l, s_w + tc.off_b1, tc.K1, 128, idesc128, true);
+      umma_commit(bar_mma);
+    }
+    mbar_wait(bar_mma, phase); phase ^= 1;
+    tc_fence_after();
+    ep128(t_lane, half, r, wg, g1, b1, xch);
+    tc_fence_before();
+    wg_sync(wg);
+    // ================= GEMM2 / epilogue 2 =================
+    if (issuer) {
+      tc_fence_after();
+      issue_gemm_ts2(t_d2, t_r0, s_w + tc.off_b2t, 32, idesc32);
+      issue_gemm(t_d2, s_a1h, s_a1l, s_w + tc.off_b2a, tc.K1, 32, idesc32, false);
+      umma_commit(bar_mma);
+    }
+    mbar_wait(bar_mma, phase); phase ^= 1;
+    tc_fence_after();
+    ep32(t_d2_lane, half, r, wg, g2, b2, xch, row_a3h, row_a3l);
+    tc_fence_before();
+    fence_proxy_async();
+    wg_sync(wg);
+    // ================= GEMM3 / epilogue 3 =================
+    if (issuer) {
+      tc_fence_after();
+      issue_gemm(t_r0, s_a3h, s_a3l, s_w + tc.off_b3, tc.K3, 128, idesc128, true);
+      umma_commit(bar_mma);
+    }
+    mbar_wait(bar_mma, phase); phase ^= 1;
+    tc_fence_after();
+    ep128(t_lane, half, r, wg, g3, b3, xch);
+    tc_fence_before();
+    wg_sync(wg);
+    // ================= GEMM4 / epilogue 4 =================
+    if (issuer) {
+      tc_fence_after();
+      issue_gemm_ts2(t_d2, t_r0, s_w + tc.off_b4t, 32, idesc32);
+      issue_gemm(t_d2, s_a3h, s_a3l, s_w + tc.off_b4a, tc.K3, 32, idesc32, false);
+      umma_commit(bar_mma);
+    }
+    mbar_wait(bar_mma, phase); phase ^= 1;
+    tc_fence_after();
+    // A5 = [t4 | 1 | 0] reuses the A1 buffers (GEMM2 was their last reader); the one / zero columns are still in place
+    ep32(t_d2_lane, half, r, wg, g4, b4, xch, row_a1h, row_a1l);
+    tc_fence_before();
+    fence_proxy_async();
+    wg_sync(wg);
+    // ================= GEMM5 / residual rows =================
+    if (issuer) {
+      tc_fence_after();
+      issue_gemm(t_r0, s_a1h, s_a1l, s_w + tc.off_b5, tc.K5, tc.N5, idescN5, true);
+      umma_commit(bar_mma);
+    }
+    mbar_wait(bar_mma, phase); phase ^= 1;
+    tc_fence_after();
+    {
+      // this thread's half of the N5 output columns
+      const int ncol = tc.N5 >> 1, col0 = half * ncol;
+      float v[32];
+      if (ncol == 16) tmem_ld16(t_lane + col0, v); else tmem_ld32(t_lane + col0, v);
+      tmem_ld_wait();
+      if (valid && z_out != nullptr) {
+        const float* zb = cb.zbase + cell * L;
+        float* dst = z_out + (cell * S + s) * (int64_t)L;
+#pragma unroll
+        for (int l = 0; l < 32; ++l)
+          if (l < ncol && col0 + l < L) dst[col0 + l] = __ldg(zb + col0 + l) + v[l];
+      }
+      if (need_dist) {
+        // A1/A3 are dead (GEMM5 done): overlay the fp32 residual tile on them
+#pragma unroll
+        for (int l = 0; l < 32; ++l)
+          if (l < ncol && col0 + l < Kz) zf[r * zld + col0 + l] = (col0 + l < L && valid) ? v[l] : 0.f;
+      }
+    }
+    tc_fence_before();
+    wg_sync(wg);
+    if (!need_dist) continue;
+
+    // ================= centre per cell, norms, (hi, lo) Gram operands =================
+    for (int idx = wt; idx < cells_per_tile * Kz; idx += 256) {
+      const int cl = idx / Kz, l = idx - cl * Kz;
+      float sum = 0.f;
+      for (int q = 0; q < S; ++q) sum += zf[(cl * S + q) * zld + l];
+      mean_s[cl * Kz + l] = sum / (float)S;
+    }
+    wg_sync(wg);
+    {
+      const float* mrow = mean_s + (row_in_tile ? lc : 0) * Kz;
+      float nrm_p = 0.f;
+      const int nch = Kz >> 4;  // K chunks per half
+#pragma unroll 1
+      for (int cc = 0; cc < nch; ++cc) {
+        const int c = half * nch + cc;
+        uint32_t hw[4], lw[4];
+#pragma unroll
+        for (int j2 = 0; j2 < 4; ++j2) {
+          const int k0 = c * 8 + 2 * j2;
+          const float a = zf[r * zld + k0] - mrow[k0];
+          const float b = zf[r * zld + k0 + 1] - mrow[k0 + 1];
+          split2(a, b, hw[j2], lw[j2]);
+          // norms from the values the tensor core sees (hi + lo), so that n_i + n_j - 2 g cancels consistently
+          const float ar = h2f_lo(hw[j2]) + h2f_lo(lw[j2]), br = h2f_hi(hw[j2]) + h2f_hi(lw[j2]);
+          nrm_p = fmaf(ar, ar, nrm_p);
+          nrm_p = fmaf(br, br, nrm_p);
+        }
+        *reinterpret_cast<uint4*>(zh + c * 2048 + r * 16) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+        *reinterpret_cast<uint4*>(zl + c * 2048 + r * 16) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+      }
+      xch[half * 128 + r].x = nrm_p;
+    }
+    fence_proxy_async();
+    wg_sync(wg);
+    // ================= Gram on the tensor cores =================
+    if (issuer) {
+      tc_fence_after();
+      const uint32_t lbo = 128 * 16;
+      for (int ks = 0; ks < Kz / 16; ++ks) {
+        const uint64_t dh = umma_desc(s_zh + ks * 2 * lbo, lbo, 128), dl = umma_desc(s_zl + ks * 2 * lbo, lbo, 128);
+        umma_f16(t_r0, dh, dh, idesc128, ks == 0 ? 0u : 1u);
+        umma_f16(t_r0, dh, dl, idesc128, 1u);
+        umma_f16(t_r0, dl, dh, idesc128, 1u);
+      }
+      umma_commit(bar_mma);
+    }
+    const float n_i = xch[r].x + xch[128 + r].x;
+    if (half == 0) nrm_s[r] = n_i;
+    mbar_wait(bar_mma, phase); phase ^= 1;
+    tc_fence_after();
+
+    // ================= group-run bookkeeping =================
+    bool use_acc = false;
+    if (gp.n_keys > 0) {
+      const int first_code = gp.comp_sorted[min(tile * cells_per_tile, n_cells - 1)];
+      use_acc = wg_all(wg, ((!valid) || code == first_code) ? 1 : 0) != 0;  // also publishes nrm_s
+      if (use_acc) {
+        if (issuer) { while (atomicCAS(&ctrl->lock, 0, 1) != 0) __nanosleep(20); }
+        wg_sync(wg);
+        tc_fence_after();
+        const int cur = *reinterpret_cast<volatile int*>(&ctrl->cur_code);
+        const int cur_valid = *reinterpret_cast<volatile int*>(&ctrl->cur_valid);
+        if (cur_valid && cur != first_code) {
+          const long long rep = *reinterpret_cast<volatile long long*>(&ctrl->cur_cell);
+          flush_acc(t_acc_lane, half, gp, rep, S, c0, row_in_tile, r);
+        }
+        wg_sync(wg);
+        if (issuer) { ctrl->cur_code = first_code; ctrl->cur_valid = 1; ctrl->cur_cell = gp.order[tile * cells_per_tile]; }
+      }
+    } else {
+      wg_sync(wg);  // publishes nrm_s
+    }
+    // ================= distance epilogue: this thread's chunks of row r =================
+#pragma unroll 1
+    for (int c = ch_lo; c < ch_hi; ++c) {
+      float g[32];
+      tmem_ld32(t_lane + c * 32, g);
+      tmem_ld_wait();
+      uint32_t flagged = 0u;
+#pragma unroll
+      for (int q4 = 0; q4 < 8; ++q4) {
+        const float4 nj = *reinterpret_cast<const float4*>(nrm_s + c * 32 + 4 * q4);
+        const float njv[4] = {nj.x, nj.y, nj.z, nj.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int q = 4 * q4 + e, j = c * 32 + q;          // column = tile row of the other sample
+          const bool in = valid && (unsigned)(j - c0) < (unsigned)S && j != r;
+          const float sn = n_i + njv[e];
+          const float d2 = fmaf(-2.0f, g[q], sn);
+          if (in && d2 < sn * (1.0f / 4096.0f)) flagged |= 1u << q;  // cancellation dominated
+          const float d = sqrt_approx(fmaxf(d2, 0.f));
+          g[q] = in ? d : 0.f;
+        }
+      }
+      if (flagged) {  // rare: near-duplicate samples -> exact direct-difference distance
+#pragma unroll
+        for (int q = 0; q < 32; ++q)
+          if ((flagged >> q) & 1u) g[q] = sqrtf(exact_d2(zh, zl, r, c * 32 + q, L));
+      }
+      if (cell_out != nullptr && valid) {
+        float* dst = cell_out + ((size_t)cell * S + s) * S;
+        if ((S & 3) == 0) {  // c0 and S are multiples of 4: 16-byte stores
+#pragma unroll
+          for (int q4 = 0; q4 < 8; ++q4) {
+            const int j = c * 32 + 4 * q4 - c0;
+            if (j >= 0 && j < S)
+              *reinterpret_cast<float4*>(dst + j) = make_float4(g[4 * q4], g[4 * q4 + 1], g[4 * q4 + 2], g[4 * q4 + 3]);
+          }
+        } else {
+#pragma unroll
+          for (int q = 0; q < 32; ++q) {
+            const int j = c * 32 + q - c0;
+            if (j >= 0 && j < S) dst[j] = g[q];
+          }
+        }
+      }
+      if (use_acc) {
+        float acc[32];
+        tmem_ld32(t_acc_lane + c * 32, acc);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 32; ++q) acc[q] += g[q];
+        tmem_st32(t_acc_lane + c * 32, reinterpret_cast<uint32_t*>(acc));
+      } else if (gp.n_keys > 0 && valid) {  // mixed tile: straight to the float64 sums
+        for (int k = 0; k < gp.n_keys; ++k) {
+          const int gk = gp.codes[k][cell];
+          if (gk < 0) continue;
+          double* base = gp.sums[k] + ((size_t)gk * S + s) * S;
+#pragma unroll
+          for (int q = 0; q < 32; ++q) {
+            const int j = c * 32 + q - c0;
+            if (j >= 0 && j < S && j != s) atomicAdd(base + j, (double)g[q]);
+          }
+        }
+      }
+    }
+    if (use_acc) {
+      tmem_st_wait();
+      tc_fence_before();
+      wg_sync(wg);
+      if (issuer) { __threadfence_block(); atomicExch(&ctrl->lock, 0); }
+    }
+    tc_fence_before();
+    wg_sync(wg);  // Gram / scratch fully consumed before the next tile reuses them
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (gp.n_keys > 0 && wg == 0 && ctrl->cur_valid) {
+    flush_acc(t_acc_lane, half, gp, ctrl->cur_cell, S, c0, row_in_tile, r);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (tid < 32) tmem_dealloc(tmem_base, 512);
+}
+
+inline bool tc_fused_supported(const TcNet& tc, int S, int norm) { return tc.ready && norm == MRVI_NORM_L2 && S >= 4 && S <= 128; }
+
+inline int tc_fused_prepare(TcNet& tc, int L) {
+  const size_t bytes = fused_smem_map(tc.wimg_bytes, tc.K1, tc.K3, L).total + 1024;
+  if (bytes > 227 * 1024) return 0;  // fused path unavailable for this shape; the unfused kernels are used
+  if (cudaFuncSetAttribute(k_chain_fused_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) {
+    g_tc_error = "cudaFuncSetAttribute(k_chain_fused_tc) failed";
+    return MRVI_ERR_CUDA;
+  }
+  tc.fused_smem_bytes = bytes;
+  return 0;
+}
+
+inline void tc_launch_fused(const TcNet& tc, const NetW& net, int64_t n, const CellBuf& cb, float* z_out, float* cell_out,
+                            const GroupPlan& gp, cudaStream_t st) {
+  const int S = net.S;
+  const int cpt = kTcRows / S;
+  const int64_t n_tiles = (n + cpt - 1) / cpt;
+  if (n_tiles == 0) return;
+  const int grid = (int)std::min<int64_t>((n_tiles + 1) / 2, tc.sm_count);
+  const int64_t tiles_per_cta = (n_tiles + grid - 1) / grid;
+  k_chain_fused_tc<<<grid, kFusedThreads, tc.fused_smem_bytes, st>>>(tc, cb, n, S, net.L, net.Lq, z_out, cell_out, gp,
+                                                                    n_tiles, cpt, tiles_per_cta);
+}
+
+}  // namespace mrvi

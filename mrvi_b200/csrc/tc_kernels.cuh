@@ -63,6 +63,7 @@ struct TcNet {
   TcLn ln;
   int sm_count = 148;
   size_t smem_bytes = 0;
+  size_t fused_smem_bytes = 0;  // 0: fused kernel unavailable for this shape
   bool ready = false;
 };
 

@@ -180,3 +180,50 @@ def test_tc_matches_oracle(built_library, name, dk, n):
     ref_sum = np.stack([dref[codes[0] == g].sum(0) for g in range(4)])
     assert _relerr(res["group_sums"][0], ref_sum) < TOL["tc"]
     h.close()
+
+
+@pytest.mark.parametrize("S,n", [(32, 700), (128, 90), (15, 333), (48, 150)])
+def test_tc_fused_groups_skewed_two_keys(built_library, S, n):
+    """Fused kernel: Zipf-skewed groups (long and short runs, mixed tiles at the boundaries), two keys with -1
+    (= in no group) codes, groupby-only output, vs the oracle distances."""
+    dims = mrvi_b200.MrviDims(n_input=80, n_sample=S)
+    params, h = _model(dims, seed=7, precision="tc")
+    X, sid = _inputs(n, 80, S, seed=8)
+    rng = np.random.default_rng(1)
+    k0 = np.minimum(rng.zipf(1.6, size=n) - 1, 6).astype(np.int32)  # 7 groups, heavily skewed
+    k1 = rng.integers(-1, 3, size=n).astype(np.int32)               # -1 = no group
+    res = h.run_host(X, sid, [k0, k1], [7, 3], keep_cell=False)
+    assert "cell" not in res
+    dref = orc.pairwise_distances(orc.counterfactual_z(params, X, sid, dtype=np.float64))
+    scale = dref.max()
+    for k, (codes, ng) in enumerate([(k0, 7), (k1, 3)]):
+        assert np.array_equal(res["group_counts"][k], np.bincount(codes[codes >= 0], minlength=ng))
+        ref_sum = np.stack([dref[codes == g].sum(0) for g in range(ng)])
+        cnt = np.maximum(res["group_counts"][k], 1)[:, None, None]
+        assert np.abs(res["group_sums"][k] / cnt - ref_sum / cnt).max() / scale < TOL["tc"]
+    # keep_cell + groups in the same call give the same sums (run accumulation vs per-cell rows)
+    res2 = h.run_host(X, sid, [k0, k1], [7, 3], keep_cell=True, chunk_cells=256)
+    for k in range(2):
+        assert np.allclose(res2["group_sums"][k], res["group_sums"][k], rtol=1e-5, atol=1e-5 * scale)
+        ref_from_cells = np.stack([res2["cell"][[k0, k1][k] == g].astype(np.float64).sum(0) for g in range([7, 3][k])])
+        assert np.allclose(res2["group_sums"][k], ref_from_cells, rtol=1e-5, atol=1e-5 * scale)
+    h.close()
+
+
+def test_tc_fused_near_duplicate_samples(built_library):
+    """Two samples with identical / nearly identical embeddings: cancellation-dominated Gram entries must take
+    the exact direct-difference route (distance 0 resp. tiny, not sqrt of rounding noise)."""
+    dims = mrvi_b200.MrviDims(n_input=60, n_sample=32)
+    params = mrvi_b200.init_params(dims, seed=9)
+    emb = params["qz/Embed_0/embedding"]
+    emb[5] = emb[3]                      # exact duplicate
+    emb[7] = emb[6] * (1 + 1e-3)         # near duplicate
+    h = _capi.Handle(dims, params, device=0, precision=_capi.PRECISION_TC)
+    X, sid = _inputs(200, 60, 32, seed=3)
+    res = h.run_host(X, sid, keep_cell=True)
+    dref = orc.pairwise_distances(orc.counterfactual_z(params, X, sid, dtype=np.float64))
+    scale = dref.max(axis=(1, 2), keepdims=True)
+    assert np.all(res["cell"][:, 3, 5] == 0) and np.all(res["cell"][:, 5, 3] == 0)
+    assert (np.abs(res["cell"] - dref) / scale).max() < TOL["tc"]
+    assert (np.abs(res["cell"][:, 6, 7] - dref[:, 6, 7]) / scale[:, 0, 0]).max() < 2e-4
+    h.close()
