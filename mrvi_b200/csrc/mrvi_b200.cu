@@ -5,6 +5,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -14,6 +15,7 @@
 #include "common.cuh"
 #include "fp32_kernels.cuh"
 #include "tc_kernels.cuh"
+#include "tc_encoder.cuh"
 #include "tc_fused.cuh"
 
 namespace mrvi {
@@ -108,6 +110,7 @@ struct MrviHandle {
   NetW net{};
   TcNet tc{};
   EncTc enc_tc{};
+  EncTail enc_tail{};
   float* h1buf = nullptr;  // [chunk][128] Dense_0 output of the tensor-core encoder GEMM
   // workspace for one chunk of cells
   int64_t chunk_cells = 0;
@@ -331,6 +334,11 @@ static int setup_workspace(MrviHandle* h) {
 static int launch_encoder(MrviHandle* h, const float* X, int64_t ldx, const int32_t* sid, int64_t n, cudaStream_t st) {
   const int grid = (int)((n + kTM - 1) / kTM);
   const int vec_ok = ((ldx % 4) == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
+  if (h->precision == MRVI_PRECISION_TC && h->enc_tc.ready && h->enc_tail.ready) {
+    enc_full_tc_launch(h->enc_tc, h->enc_tail, X, ldx, sid, n, h->net.G, h->cb, st);
+    LAUNCH_CHECK();
+    return 0;
+  }
   const float* h1 = nullptr;
   if (h->precision == MRVI_PRECISION_TC && h->enc_tc.ready) {
     enc_tc_launch(h->enc_tc, X, ldx, n, h->net.G, h->h1buf, st);
@@ -543,6 +551,9 @@ int mrvi_create(const MrviDims* dims, int32_t n_params, const char* const* names
     if ((err = enc_tc_build(h->enc_tc, h->net, pt.m, h->arena))) return fail(err, "%s", tc_error());
     if (h->enc_tc.ready) CUDA_TRY(h->arena.alloc((void**)&h->h1buf, (size_t)h->chunk_cells * 128 * sizeof(float)));
     if ((err = tc_fused_prepare(h->tc, h->dims.n_latent))) return fail(err, "%s", tc_error());
+    if (h->enc_tc.ready && !getenv("MRVI_B200_FP32_ENCODER_TAIL")) {
+      if ((err = enc_tail_build(h->enc_tail, h->net, pt.m, h->arena))) return fail(err, "%s", tc_error());
+    }
   }
   CUDA_TRY(cudaEventCreate(&h->ev_call[0]));
   CUDA_TRY(cudaEventCreate(&h->ev_call[1]));

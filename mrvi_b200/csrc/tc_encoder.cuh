@@ -1,0 +1,419 @@
+// Whole encoder x -> u on the tensor cores (reference _module.py:173-202), one CTA = 128 cells.
+//
+// Phase 1 (HBM bound): H1 = log1p(X) . W0, the warp-specialised 3-stage pipeline of k_enc_gemm_tc.
+// Phase 2 (the "tail", hidden behind the other resident CTA's phase 1): the 128-wide layers
+//   h = gelu(gamma0[s] LN(H1 + b0) + beta0[s])                     ConditionalNormalization_0
+//   h = gelu(gamma1[s] LN(Dense_1 h) + beta1[s]) + sample_effect[s]  ConditionalNormalization_1, Embed_0
+//   per ResnetBlock:  t = relu(LN(Dense_0 h)) + h ;  h = relu(LN(Dense_out t))     (relu / relu)
+//   u = Dense_mean h ;  then per row  LN(u), query tokens, z_base  (reference _module.py:142, 166-170,
+//   _components.py:195-197)
+// run as tcgen05 GEMMs whose A operand is the previous layer's activation kept IN TMEM as (hi, lo) f16
+// pairs (TS-mode MMA, two 128-column regions used alternately; the residual `+ h` is re-read from
+// the previous region) against (hi, lo) f16 weights streamed per layer by TMA into the freed
+// pipeline stages:  D = Ah.Wh + Al.Wh + Ah.Wl  (~21 significant bits; single-f16 weights here would
+// cost 4-8e-4 normwise on the distances).  Epilogues are thread-per-row (TMEM lane =
+// cell), chunked by 32 columns, fp32.
+#pragma once
+#include "tc_kernels.cuh"
+
+namespace mrvi {
+
+constexpr int kEncMaxLayers = 1 + 2 * kMaxBlocks;
+constexpr int kEncLayerBytes = 2 * 128 * 128 * 2;  // hi | lo of a [128 x 128] f16 operand
+constexpr int kEncHeadBytes = 2 * 32 * 128 * 2;    // hi | lo of the [32 x 128] mean head
+
+struct EncTail {
+  const float *gamma0, *beta0, *gamma1, *beta1, *sample_effect;  // [S][128]
+  const uint8_t* wl[kEncMaxLayers];  // Dense_1, then (Dense_0, Dense_out) per ResnetBlock
+  const float* bl[kEncMaxLayers];    // biases [128]
+  const float* lg[kEncMaxLayers];    // LayerNorm scale [128] (null for the conditional layer)
+  const float* lb[kEncMaxLayers];
+  int n_layers;                      // 1 + 2 * n_blocks
+  const uint8_t* whead;              // mean head [32 x 128] hi | lo
+  const float* bhead;                // [Lq]
+  const float *uln_g, *uln_b;        // [Lq]
+  const float* wq;                   // [Lq][16]   DenseGeneral_0 (query tokens)
+  const float *wzb, *bzb;            // [Lq][L], [L]  qz/Dense_0 (null when isomorphic)
+  int Lq, L, S;
+  bool ready;
+};
+
+__device__ __forceinline__ float f16lo(uint32_t w) { return __half2float(__ushort_as_half((unsigned short)(w & 0xFFFFu))); }
+__device__ __forceinline__ float f16hi(uint32_t w) { return __half2float(__ushort_as_half((unsigned short)(w >> 16))); }
+
+// One tail epilogue for this thread's row: y = act(LN(D * scale + bias) * g + b) [+ add] [+ residual],
+// written back in place as the next A operand ([16 hi words | 16 lo words] per 32-column chunk).
+// ACT: 1 relu, 2 gelu.  g may be null (no scale).  t_res: TMEM address of the residual's region or 0.
+template <int ACT>
+__device__ __forceinline__ void enc_ep(uint32_t t_d, uint32_t t_res, float scale, const float* __restrict__ bias,
+                                       const float* __restrict__ g, const float* __restrict__ b,
+                                       const float* __restrict__ add) {
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+  for (int p = 0; p < 4; ++p) {
+    float v[32];
+    tmem_ld32(t_d + p * 32, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + p * 32) + q);
+      const float x0 = fmaf(v[4 * q], scale, b4.x), x1 = fmaf(v[4 * q + 1], scale, b4.y);
+      const float x2 = fmaf(v[4 * q + 2], scale, b4.z), x3 = fmaf(v[4 * q + 3], scale, b4.w);
+      s1 += (x0 + x1) + (x2 + x3);
+      s2 = fmaf(x0, x0, s2); s2 = fmaf(x1, x1, s2); s2 = fmaf(x2, x2, s2); s2 = fmaf(x3, x3, s2);
+    }
+  }
+  const float mean = s1 * (1.0f / 128);
+  const float var = fmaxf(fmaf(s2, 1.0f / 128, -mean * mean), 0.f);
+  const float rstd = 1.0f / sqrtf(var + kLnEps);
+  const float nb = -mean * rstd;
+#pragma unroll 1
+  for (int p = 0; p < 4; ++p) {
+    float v[32];
+    uint32_t rw[32];
+    tmem_ld32(t_d + p * 32, v);
+    if (t_res) tmem_ld32(t_res + p * 32, reinterpret_cast<float*>(rw));
+    tmem_ld_wait();
+    uint32_t out[32];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 bi = __ldg(reinterpret_cast<const float4*>(bias + p * 32) + q);
+      const float4 b4 = __ldg(reinterpret_cast<const float4*>(b + p * 32) + q);
+      float4 g4 = make_float4(1.f, 1.f, 1.f, 1.f), a4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (g) g4 = __ldg(reinterpret_cast<const float4*>(g + p * 32) + q);
+      if (add) a4 = __ldg(reinterpret_cast<const float4*>(add + p * 32) + q);
+      float y[4];
+      const float xs[4] = {fmaf(v[4 * q], scale, bi.x), fmaf(v[4 * q + 1], scale, bi.y), fmaf(v[4 * q + 2], scale, bi.z),
+                           fmaf(v[4 * q + 3], scale, bi.w)};
+      const float gs[4] = {g4.x, g4.y, g4.z, g4.w}, bs[4] = {b4.x, b4.y, b4.z, b4.w}, as[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float t = fmaf(fmaf(xs[e], rstd, nb), gs[e], bs[e]);
+        t = (ACT == 1) ? fmaxf(t, 0.f) : gelu_tanh_f(t);
+        y[e] = t + as[e];
+      }
+      if (t_res) {  // residual = previous activation (hi + lo), element 2j in the low halves of words j / 16+j
+        const uint32_t h0 = rw[2 * q], l0 = rw[16 + 2 * q], h1 = rw[2 * q + 1], l1 = rw[16 + 2 * q + 1];
+        y[0] += f16lo(h0) + f16lo(l0); y[1] += f16hi(h0) + f16hi(l0);
+        y[2] += f16lo(h1) + f16lo(l1); y[3] += f16hi(h1) + f16hi(l1);
+      }
+      split2(y[0], y[1], out[2 * q], out[16 + 2 * q]);
+      split2(y[2], y[3], out[2 * q + 1], out[16 + 2 * q + 1]);
+    }
+    tmem_st32(t_d + p * 32, out);
+  }
+  tmem_st_wait();
+}
+
+__global__ void __launch_bounds__(kEncThreads, 2)
+k_encoder_tc(const float* __restrict__ X, int64_t ldx, const int32_t* __restrict__ sample_idx, int64_t n_cells, int G,
+             EncTc enc, const __grid_constant__ EncTail tail, CellBuf cb, int x_vec_ok) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kEncStages * kEncStageBytes);
+  uint64_t* full = bars;                    // [stages] producers (128) + B expect_tx (1)
+  uint64_t* empty = bars + kEncStages;      // [stages] tcgen05.commit
+  uint64_t* acc_bar = bars + 2 * kEncStages;
+  uint64_t* bar_a = acc_bar + 1;            // tail: activation of the next layer is in TMEM (128 arrivals)
+  uint64_t* bar_d = acc_bar + 2;            // tail: layer MMAs committed
+  uint64_t* bar_w = acc_bar + 3;            // tail: layer weights landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 4);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nkb = enc.n_kblocks;
+  const int64_t cell0 = (int64_t)blockIdx.x * 128;
+  const int NL = tail.n_layers;
+
+  if (tid == 0) {
+    for (int s = 0; s < kEncStages; ++s) { mbar_init(full + s, 129); mbar_init(empty + s, 1); }
+    mbar_init(acc_bar, 1);
+    mbar_init(bar_a, 128);
+    mbar_init(bar_d, 1);
+    mbar_init(bar_w, 1);
+    fence_mbar_init();
+  }
+  if (warp == 4) tmem_alloc(tmem_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  uint8_t* wbuf = smem;  // tail weights overlay pipeline stages 0-1 (66 KB) once phase 1 has drained
+
+  if (warp < 4) {
+    // ------------------------------------------------------------ phase 1 producers
+    const int rsub = lane >> 2, chunk = lane & 3;
+    float4 cur[8], nxt[8];
+    auto load = [&](int kb, float4 (&dst)[8]) {
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        const int row = warp * 32 + p * 8 + rsub;
+        const int64_t cell = cell0 + row;
+        const int k = kb * kEncBK + chunk * 8;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+        if (cell < n_cells) {
+          const float* src = X + cell * ldx + k;
+          if (x_vec_ok && k + 8 <= G) {
+            a = __ldg(reinterpret_cast<const float4*>(src));
+            b = __ldg(reinterpret_cast<const float4*>(src) + 1);
+          } else {
+            float t[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) t[j] = (k + j < G) ? __ldg(src + j) : 0.f;
+            a = make_float4(t[0], t[1], t[2], t[3]);
+            b = make_float4(t[4], t[5], t[6], t[7]);
+          }
+        }
+        dst[2 * p] = a;
+        dst[2 * p + 1] = b;
+      }
+    };
+    load(0, cur);
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % kEncStages;
+      if (kb + 1 < nkb) load(kb + 1, nxt);
+      if (kb >= kEncStages) mbar_wait(empty + s, ((kb / kEncStages) - 1) & 1);
+      uint8_t* stage = smem + s * kEncStageBytes;
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        const int row = warp * 32 + p * 8 + rsub;
+        const float4 a = cur[2 * p], b = cur[2 * p + 1];
+        uint32_t h[4], l[4];
+        split2(log1p_fast(a.x), log1p_fast(a.y), h[0], l[0]);
+        split2(log1p_fast(a.z), log1p_fast(a.w), h[1], l[1]);
+        split2(log1p_fast(b.x), log1p_fast(b.y), h[2], l[2]);
+        split2(log1p_fast(b.z), log1p_fast(b.w), h[3], l[3]);
+        *reinterpret_cast<uint4*>(stage + chunk * kEncALbo + row * 16) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4*>(stage + kEncAHalf + chunk * kEncALbo + row * 16) = make_uint4(l[0], l[1], l[2], l[3]);
+      }
+      fence_proxy_async();
+      mbar_arrive(full + s);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) cur[j] = nxt[j];
+    }
+    // ------------------------------------------------------------ phase 2 epilogues (thread = cell = TMEM lane)
+    const int row = tid;
+    const int64_t cell = cell0 + row;
+    const bool valid = cell < n_cells;
+    int sid = valid ? sample_idx[cell] : 0;
+    sid = min(max(sid, 0), tail.S - 1);
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    const uint32_t t_reg[2] = {tmem_base + lane_off, tmem_base + 128 + lane_off};
+    mbar_wait(acc_bar, 0);
+    tc_fence_after();
+    // ConditionalNormalization_0 + gelu on H1 = D / 2^8 + b0          (reference _module.py:190-195)
+    enc_ep<2>(t_reg[0], 0u, 1.0f / kEncWScale, enc.b0, tail.gamma0 + (size_t)sid * 128, tail.beta0 + (size_t)sid * 128, nullptr);
+    tc_fence_before();
+    mbar_arrive(bar_a);
+    for (int li = 0; li < NL; ++li) {
+      mbar_wait(bar_d, li & 1);
+      tc_fence_after();
+      const uint32_t t_d = t_reg[(li + 1) & 1], t_a = t_reg[li & 1];
+      if (li == 0) {        // Dense_1 -> ConditionalNormalization_1 + gelu, + sample_effect   (reference _module.py:190-199)
+        enc_ep<2>(t_d, 0u, 1.0f, tail.bl[0], tail.gamma1 + (size_t)sid * 128, tail.beta1 + (size_t)sid * 128,
+                  tail.sample_effect + (size_t)sid * 128);
+      } else if (li & 1) {  // ResnetBlock Dense_0: relu(LN(.)) + h                            (reference _components.py:41-49)
+        enc_ep<1>(t_d, t_a, 1.0f, tail.bl[li], tail.lg[li], tail.lb[li], nullptr);
+      } else {              // ResnetBlock Dense_out: relu(LN(.))                               (reference _components.py:49-51)
+        enc_ep<1>(t_d, 0u, 1.0f, tail.bl[li], tail.lg[li], tail.lb[li], nullptr);
+      }
+      tc_fence_before();
+      mbar_arrive(bar_a);
+    }
+    // ---- mean head: u, LN(u), query tokens, z_base                                          (reference _components.py:95)
+    mbar_wait(bar_d, NL & 1);
+    tc_fence_after();
+    {
+      float u[32];
+      tmem_ld32(t_reg[(NL + 1) & 1], u);
+      tmem_ld_wait();
+      const int Lq = tail.Lq, L = tail.L;
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int l = 0; l < 32; ++l) {
+        u[l] = (l < Lq) ? u[l] + __ldg(tail.bhead + l) : 0.f;
+        s1 += u[l];
+        s2 = fmaf(u[l], u[l], s2);
+      }
+      const float mean = s1 / (float)Lq;
+      const float var = fmaxf(s2 / (float)Lq - mean * mean, 0.f);
+      const float rstd = 1.0f / sqrtf(var + kLnEps);
+      float ul[32];
+#pragma unroll
+      for (int l = 0; l < 32; ++l)
+        ul[l] = (l < Lq) ? (u[l] - mean) * (rstd * __ldg(tail.uln_g + l)) + __ldg(tail.uln_b + l) : 0.f;
+      if (valid) {
+#pragma unroll
+        for (int l = 0; l < 32; ++l)
+          if (l < Lq) { cb.u[cell * Lq + l] = u[l]; cb.u_ln[cell * Lq + l] = ul[l]; }
+        float qt[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) qt[i] = 0.f;
+#pragma unroll
+        for (int l = 0; l < 32; ++l)
+          if (l < Lq) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) qt[i] = fmaf(ul[l], __ldg(tail.wq + l * 16 + i), qt[i]);
+          }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          reinterpret_cast<float4*>(cb.q_tok + cell * 16)[i] = make_float4(qt[4 * i], qt[4 * i + 1], qt[4 * i + 2], qt[4 * i + 3]);
+        if (tail.wzb != nullptr) {
+          for (int j = 0; j < L; ++j) {
+            float a = __ldg(tail.bzb + j);
+#pragma unroll
+            for (int l = 0; l < 32; ++l)
+              if (l < Lq) a = fmaf(u[l], __ldg(tail.wzb + l * L + j), a);
+            cb.zbase[cell * L + j] = a;
+          }
+        } else {
+#pragma unroll
+          for (int l = 0; l < 32; ++l)
+            if (l < Lq) cb.zbase[cell * L + l] = u[l];
+        }
+      }
+    }
+    tc_fence_before();
+  } else if (warp == 4) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_f16(128);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % kEncStages;
+        mbar_wait(full + s, (kb / kEncStages) & 1);
+        tc_fence_after();
+        const uint32_t a_h = smem_u32(smem + s * kEncStageBytes), a_l = a_h + kEncAHalf;
+        const uint32_t b_h = a_h + 2 * kEncAHalf, b_l = b_h + 4 * 2048;
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+          const uint64_t ah = umma_desc(a_h + ks * 2 * kEncALbo, kEncALbo, 128);
+          const uint64_t al = umma_desc(a_l + ks * 2 * kEncALbo, kEncALbo, 128);
+          const uint64_t bh = umma_desc(b_h + ks * 2 * 2048, 2048, 128);
+          const uint64_t bl = umma_desc(b_l + ks * 2 * 2048, 2048, 128);
+          umma_f16(tmem_base, ah, bh, idesc, (kb | ks) ? 1u : 0u);
+          umma_f16(tmem_base, al, bh, idesc, 1u);
+          umma_f16(tmem_base, ah, bl, idesc, 1u);
+        }
+        umma_commit(empty + s);
+      }
+      umma_commit(acc_bar);
+      // tail layers: A from TMEM region li % 2, D to region (li + 1) % 2
+      const uint32_t s_wb = smem_u32(wbuf);
+      for (int li = 0; li <= NL; ++li) {
+        const int N = li < NL ? 128 : 32;
+        const uint32_t idn = umma_idesc_f16(N), lbo = (uint32_t)N * 16;
+        const uint32_t w_hi = s_wb, w_lo = s_wb + (uint32_t)N * 128 * 2;
+        mbar_wait(bar_w, li & 1);
+        mbar_wait(bar_a, li & 1);
+        tc_fence_after();
+        const uint32_t t_a = tmem_base + (li & 1) * 128, t_d = tmem_base + ((li + 1) & 1) * 128;
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint32_t a = t_a + (ks >> 1) * 32 + (ks & 1) * 8;
+          const uint64_t bh = umma_desc(w_hi + ks * 2 * lbo, lbo, 128), bl = umma_desc(w_lo + ks * 2 * lbo, lbo, 128);
+          umma_f16_ts(t_d, a, bh, idn, ks == 0 ? 0u : 1u);
+          umma_f16_ts(t_d, a + 16, bh, idn, 1u);
+          umma_f16_ts(t_d, a, bl, idn, 1u);
+        }
+        umma_commit(bar_d);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ weight loader (TMA bulk copies)
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % kEncStages;
+        if (kb >= kEncStages) mbar_wait(empty + s, ((kb / kEncStages) - 1) & 1);
+        mbar_expect_tx(full + s, kEncBBytes);
+        bulk_g2s(smem + s * kEncStageBytes + 2 * kEncAHalf, enc.w0img + (size_t)kb * kEncBBytes, kEncBBytes, full + s);
+      }
+      mbar_wait(acc_bar, 0);  // phase 1 MMAs have drained: stages 0-1 become the tail weight buffer
+      for (int li = 0; li <= NL; ++li) {
+        if (li > 0) mbar_wait(bar_d, (li - 1) & 1);  // previous layer no longer reads the buffer
+        const uint32_t bytes = li < NL ? kEncLayerBytes : kEncHeadBytes;
+        const uint8_t* src = li < NL ? tail.wl[li] : tail.whead;
+        mbar_expect_tx(bar_w, bytes);
+        for (uint32_t o = 0; o < bytes; o += 16384) bulk_g2s(wbuf + o, src + o, 16384, bar_w);
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem_base, 256);
+}
+
+// ---- host side: pack the tail weights
+inline uint32_t enc_pack_hilo(std::vector<uint8_t>& img, const float* W /*[K=128][N]*/, int N, int Npad) {
+  // canonical K-major [Npad x 128] f16, hi image then lo image
+  const uint32_t off = (uint32_t)img.size();
+  const size_t half_elems = (size_t)Npad * 128;
+  img.resize(off + 2 * half_elems * 2, 0);
+  __half* hi = reinterpret_cast<__half*>(img.data() + off);
+  __half* lo = hi + half_elems;
+  for (int k = 0; k < 128; ++k)
+    for (int n = 0; n < N; ++n) {
+      const float w = W[(size_t)k * N + n];
+      const __half h = __float2half_rn(w);
+      const size_t e = (size_t)(k / 8) * ((size_t)Npad * 8) + (size_t)n * 8 + (k % 8);
+      hi[e] = h;
+      lo[e] = __float2half_rn(w - __half2float(h));
+    }
+  return off;
+}
+
+inline int enc_tail_build(EncTail& t, const NetW& net, const tc_detail::PMap& pm, DeviceArena& arena) {
+  using tc_detail::P;
+  t.ready = false;
+  if (net.H != 128 || net.Lq > 31) return 0;
+  std::vector<uint8_t> img;
+  std::vector<uint32_t> offs;
+  offs.push_back(enc_pack_hilo(img, P(pm, "qu/Dense_1/kernel"), 128, 128));
+  for (int b = 0; b < net.n_enc_blocks; ++b) {
+    const std::string rb = "qu/NormalDistOutputNN_0/ResnetBlock_" + std::to_string(b);
+    offs.push_back(enc_pack_hilo(img, P(pm, rb + "/Dense_0/kernel"), 128, 128));
+    offs.push_back(enc_pack_hilo(img, P(pm, rb + "/Dense_1/kernel"), 128, 128));
+  }
+  const uint32_t off_head = enc_pack_hilo(img, P(pm, "qu/NormalDistOutputNN_0/Dense_0/kernel"), net.Lq, 32);
+  const uint8_t* dimg = nullptr;
+  int err;
+  if ((err = tc_upload(arena, img.data(), img.size(), (const void**)&dimg))) return err;
+  t.n_layers = 1 + 2 * net.n_enc_blocks;
+  for (int i = 0; i < t.n_layers; ++i) t.wl[i] = dimg + offs[i];
+  t.whead = dimg + off_head;
+  t.gamma0 = net.gamma[0]; t.beta0 = net.beta[0]; t.gamma1 = net.gamma[1]; t.beta1 = net.beta[1];
+  t.sample_effect = net.sample_effect;
+  t.bl[0] = net.enc1.b; t.lg[0] = nullptr; t.lb[0] = nullptr;
+  for (int b = 0; b < net.n_enc_blocks; ++b) {
+    const ResnetW& rb = net.enc_blocks[b];
+    t.bl[1 + 2 * b] = rb.d0.b; t.lg[1 + 2 * b] = rb.ln0.scale; t.lb[1 + 2 * b] = rb.ln0.bias;
+    t.bl[2 + 2 * b] = rb.dout.b; t.lg[2 + 2 * b] = rb.ln1.scale; t.lb[2 + 2 * b] = rb.ln1.bias;
+  }
+  t.bhead = net.enc_mean.b;
+  t.uln_g = net.u_ln.scale; t.uln_b = net.u_ln.bias;
+  // query-token and z_base weights as dense [Lq][16] / [Lq][L] fp32 (the packed fp32 copies are padded)
+  std::vector<float> wq((size_t)net.Lq * 16);
+  const float* wqs = P(pm, "qz/AttentionBlock_0/DenseGeneral_0/kernel");
+  for (size_t i = 0; i < wq.size(); ++i) wq[i] = wqs[i];
+  if ((err = tc_upload(arena, wq.data(), wq.size() * sizeof(float), (const void**)&t.wq))) return err;
+  t.wzb = nullptr; t.bzb = nullptr;
+  if (net.has_zbase) {
+    const float* w = P(pm, "qz/Dense_0/kernel");
+    const float* b = P(pm, "qz/Dense_0/bias");
+    if ((err = tc_upload(arena, w, (size_t)net.Lq * net.L * sizeof(float), (const void**)&t.wzb))) return err;
+    if ((err = tc_upload(arena, b, (size_t)net.L * sizeof(float), (const void**)&t.bzb))) return err;
+  }
+  t.Lq = net.Lq; t.L = net.L; t.S = net.S;
+  if (cudaFuncSetAttribute(k_encoder_tc, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)((size_t)kEncStages * kEncStageBytes + 256 + 1024)) != cudaSuccess) {
+    g_tc_error = "cudaFuncSetAttribute(k_encoder_tc) failed";
+    return MRVI_ERR_CUDA;
+  }
+  t.ready = true;
+  return 0;
+}
+
+inline void enc_full_tc_launch(const EncTc& enc, const EncTail& tail, const float* X, int64_t ldx, const int32_t* sid, int64_t n,
+                               int G, const CellBuf& cb, cudaStream_t st) {
+  const int grid = (int)((n + 127) / 128);
+  const int vec_ok = ((ldx % 4) == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
+  k_encoder_tc<<<grid, kEncThreads, enc.smem_bytes, st>>>(X, ldx, sid, n, G, enc, tail, cb, vec_ok);
+}
+
+}  // namespace mrvi
