@@ -166,16 +166,17 @@ k_encoder_tc(const float* __restrict__ X, int64_t ldx, const int32_t* __restrict
         dst[2 * p + 1] = b;
       }
     };
-    load(0, cur);
-    for (int kb = 0; kb < nkb; ++kb) {
+    // two K blocks of register prefetch ahead of the block being converted (memory-level parallelism:
+    // 3 x 16 KB of loads in flight per CTA)
+    float4 nx2[8];
+    auto convert = [&](int kb, const float4 (&src)[8]) {
       const int s = kb % kEncStages;
-      if (kb + 1 < nkb) load(kb + 1, nxt);
       if (kb >= kEncStages) mbar_wait(empty + s, ((kb / kEncStages) - 1) & 1);
       uint8_t* stage = smem + s * kEncStageBytes;
 #pragma unroll
       for (int p = 0; p < 4; ++p) {
         const int row = warp * 32 + p * 8 + rsub;
-        const float4 a = cur[2 * p], b = cur[2 * p + 1];
+        const float4 a = src[2 * p], b = src[2 * p + 1];
         uint32_t h[4], l[4];
         split2(log1p_fast(a.x), log1p_fast(a.y), h[0], l[0]);
         split2(log1p_fast(a.z), log1p_fast(a.w), h[1], l[1]);
@@ -186,8 +187,20 @@ k_encoder_tc(const float* __restrict__ X, int64_t ldx, const int32_t* __restrict
       }
       fence_proxy_async();
       mbar_arrive(full + s);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) cur[j] = nxt[j];
+    };
+    load(0, cur);
+    if (nkb > 1) load(1, nxt);
+    for (int kb = 0; kb < nkb; kb += 3) {
+      if (kb + 2 < nkb) load(kb + 2, nx2);
+      convert(kb, cur);
+      if (kb + 1 < nkb) {
+        if (kb + 3 < nkb) load(kb + 3, cur);
+        convert(kb + 1, nxt);
+      }
+      if (kb + 2 < nkb) {
+        if (kb + 4 < nkb) load(kb + 4, nxt);
+        convert(kb + 2, nx2);
+      }
     }
     // ------------------------------------------------------------ phase 2 epilogues (thread = cell = TMEM lane)
     const int row = tid;
