@@ -1,0 +1,127 @@
+"""Generate golden vectors by EXECUTING THE REFERENCE'S OWN SOURCE (TEST INFRASTRUCTURE ONLY).
+
+`/root/reference/src/mrvi/_components.py` and `_module.py` are imported unmodified on top of the numpy
+shim of flax / jax / numpyro / scvi in `oracle/flax_shim` (the real packages are not installable here).
+`MrVAE(...).apply({"params": tree}, method=inference, x, sample_index, cf_sample=s, use_mean=True)["z"]`
+is evaluated for every counterfactual sample s, exactly as `mapped_inference_fn` does
+(`_model.py:336-365`), in float64.  The outputs, the inputs and the seeds go to `tests/golden/*.npz`;
+`tests/test_golden.py` checks the oracle (and, on the GPU box, the CUDA path) against them and, when
+/root/reference is present, re-runs this comparison live.
+
+  python -m oracle.gen_golden            # rewrites tests/golden/
+"""
+from __future__ import annotations
+
+import importlib.util
+import os
+import sys
+import types
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SHIM = os.path.join(ROOT, "oracle", "flax_shim")
+REF_SRC = "/root/reference/src/mrvi"
+
+CASES = {
+    # name: (MrviDims kwargs, MrVAE kwargs of the reference, n_cells, seeds)
+    "default_S4": (dict(n_input=100, n_sample=4), dict(), 48, (0, 1)),
+    "iso_L10_S15": (dict(n_input=60, n_sample=15, n_latent=10, n_latent_u=10), dict(n_latent=10), 32, (2, 3)),
+    "latent_u5": (dict(n_input=40, n_sample=6, n_latent=10, n_latent_u=5), dict(n_latent=10, n_latent_u=5), 32, (4, 5)),
+    "use_map_false": (dict(n_input=30, n_sample=5, use_map=False), dict(qz_kwargs={"use_map": False}), 24, (6, 7)),
+}
+
+
+def reference_available() -> bool:
+    return os.path.isfile(os.path.join(REF_SRC, "_module.py"))
+
+
+def load_reference_modules():
+    """Import the reference's _components / _module as package `mrvi_ref` with the shim on sys.path."""
+    if "mrvi_ref._module" in sys.modules:
+        return sys.modules["mrvi_ref._components"], sys.modules["mrvi_ref._module"]
+    saved_path = list(sys.path)
+    saved_mods = {k: sys.modules.get(k) for k in ("jax", "flax", "numpyro", "scvi")}
+    sys.path.insert(0, SHIM)
+    try:
+        pkg = types.ModuleType("mrvi_ref")
+        pkg.__path__ = [REF_SRC]
+        sys.modules["mrvi_ref"] = pkg
+        mods = []
+        for name in ("_constants", "_components", "_module"):
+            spec = importlib.util.spec_from_file_location(f"mrvi_ref.{name}", os.path.join(REF_SRC, f"{name}.py"))
+            m = importlib.util.module_from_spec(spec)
+            sys.modules[f"mrvi_ref.{name}"] = m
+            spec.loader.exec_module(m)
+            mods.append(m)
+        return mods[1], mods[2]
+    finally:
+        sys.path[:] = saved_path
+        # keep the shim modules importable only under their own names inside mrvi_ref; drop them from the
+        # global table if they were not there before, so the rest of the test session is unaffected
+        for k, v in saved_mods.items():
+            if v is None:
+                for name in [n for n in sys.modules if n == k or n.startswith(k + ".")]:
+                    sys.modules.pop(name, None)
+
+
+def nest(flat):
+    tree = {}
+    for k, v in flat.items():
+        node = tree
+        parts = k.split("/")
+        for p in parts[:-1]:
+            node = node.setdefault(p, {})
+        node[parts[-1]] = np.asarray(v, dtype=np.float64)
+    return tree
+
+
+def reference_z(flat, dims, vae_kwargs, X, sid):
+    """z[b, s, :] by running the reference's MrVAE.inference for every counterfactual sample."""
+    _, module = load_reference_modules()
+    vae = module.MrVAE(n_input=dims.n_input, n_sample=dims.n_sample, n_batch=2, n_labels=1, n_continuous_cov=0,
+                       training=False, **vae_kwargs)
+    tree = nest(flat)
+    # the reference also evaluates the (unused under use_mean) scale head of q(u|x): give it parameters
+    H, Lq = flat["qu/NormalDistOutputNN_0/Dense_0/kernel"].shape
+    tree["qu"]["NormalDistOutputNN_0"]["Dense_1"] = {"kernel": np.zeros((H, Lq)), "bias": np.zeros(Lq)}
+    variables = {"params": tree}
+    x = np.asarray(X, dtype=np.float64)
+    sample_index = np.asarray(sid, dtype=np.float64).reshape(-1, 1)  # scvi loader hands floats, (B, 1)
+    zs = []
+    for s in range(dims.n_sample):
+        cf = np.full((x.shape[0], 1), s)
+        out = vae.apply(variables, method=vae.inference, x=x, sample_index=sample_index, cf_sample=cf, use_mean=True)
+        zs.append(np.asarray(out["z"]))
+    return np.stack(zs, axis=1)  # out_axes=-2  ->  (cell, sample, latent)
+
+
+def make_case(name):
+    sys.path.insert(0, ROOT)
+    import mrvi_b200
+
+    dk, vk, n, (pseed, xseed) = CASES[name]
+    dims = mrvi_b200.MrviDims(**dk)
+    flat = mrvi_b200.init_params(dims, seed=pseed)
+    X = mrvi_b200.synthetic_counts(n, dims.n_input, seed=xseed)
+    sid = np.random.default_rng(xseed).integers(0, dims.n_sample, n).astype(np.int32)
+    return dims, vk, flat, X, sid
+
+
+def main():
+    if not reference_available():
+        raise SystemExit("/root/reference is not present: golden vectors can only be regenerated in the build container")
+    out_dir = os.path.join(ROOT, "tests", "golden")
+    os.makedirs(out_dir, exist_ok=True)
+    for name in CASES:
+        dims, vk, flat, X, sid = make_case(name)
+        z = reference_z(flat, dims, vk, X, sid)
+        delta = z[:, None, :, :] - z[:, :, None, :]
+        d = np.sqrt((delta ** 2).sum(-1))  # `_model.py:547-550`
+        np.savez_compressed(os.path.join(out_dir, f"{name}.npz"), X=X, sid=sid, z=z.astype(np.float64), d=d.astype(np.float64),
+                            **{"param|" + k.replace("/", "|"): v for k, v in flat.items()})
+        print(f"{name}: z {z.shape}, max|z| {np.abs(z).max():.4f}, median d {np.median(d):.4f}")
+
+
+if __name__ == "__main__":
+    main()

@@ -9,7 +9,7 @@ It restates, operation by operation and in numpy, the reference's
 reference ``file:line`` it follows (paths relative to the reference repo root,
 ``src/mrvi/...``).
 
-PARITY UNPINNED at the third-party boundary.  The reference executes its arithmetic through
+PARITY PINNED AGAINST THE REFERENCE SOURCE, UNPINNED ONLY at the third-party boundary.  The reference executes its arithmetic through
 flax.linen / jax / numpyro / scvi-tools, none of which is installed here (no wheel, no network),
 and its own tests hold no numeric golden vectors for this path (``tests/test_model.py:233-241``
 check only shapes and symmetry).  So the semantics of the flax primitives below

@@ -1,0 +1,62 @@
+"""Golden vectors produced by executing the reference's own `_components.py` / `_module.py` on the numpy
+flax shim (`oracle/gen_golden.py`).  They pin the oracle's composition of the network against the
+reference source; the flax primitives themselves remain restated (see the oracle header)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import mrvi_b200
+from oracle import gen_golden as gg
+from oracle import mrvi_oracle as orc
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+
+
+def _load(path):
+    z = np.load(path)
+    flat = {k[len("param|"):].replace("|", "/"): z[k] for k in z.files if k.startswith("param|")}
+    return flat, z["X"], z["sid"], z["z"], z["d"]
+
+
+def test_golden_files_exist():
+    assert {os.path.basename(p)[:-4] for p in GOLDEN} == set(gg.CASES)
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_oracle_matches_reference_source_goldens(path):
+    flat, X, sid, z_ref, d_ref = _load(path)
+    z = orc.counterfactual_z(flat, X, sid, dtype=np.float64)
+    assert np.abs(z - z_ref).max() < 1e-12
+    assert np.abs(orc.pairwise_distances(z) - d_ref).max() < 1e-12
+    # the reference's dtype (float32) stays within the fp32 parity bar of the goldens
+    z32 = orc.counterfactual_z(flat, X, sid, dtype=np.float32)
+    assert np.abs(orc.pairwise_distances(z32) - d_ref).max() / d_ref.max() < 1e-5
+
+
+@pytest.mark.skipif(not gg.reference_available(), reason="/root/reference only exists in the build container")
+@pytest.mark.parametrize("name", list(gg.CASES))
+def test_goldens_regenerate_from_reference_source(name):
+    """Re-execute the reference source on the shim and compare with the committed fixtures."""
+    dims, vk, flat, X, sid = gg.make_case(name)
+    z = gg.reference_z(flat, dims, vk, X, sid)
+    stored = np.load(os.path.join(os.path.dirname(__file__), "golden", f"{name}.npz"))
+    assert np.array_equal(stored["X"], X) and np.array_equal(stored["sid"], sid)
+    assert np.abs(z - stored["z"]).max() < 1e-13
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-5), ("tc", 1e-3)])
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_cuda_matches_reference_source_goldens(built_library, path, precision, tol):
+    from mrvi_b200 import _capi
+
+    flat, X, sid, z_ref, d_ref = _load(path)
+    dims = mrvi_b200.infer_dims(flat)
+    h = _capi.Handle(dims, flat, device=0, precision=_capi.PRECISION_FP32 if precision == "fp32" else _capi.PRECISION_TC)
+    res = h.run_host(X, sid, keep_cell=True, want_z=True)
+    scale = d_ref.max(axis=(1, 2), keepdims=True)
+    assert (np.abs(res["cell"] - d_ref) / scale).max() < tol
+    assert np.abs(res["z"] - z_ref).max() / np.abs(z_ref).max() < tol
+    h.close()
