@@ -553,6 +553,8 @@ k_chain_fused_tc(const __grid_constant__ TcNet tc, CellBuf cb, int64_t n_cells, 
       tmem_ld32(t_lane + c * 32, g);
       tmem_ld_wait();
       uint32_t flagged = 0u;
+      // fast path (warp-uniform): the whole chunk lies inside every lane's cell and every row is valid
+      const bool full = __all_sync(0xffffffffu, valid && c * 32 >= c0 && c * 32 + 32 <= c0 + S);
 #pragma unroll
       for (int q4 = 0; q4 < 8; ++q4) {
         const float4 nj = *reinterpret_cast<const float4*>(nrm_s + c * 32 + 4 * q4);
@@ -560,7 +562,7 @@ k_chain_fused_tc(const __grid_constant__ TcNet tc, CellBuf cb, int64_t n_cells, 
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int q = 4 * q4 + e, j = c * 32 + q;          // column = tile row of the other sample
-          const bool in = valid && (unsigned)(j - c0) < (unsigned)S && j != r;
+          const bool in = full ? (j != r) : (valid && (unsigned)(j - c0) < (unsigned)S && j != r);
           const float sn = n_i + njv[e];
           const float d2 = fmaf(-2.0f, g[q], sn);
           if (in && d2 < sn * (1.0f / 4096.0f)) flagged |= 1u << q;  // cancellation dominated
