@@ -121,6 +121,18 @@ int mrvi_run_host(MrviHandle* h, int64_t n_cells, const float* X, int64_t ldx,
                   float* u_out, int64_t chunk_cells);
 
 /*
+ * mrvi_run_host with X given as a host CSR matrix (scipy.sparse.csr_matrix layout: indptr [n_cells+1]
+ * int64, indices [nnz] int32 column ids in [0, n_input), data [nnz] float32).  Replaces the host-side
+ * densify of scvi's AnnDataLoader (src/mrvi/_model.py:317-319): only the non-zeros cross PCIe, each
+ * chunk is expanded to dense rows on the GPU.  Other arguments as mrvi_run_host.
+ */
+int mrvi_run_host_csr(MrviHandle* h, int64_t n_cells, const int64_t* indptr, const int32_t* indices,
+                      const float* data, const int32_t* sample_idx, int32_t n_keys,
+                      const int32_t* const* group_codes, const int32_t* n_groups, int32_t norm,
+                      float* cell_out, double* const* group_sums, int64_t* const* group_counts,
+                      float* z_out, float* u_out, int64_t chunk_cells);
+
+/*
  * Stage (3) alone on device buffers: pairwise distances of given representations
  * z [n_cells, S, L] (the seam of _compute_distances_from_representations, _model.py:542-584),
  * with the same outputs as mrvi_run_device.  Used by the parity tests to isolate the stage.

@@ -29,6 +29,7 @@ EXPORTED_SYMBOLS = (
     "mrvi_destroy",
     "mrvi_run_device",
     "mrvi_run_host",
+    "mrvi_run_host_csr",
     "mrvi_distances_device",
     "mrvi_last_stage_ms",
 )
@@ -77,6 +78,9 @@ def load_library():
     lib.mrvi_run_host.restype = C.c_int
     lib.mrvi_run_host.argtypes = [vp, i64, vp, i64, vp, i32, C.POINTER(vp), C.POINTER(i32), i32, vp,
                                   C.POINTER(vp), C.POINTER(vp), vp, vp, i64]
+    lib.mrvi_run_host_csr.restype = C.c_int
+    lib.mrvi_run_host_csr.argtypes = [vp, i64, vp, vp, vp, vp, i32, C.POINTER(vp), C.POINTER(i32), i32, vp,
+                                      C.POINTER(vp), C.POINTER(vp), vp, vp, i64]
     lib.mrvi_distances_device.restype = C.c_int
     lib.mrvi_distances_device.argtypes = [vp, i64, vp, i32, C.POINTER(vp), C.POINTER(i32), i32, vp,
                                           C.POINTER(vp), vp]
@@ -172,12 +176,20 @@ class Handle:
         if norm not in NORMS:
             raise ValueError(f"norm {norm} not supported")
         d = self.dims
-        if X.dtype != np.float32 or X.ndim != 2 or X.strides[1] != 4 or X.strides[0] % 4 != 0:
+        csr = None
+        if hasattr(X, "tocsr") and not isinstance(X, np.ndarray):  # scipy sparse: ship the non-zeros, densify on the GPU
+            X = X.tocsr()
+            if not X.has_canonical_format:
+                X = X.copy()
+                X.sum_duplicates()
+            csr = (np.ascontiguousarray(X.indptr, dtype=np.int64), np.ascontiguousarray(X.indices, dtype=np.int32),
+                   np.ascontiguousarray(X.data, dtype=np.float32))
+        elif X.dtype != np.float32 or X.ndim != 2 or X.strides[1] != 4 or X.strides[0] % 4 != 0:
             X = np.ascontiguousarray(X, dtype=np.float32)
         n = X.shape[0]
         if X.shape[1] != d.n_input:
             raise ValueError(f"X has {X.shape[1]} genes, model expects {d.n_input}")
-        ldx = X.strides[0] // 4 if n > 1 else d.n_input
+        ldx = d.n_input if (csr is not None or n <= 1) else X.strides[0] // 4
         sid = np.ascontiguousarray(sample_idx, dtype=np.int32).reshape(-1)
         if sid.shape[0] != n:
             raise ValueError("sample_idx length does not match X")
@@ -196,11 +208,14 @@ class Handle:
         counts = [np.zeros((g,), dtype=np.int64) for g in n_groups]
         z = np.empty((n, S, L), dtype=np.float32) if want_z else None
         u = np.empty((n, Lq), dtype=np.float32) if want_u else None
-        _check(load_library().mrvi_run_host(
-            self._h, n, X.ctypes.data, ldx, sid.ctypes.data, len(codes), _ptr_array([c.ctypes.data for c in codes]),
-            _i32_array(n_groups), NORMS[norm], out["cell"].ctypes.data if keep_cell else None,
-            _ptr_array([s.ctypes.data for s in sums]), _ptr_array([c.ctypes.data for c in counts]),
-            z.ctypes.data if want_z else None, u.ctypes.data if want_u else None, int(chunk_cells)))
+        tail = (sid.ctypes.data, len(codes), _ptr_array([c.ctypes.data for c in codes]),
+                _i32_array(n_groups), NORMS[norm], out["cell"].ctypes.data if keep_cell else None,
+                _ptr_array([s.ctypes.data for s in sums]), _ptr_array([c.ctypes.data for c in counts]),
+                z.ctypes.data if want_z else None, u.ctypes.data if want_u else None, int(chunk_cells))
+        if csr is not None:
+            _check(load_library().mrvi_run_host_csr(self._h, n, csr[0].ctypes.data, csr[1].ctypes.data, csr[2].ctypes.data, *tail))
+        else:
+            _check(load_library().mrvi_run_host(self._h, n, X.ctypes.data, ldx, *tail))
         out["group_sums"] = sums
         out["group_counts"] = counts
         if want_z:

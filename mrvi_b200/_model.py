@@ -152,12 +152,14 @@ class MrVI:
         sample_codes = self._sample_codes(adata)[idx]
         whole = indices is None
         X = adata.X
-        if whole and isinstance(X, np.ndarray) and X.dtype == np.float32 and X.flags.c_contiguous:
+        if hasattr(X, "tocsr") and not isinstance(X, np.ndarray):
+            Xh = X.tocsr() if whole else X.tocsr()[idx]  # stays sparse: densified on the GPU (mrvi_run_host_csr)
+        elif whole and isinstance(X, np.ndarray) and X.dtype == np.float32 and X.flags.c_contiguous:
             Xh = X
         elif whole:
             Xh = dense_float32(X)
         else:
-            Xh = dense_float32(X[idx] if not hasattr(X, "tocsr") else X.tocsr()[idx])
+            Xh = dense_float32(X[idx])
 
         generic = [r for r in reductions if not _is_identity_fn(r.fn)]
         if generic:
@@ -252,6 +254,28 @@ class MrVI:
             final[gr.name] = DataArray(np.stack(arrs, axis=0), dims=[f"{gr.group_by}_name", *g0.dims],
                                        coords={**dict(g0.coords), f"{gr.group_by}_name": np.asarray(cats)}, name=g0.name)
         return Dataset(final)
+
+    def get_latent_representation(self, adata=None, indices: Optional[Sequence[int]] = None, batch_size: Optional[int] = None,
+                                  use_mean: bool = True, give_z: bool = False) -> np.ndarray:
+        """Reference `_model.py:221-271`: ``u`` (n_obs, n_latent_u) or, with ``give_z``, ``z`` of every cell for
+        its OWN sample (n_obs, n_latent).  A by-product of stages (1)+(2): ``u`` comes
+        straight from the encoder; ``z`` is row ``sample_idx[cell]`` of the counterfactual tile."""
+        if not use_mean:
+            raise NotImplementedError("use_mean=False depends on the JAX PRNG streams of the reference (SURVEY.md 8(f)-1)")
+        self._check_if_trained(warn=False)
+        adata = self.adata if adata is None else adata
+        idx = np.arange(adata.n_obs) if indices is None else np.asarray(indices).astype(int).reshape(-1)
+        sample_codes = self._sample_codes(adata)[idx]
+        X = adata.X
+        if hasattr(X, "tocsr") and not isinstance(X, np.ndarray):
+            Xh = X.tocsr() if indices is None else X.tocsr()[idx]
+        else:
+            Xh = dense_float32(X) if indices is None else dense_float32(X[idx])
+        res = self._handle.run_host(Xh, sample_codes, keep_cell=False, want_u=not give_z, want_z=give_z)
+        self.last_stage_ms = self._handle.last_stage_ms()
+        if give_z:
+            return np.ascontiguousarray(res["z"][np.arange(len(idx)), sample_codes])
+        return res["u"]
 
     def get_local_sample_representation(self, adata=None, indices: Optional[Sequence[int]] = None, batch_size: int = 256,
                                         use_mean: bool = True, use_vmap: bool = True):

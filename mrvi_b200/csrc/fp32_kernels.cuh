@@ -654,6 +654,20 @@ __global__ void k_sample_tables(const float* __restrict__ embed, const float* __
   }
 }
 
+// CSR rows [0, n) of one chunk -> dense row-major X [n][G] (the buffer is zeroed before): one warp per row.
+// indptr_rel holds the chunk's n+1 row pointers (absolute), nz0 = indptr of the chunk's first row.
+__global__ void k_csr_densify(const int64_t* __restrict__ indptr, int64_t nz0, const int32_t* __restrict__ indices,
+                              const float* __restrict__ data, int64_t n, int G, float* __restrict__ X) {
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n) return;
+  const int lane = threadIdx.x & 31;
+  const int64_t b = indptr[row] - nz0, e = indptr[row + 1] - nz0;
+  for (int64_t k = b + lane; k < e; k += 32) {
+    const int c = indices[k];
+    if (c >= 0 && c < G) X[row * G + c] = data[k];
+  }
+}
+
 // composite group code of each cell (mixed radix over (code_k + 1)), for the per-chunk sort
 __global__ void k_composite_codes(GroupPlan gp, const int32_t* n_groups_dev, int64_t n, int32_t* comp,
                                   int32_t* idx) {

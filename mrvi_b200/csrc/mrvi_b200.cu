@@ -70,6 +70,10 @@ struct HostStage {  // device-side staging of mrvi_run_host, cached across calls
   int n_keys = 0;
   bool has_cell = false, has_z = false, has_u = false;
   float* X[2] = {nullptr, nullptr};
+  int64_t* csr_ptr[2] = {nullptr, nullptr};   // CSR staging (mrvi_run_host_csr)
+  int32_t* csr_idx[2] = {nullptr, nullptr};
+  float* csr_val[2] = {nullptr, nullptr};
+  int64_t csr_nnz_cap = 0;
   int32_t* sid[2] = {nullptr, nullptr};
   int32_t* codes[2][kMaxKeys] = {};
   float* cell[2] = {nullptr, nullptr};
@@ -605,12 +609,17 @@ int mrvi_distances_device(MrviHandle* h, int64_t n_cells, const float* z, int32_
   return 0;
 }
 
-int mrvi_run_host(MrviHandle* h, int64_t n_cells, const float* X, int64_t ldx, const int32_t* sample_idx,
-                  int32_t n_keys, const int32_t* const* group_codes, const int32_t* n_groups, int32_t norm,
-                  float* cell_out, double* const* group_sums, int64_t* const* group_counts, float* z_out,
-                  float* u_out, int64_t chunk_cells) {
+static int run_host_impl(MrviHandle* h, int64_t n_cells, const float* X, int64_t ldx, const int64_t* indptr,
+                         const int32_t* indices, const float* data, const int32_t* sample_idx,
+                         int32_t n_keys, const int32_t* const* group_codes, const int32_t* n_groups, int32_t norm,
+                         float* cell_out, double* const* group_sums, int64_t* const* group_counts, float* z_out,
+                         float* u_out, int64_t chunk_cells) {
   int err;
-  if ((err = validate_run(h, n_cells, X, ldx, sample_idx, n_keys, group_codes, n_groups, norm, group_sums))) return err;
+  const bool csr = indptr != nullptr;
+  if ((err = validate_run(h, n_cells, csr ? (const void*)indptr : (const void*)X, csr ? h->dims.n_input : ldx, sample_idx, n_keys,
+                          group_codes, n_groups, norm, group_sums))) return err;
+  if (csr && n_cells > 0 && (!indices || !data) && indptr[n_cells] > indptr[0])
+    return fail(MRVI_ERR_INVALID_ARG, "CSR indices / data is null");
   CUDA_TRY(cudaSetDevice(h->device));
   const NetW& net = h->net;
   const int S = net.S, L = net.L, G = net.G, Lq = net.Lq;
@@ -643,7 +652,11 @@ int mrvi_run_host(MrviHandle* h, int64_t n_cells, const float* X, int64_t ldx, c
   }
   bool sums_ok = true;
   for (int k = 0; k < n_keys; ++k) sums_ok &= hs.sums_elems[k] >= (size_t)n_groups[k] * S * S;
-  if (hs.chunk < ch || hs.n_keys < n_keys || (cell_out && !hs.has_cell) || (z_out && !hs.has_z) || (u_out && !hs.has_u) || !sums_ok) {
+  int64_t max_nnz = 0;
+  if (csr)
+    for (int64_t lo = 0; lo < n_cells; lo += ch) max_nnz = std::max(max_nnz, indptr[std::min(n_cells, lo + ch)] - indptr[lo]);
+  if (hs.chunk < ch || hs.n_keys < n_keys || (cell_out && !hs.has_cell) || (z_out && !hs.has_z) || (u_out && !hs.has_u) || !sums_ok ||
+      (csr && hs.csr_nnz_cap < max_nnz)) {
     CUDA_TRY(cudaDeviceSynchronize());
     hs.free_buffers();
     auto A = [&](void** p, size_t bytes) -> cudaError_t {
@@ -653,6 +666,12 @@ int mrvi_run_host(MrviHandle* h, int64_t n_cells, const float* X, int64_t ldx, c
     };
     for (int b = 0; b < 2; ++b) {
       CUDA_TRY(A((void**)&hs.X[b], ch * G * sizeof(float)));
+      hs.csr_ptr[b] = nullptr; hs.csr_idx[b] = nullptr; hs.csr_val[b] = nullptr;
+      if (csr) {
+        CUDA_TRY(A((void**)&hs.csr_ptr[b], (ch + 1) * sizeof(int64_t)));
+        CUDA_TRY(A((void**)&hs.csr_idx[b], std::max<int64_t>(max_nnz, 1) * sizeof(int32_t)));
+        CUDA_TRY(A((void**)&hs.csr_val[b], std::max<int64_t>(max_nnz, 1) * sizeof(float)));
+      }
       CUDA_TRY(A((void**)&hs.sid[b], ch * sizeof(int32_t)));
       for (int k = 0; k < n_keys; ++k) CUDA_TRY(A((void**)&hs.codes[b][k], ch * sizeof(int32_t)));
       hs.cell[b] = nullptr; hs.z[b] = nullptr; hs.u[b] = nullptr;
@@ -665,6 +684,7 @@ int mrvi_run_host(MrviHandle* h, int64_t n_cells, const float* X, int64_t ldx, c
       hs.sums_elems[k] = (size_t)n_groups[k] * S * S;
       CUDA_TRY(A((void**)&hs.sums[k], hs.sums_elems[k] * sizeof(double)));
     }
+    hs.csr_nnz_cap = csr ? max_nnz : 0;
     hs.chunk = ch; hs.n_keys = n_keys; hs.has_cell = cell_out != nullptr; hs.has_z = z_out != nullptr; hs.has_u = u_out != nullptr;
   }
   ch = std::min(ch, hs.chunk);
@@ -678,8 +698,17 @@ int mrvi_run_host(MrviHandle* h, int64_t n_cells, const float* X, int64_t ldx, c
     const int64_t m = std::min(ch, n_cells - lo);
     // H2D (wait until the kernels of chunk c-2 released input buffers b)
     if (c >= 2) CUDA_TRY(cudaStreamWaitEvent(hs.s_h2d, hs.ev_comp[b], 0));
-    CUDA_TRY(cudaMemcpy2DAsync(hs.X[b], (size_t)G * sizeof(float), X + lo * ldx, (size_t)ldx * sizeof(float),
-                               (size_t)G * sizeof(float), (size_t)m, cudaMemcpyHostToDevice, hs.s_h2d));
+    if (csr) {
+      const int64_t nz0 = indptr[lo], nnz = indptr[lo + m] - nz0;
+      CUDA_TRY(cudaMemcpyAsync(hs.csr_ptr[b], indptr + lo, (m + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, hs.s_h2d));
+      if (nnz > 0) {
+        CUDA_TRY(cudaMemcpyAsync(hs.csr_idx[b], indices + nz0, nnz * sizeof(int32_t), cudaMemcpyHostToDevice, hs.s_h2d));
+        CUDA_TRY(cudaMemcpyAsync(hs.csr_val[b], data + nz0, nnz * sizeof(float), cudaMemcpyHostToDevice, hs.s_h2d));
+      }
+    } else {
+      CUDA_TRY(cudaMemcpy2DAsync(hs.X[b], (size_t)G * sizeof(float), X + lo * ldx, (size_t)ldx * sizeof(float),
+                                 (size_t)G * sizeof(float), (size_t)m, cudaMemcpyHostToDevice, hs.s_h2d));
+    }
     CUDA_TRY(cudaMemcpyAsync(hs.sid[b], sample_idx + lo, m * sizeof(int32_t), cudaMemcpyHostToDevice, hs.s_h2d));
     for (int k = 0; k < n_keys; ++k)
       CUDA_TRY(cudaMemcpyAsync(hs.codes[b][k], group_codes[k] + lo, m * sizeof(int32_t), cudaMemcpyHostToDevice, hs.s_h2d));
@@ -687,6 +716,11 @@ int mrvi_run_host(MrviHandle* h, int64_t n_cells, const float* X, int64_t ldx, c
     // compute (wait for inputs, and for the D2H of chunk c-2 to release output buffers b)
     CUDA_TRY(cudaStreamWaitEvent(hs.s_comp, hs.ev_h2d[b], 0));
     if (c >= 2) CUDA_TRY(cudaStreamWaitEvent(hs.s_comp, hs.ev_d2h[b], 0));
+    if (csr) {  // expand the chunk's non-zeros to dense rows on the GPU
+      CUDA_TRY(cudaMemsetAsync(hs.X[b], 0, (size_t)m * G * sizeof(float), hs.s_comp));
+      k_csr_densify<<<(unsigned)((m + 7) / 8), 256, 0, hs.s_comp>>>(hs.csr_ptr[b], indptr[lo], hs.csr_idx[b], hs.csr_val[b], m, G, hs.X[b]);
+      LAUNCH_CHECK();
+    }
     if ((err = run_device_impl(h, m, hs.X[b], G, hs.sid[b], n_keys, hs.codes[b], n_groups, norm,
                                cell_out ? hs.cell[b] : nullptr, hs.sums, z_out ? hs.z[b] : nullptr,
                                u_out ? hs.u[b] : nullptr, hs.s_comp, false))) return err;
@@ -707,6 +741,23 @@ int mrvi_run_host(MrviHandle* h, int64_t n_cells, const float* X, int64_t ldx, c
   CUDA_TRY(cudaStreamSynchronize(hs.s_comp));
   CUDA_TRY(cudaStreamSynchronize(hs.s_d2h));
   return 0;
+}
+
+int mrvi_run_host(MrviHandle* h, int64_t n_cells, const float* X, int64_t ldx, const int32_t* sample_idx,
+                  int32_t n_keys, const int32_t* const* group_codes, const int32_t* n_groups, int32_t norm,
+                  float* cell_out, double* const* group_sums, int64_t* const* group_counts, float* z_out,
+                  float* u_out, int64_t chunk_cells) {
+  return run_host_impl(h, n_cells, X, ldx, nullptr, nullptr, nullptr, sample_idx, n_keys, group_codes, n_groups, norm, cell_out,
+                       group_sums, group_counts, z_out, u_out, chunk_cells);
+}
+
+int mrvi_run_host_csr(MrviHandle* h, int64_t n_cells, const int64_t* indptr, const int32_t* indices, const float* data,
+                      const int32_t* sample_idx, int32_t n_keys, const int32_t* const* group_codes, const int32_t* n_groups,
+                      int32_t norm, float* cell_out, double* const* group_sums, int64_t* const* group_counts, float* z_out,
+                      float* u_out, int64_t chunk_cells) {
+  if (!indptr) return fail(MRVI_ERR_INVALID_ARG, "indptr is null");
+  return run_host_impl(h, n_cells, nullptr, h ? h->dims.n_input : 0, indptr, indices, data, sample_idx, n_keys, group_codes, n_groups,
+                       norm, cell_out, group_sums, group_counts, z_out, u_out, chunk_cells);
 }
 
 int mrvi_last_stage_ms(MrviHandle* h, float out_ms[4]) {

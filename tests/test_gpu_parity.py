@@ -227,3 +227,49 @@ def test_tc_fused_near_duplicate_samples(built_library):
     assert (np.abs(res["cell"] - dref) / scale).max() < TOL["tc"]
     assert (np.abs(res["cell"][:, 6, 7] - dref[:, 6, 7]) / scale[:, 0, 0]).max() < 2e-4
     h.close()
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-5), ("tc", 1e-3)])
+def test_latent_representation_api(built_library, precision, tol):
+    """get_latent_representation (reference `_model.py:221-271`): u, and z of each cell for its own sample."""
+    ad = mrvi_b200.synthetic_iid(n_obs=250, n_vars=80, n_sample=6, seed=5)
+    dims = mrvi_b200.MrviDims(n_input=80, n_sample=6)
+    params = mrvi_b200.init_params(dims, seed=2)
+    model = mrvi_b200.MrVI(ad, params, sample_key="sample_str", precision=precision)
+    sid = model._sample_codes(ad)
+    p64 = orc.cast_params(params, np.float64)
+    u_ref = orc.encoder_xu_mean(p64, ad.X.astype(np.float64), sid)
+    z_ref = orc.inference_z(p64, ad.X.astype(np.float64), sid, sid)
+    u = model.get_latent_representation()
+    z = model.get_latent_representation(give_z=True)
+    assert u.shape == (250, 10) and z.shape == (250, 30)
+    assert _relerr(u, u_ref) < 2e-5
+    assert _relerr(z, z_ref) < tol
+    sub = model.get_latent_representation(indices=[5, 3, 200])
+    assert np.array_equal(sub, u[[5, 3, 200]]) or _relerr(sub, u_ref[[5, 3, 200]]) < 2e-5
+    model.close()
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tc"])
+def test_sparse_csr_input_equals_dense(built_library, precision):
+    """scipy CSR X goes through mrvi_run_host_csr (non-zeros over PCIe, densify on the GPU): bit-identical to dense."""
+    import scipy.sparse as sp
+
+    dims = mrvi_b200.MrviDims(n_input=150, n_sample=9)
+    params, h = _model(dims, seed=5, precision=precision)
+    X, sid = _inputs(777, 150, 9, seed=4)
+    X[5] = 0  # an all-zero cell
+    codes = [np.random.default_rng(0).integers(0, 3, size=777).astype(np.int32)]
+    a = h.run_host(X, sid, codes, [3], keep_cell=True, want_u=True)
+    b = h.run_host(sp.csr_matrix(X), sid, codes, [3], keep_cell=True, want_u=True, chunk_cells=200)
+    assert np.array_equal(a["u"], b["u"])
+    assert np.array_equal(a["cell"], b["cell"])
+    assert np.allclose(a["group_sums"][0], b["group_sums"][0], rtol=1e-6)
+    # through the host API with a sparse AnnData-like object
+    ad = mrvi_b200.SimpleAnnData(sp.csr_matrix(X), mrvi_b200.synthetic_iid(n_obs=777, n_vars=150, n_sample=9, seed=1).obs)
+    ad.obs["sample"] = sid
+    model = mrvi_b200.MrVI(ad, params, sample_key="sample", precision=precision)
+    out = model.get_local_sample_distances(groupby="labels")
+    assert np.array_equal(np.asarray(out["cell"].values), a["cell"])
+    model.close()
+    h.close()
