@@ -41,47 +41,74 @@ struct EncTail {
 __device__ __forceinline__ float f16lo(uint32_t w) { return __half2float(__ushort_as_half((unsigned short)(w & 0xFFFFu))); }
 __device__ __forceinline__ float f16hi(uint32_t w) { return __half2float(__ushort_as_half((unsigned short)(w >> 16))); }
 
-// One tail epilogue for this thread's row: y = act(LN(D * scale + bias) * g + b) [+ add] [+ residual],
-// written back in place as the next A operand ([16 hi words | 16 lo words] per 32-column chunk).
-// ACT: 1 relu, 2 gelu.  g may be null (no scale).  t_res: TMEM address of the residual's region or 0.
+__device__ __forceinline__ void tmem_ld16f(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void enc_tail_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// One tail epilogue, two threads per row: thread (row, half) owns columns [64 half, 64 half + 64) in four
+// 16-column sub-chunks.   y = act(LN(D * scale + bias) * g + b) [+ add] [+ residual], written back in place
+// as the next A operand: per 16-column chunk [8 hi words | 8 lo words] (f16 pairs), so K slice ks of the
+// next MMA reads hi at column 16 ks and lo at 16 ks + 8.  LayerNorm partial sums are exchanged through
+// shared memory.  ACT: 1 relu, 2 gelu.  g may be null.  t_res: TMEM address of the residual region or 0.
 template <int ACT>
-__device__ __forceinline__ void enc_ep(uint32_t t_d, uint32_t t_res, float scale, const float* __restrict__ bias,
-                                       const float* __restrict__ g, const float* __restrict__ b,
-                                       const float* __restrict__ add) {
+__device__ __forceinline__ void enc_ep(uint32_t t_d, uint32_t t_res, int half, int row, float2* xch, float scale,
+                                       const float* __restrict__ bias, const float* __restrict__ g,
+                                       const float* __restrict__ b, const float* __restrict__ add) {
   float s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
   for (int p = 0; p < 4; ++p) {
-    float v[32];
-    tmem_ld32(t_d + p * 32, v);
+    const int c0 = half * 64 + p * 16;
+    float v[16];
+    tmem_ld16f(t_d + c0, v);
     tmem_ld_wait();
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + p * 32) + q);
+    for (int q = 0; q < 4; ++q) {
+      const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + c0) + q);
       const float x0 = fmaf(v[4 * q], scale, b4.x), x1 = fmaf(v[4 * q + 1], scale, b4.y);
       const float x2 = fmaf(v[4 * q + 2], scale, b4.z), x3 = fmaf(v[4 * q + 3], scale, b4.w);
       s1 += (x0 + x1) + (x2 + x3);
       s2 = fmaf(x0, x0, s2); s2 = fmaf(x1, x1, s2); s2 = fmaf(x2, x2, s2); s2 = fmaf(x3, x3, s2);
     }
   }
+  xch[half * 128 + row] = make_float2(s1, s2);
+  enc_tail_sync();
+  const float2 o = xch[(half ^ 1) * 128 + row];
+  s1 += o.x; s2 += o.y;
   const float mean = s1 * (1.0f / 128);
   const float var = fmaxf(fmaf(s2, 1.0f / 128, -mean * mean), 0.f);
   const float rstd = 1.0f / sqrtf(var + kLnEps);
   const float nb = -mean * rstd;
 #pragma unroll 1
   for (int p = 0; p < 4; ++p) {
-    float v[32];
-    uint32_t rw[32];
-    tmem_ld32(t_d + p * 32, v);
-    if (t_res) tmem_ld32(t_res + p * 32, reinterpret_cast<float*>(rw));
+    const int c0 = half * 64 + p * 16;
+    float v[16];
+    uint32_t rw[16];
+    tmem_ld16f(t_d + c0, v);
+    if (t_res) tmem_ld16f(t_res + c0, reinterpret_cast<float*>(rw));
     tmem_ld_wait();
-    uint32_t out[32];
+    uint32_t out[16];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const float4 bi = __ldg(reinterpret_cast<const float4*>(bias + p * 32) + q);
-      const float4 b4 = __ldg(reinterpret_cast<const float4*>(b + p * 32) + q);
+    for (int q = 0; q < 4; ++q) {
+      const float4 bi = __ldg(reinterpret_cast<const float4*>(bias + c0) + q);
+      const float4 b4 = __ldg(reinterpret_cast<const float4*>(b + c0) + q);
       float4 g4 = make_float4(1.f, 1.f, 1.f, 1.f), a4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (g) g4 = __ldg(reinterpret_cast<const float4*>(g + p * 32) + q);
-      if (add) a4 = __ldg(reinterpret_cast<const float4*>(add + p * 32) + q);
+      if (g) g4 = __ldg(reinterpret_cast<const float4*>(g + c0) + q);
+      if (add) a4 = __ldg(reinterpret_cast<const float4*>(add + c0) + q);
       float y[4];
       const float xs[4] = {fmaf(v[4 * q], scale, bi.x), fmaf(v[4 * q + 1], scale, bi.y), fmaf(v[4 * q + 2], scale, bi.z),
                            fmaf(v[4 * q + 3], scale, bi.w)};
@@ -89,23 +116,25 @@ __device__ __forceinline__ void enc_ep(uint32_t t_d, uint32_t t_res, float scale
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         float t = fmaf(fmaf(xs[e], rstd, nb), gs[e], bs[e]);
-        t = (ACT == 1) ? fmaxf(t, 0.f) : gelu_tanh_f(t);
+        t = (ACT == 1) ? fmaxf(t, 0.f) : gelu_fast(t);
         y[e] = t + as[e];
       }
-      if (t_res) {  // residual = previous activation (hi + lo), element 2j in the low halves of words j / 16+j
-        const uint32_t h0 = rw[2 * q], l0 = rw[16 + 2 * q], h1 = rw[2 * q + 1], l1 = rw[16 + 2 * q + 1];
+      if (t_res) {  // residual = previous activation (hi + lo): element 2j of the chunk in the low halves of words j / 8+j
+        const uint32_t h0 = rw[2 * q], l0 = rw[8 + 2 * q], h1 = rw[2 * q + 1], l1 = rw[8 + 2 * q + 1];
         y[0] += f16lo(h0) + f16lo(l0); y[1] += f16hi(h0) + f16hi(l0);
         y[2] += f16lo(h1) + f16lo(l1); y[3] += f16hi(h1) + f16hi(l1);
       }
-      split2(y[0], y[1], out[2 * q], out[16 + 2 * q]);
-      split2(y[2], y[3], out[2 * q + 1], out[16 + 2 * q + 1]);
+      split2(y[0], y[1], out[2 * q], out[8 + 2 * q]);
+      split2(y[2], y[3], out[2 * q + 1], out[8 + 2 * q + 1]);
     }
-    tmem_st32(t_d + p * 32, out);
+    tmem_st16(t_d + c0, out);
   }
   tmem_st_wait();
 }
 
-__global__ void __launch_bounds__(kEncThreads, 2)
+constexpr int kEnc2Threads = 320;  // 8 producer / epilogue warps + MMA warp + loader warp
+
+__global__ void __launch_bounds__(kEnc2Threads, 2)
 k_encoder_tc(const float* __restrict__ X, int64_t ldx, const int32_t* __restrict__ sample_idx, int64_t n_cells, int G,
              EncTc enc, const __grid_constant__ EncTail tail, CellBuf cb, int x_vec_ok) {
   extern __shared__ uint8_t smem_raw[];
@@ -124,28 +153,29 @@ k_encoder_tc(const float* __restrict__ X, int64_t ldx, const int32_t* __restrict
   const int NL = tail.n_layers;
 
   if (tid == 0) {
-    for (int s = 0; s < kEncStages; ++s) { mbar_init(full + s, 129); mbar_init(empty + s, 1); }
+    for (int s = 0; s < kEncStages; ++s) { mbar_init(full + s, 257); mbar_init(empty + s, 1); }
     mbar_init(acc_bar, 1);
-    mbar_init(bar_a, 128);
+    mbar_init(bar_a, 256);
     mbar_init(bar_d, 1);
     mbar_init(bar_w, 1);
     fence_mbar_init();
   }
-  if (warp == 4) tmem_alloc(tmem_slot, 256);
+  if (warp == 8) tmem_alloc(tmem_slot, 256);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  float2* xch = reinterpret_cast<float2*>(tmem_slot + 4);  // [2][128] partial LayerNorm sums
   uint8_t* wbuf = smem;  // tail weights overlay pipeline stages 0-1 (66 KB) once phase 1 has drained
 
-  if (warp < 4) {
-    // ------------------------------------------------------------ phase 1 producers
+  if (warp < 8) {
+    // ------------------------------------------------------------ phase 1 producers (256 threads, 2 (row, chunk) pairs each)
     const int rsub = lane >> 2, chunk = lane & 3;
-    float4 cur[8], nxt[8];
-    auto load = [&](int kb, float4 (&dst)[8]) {
+    float4 cur[4], nxt[4];
+    auto load = [&](int kb, float4 (&dst)[4]) {
 #pragma unroll
-      for (int p = 0; p < 4; ++p) {
-        const int row = warp * 32 + p * 8 + rsub;
+      for (int p = 0; p < 2; ++p) {
+        const int row = warp * 16 + p * 8 + rsub;
         const int64_t cell = cell0 + row;
         const int k = kb * kEncBK + chunk * 8;
         float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
@@ -168,14 +198,14 @@ k_encoder_tc(const float* __restrict__ X, int64_t ldx, const int32_t* __restrict
     };
     // two K blocks of register prefetch ahead of the block being converted (memory-level parallelism:
     // 3 x 16 KB of loads in flight per CTA)
-    float4 nx2[8];
-    auto convert = [&](int kb, const float4 (&src)[8]) {
+    float4 nx2[4];
+    auto convert = [&](int kb, const float4 (&src)[4]) {
       const int s = kb % kEncStages;
       if (kb >= kEncStages) mbar_wait(empty + s, ((kb / kEncStages) - 1) & 1);
       uint8_t* stage = smem + s * kEncStageBytes;
 #pragma unroll
-      for (int p = 0; p < 4; ++p) {
-        const int row = warp * 32 + p * 8 + rsub;
+      for (int p = 0; p < 2; ++p) {
+        const int row = warp * 16 + p * 8 + rsub;
         const float4 a = src[2 * p], b = src[2 * p + 1];
         uint32_t h[4], l[4];
         split2(log1p_fast(a.x), log1p_fast(a.y), h[0], l[0]);
@@ -202,18 +232,19 @@ k_encoder_tc(const float* __restrict__ X, int64_t ldx, const int32_t* __restrict
         convert(kb + 2, nx2);
       }
     }
-    // ------------------------------------------------------------ phase 2 epilogues (thread = cell = TMEM lane)
-    const int row = tid;
+    // ------------------------------------------------------------ phase 2 epilogues: thread (row, half), row = TMEM lane
+    const int row = tid & 127, half = tid >> 7;
     const int64_t cell = cell0 + row;
     const bool valid = cell < n_cells;
     int sid = valid ? sample_idx[cell] : 0;
     sid = min(max(sid, 0), tail.S - 1);
-    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
     const uint32_t t_reg[2] = {tmem_base + lane_off, tmem_base + 128 + lane_off};
     mbar_wait(acc_bar, 0);
     tc_fence_after();
     // ConditionalNormalization_0 + gelu on H1 = D / 2^8 + b0          (reference _module.py:190-195)
-    enc_ep<2>(t_reg[0], 0u, 1.0f / kEncWScale, enc.b0, tail.gamma0 + (size_t)sid * 128, tail.beta0 + (size_t)sid * 128, nullptr);
+    enc_ep<2>(t_reg[0], 0u, half, row, xch, 1.0f / kEncWScale, enc.b0, tail.gamma0 + (size_t)sid * 128,
+              tail.beta0 + (size_t)sid * 128, nullptr);
     tc_fence_before();
     mbar_arrive(bar_a);
     for (int li = 0; li < NL; ++li) {
@@ -221,12 +252,12 @@ k_encoder_tc(const float* __restrict__ X, int64_t ldx, const int32_t* __restrict
       tc_fence_after();
       const uint32_t t_d = t_reg[(li + 1) & 1], t_a = t_reg[li & 1];
       if (li == 0) {        // Dense_1 -> ConditionalNormalization_1 + gelu, + sample_effect   (reference _module.py:190-199)
-        enc_ep<2>(t_d, 0u, 1.0f, tail.bl[0], tail.gamma1 + (size_t)sid * 128, tail.beta1 + (size_t)sid * 128,
+        enc_ep<2>(t_d, 0u, half, row, xch, 1.0f, tail.bl[0], tail.gamma1 + (size_t)sid * 128, tail.beta1 + (size_t)sid * 128,
                   tail.sample_effect + (size_t)sid * 128);
       } else if (li & 1) {  // ResnetBlock Dense_0: relu(LN(.)) + h                            (reference _components.py:41-49)
-        enc_ep<1>(t_d, t_a, 1.0f, tail.bl[li], tail.lg[li], tail.lb[li], nullptr);
+        enc_ep<1>(t_d, t_a, half, row, xch, 1.0f, tail.bl[li], tail.lg[li], tail.lb[li], nullptr);
       } else {              // ResnetBlock Dense_out: relu(LN(.))                               (reference _components.py:49-51)
-        enc_ep<1>(t_d, 0u, 1.0f, tail.bl[li], tail.lg[li], tail.lb[li], nullptr);
+        enc_ep<1>(t_d, 0u, half, row, xch, 1.0f, tail.bl[li], tail.lg[li], tail.lb[li], nullptr);
       }
       tc_fence_before();
       mbar_arrive(bar_a);
@@ -234,7 +265,7 @@ k_encoder_tc(const float* __restrict__ X, int64_t ldx, const int32_t* __restrict
     // ---- mean head: u, LN(u), query tokens, z_base                                          (reference _components.py:95)
     mbar_wait(bar_d, NL & 1);
     tc_fence_after();
-    {
+    if (half == 0) {
       float u[32];
       tmem_ld32(t_reg[(NL + 1) & 1], u);
       tmem_ld_wait();
@@ -285,7 +316,7 @@ k_encoder_tc(const float* __restrict__ X, int64_t ldx, const int32_t* __restrict
       }
     }
     tc_fence_before();
-  } else if (warp == 4) {
+  } else if (warp == 8) {
     // ------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_f16(128);
@@ -320,10 +351,10 @@ k_encoder_tc(const float* __restrict__ X, int64_t ldx, const int32_t* __restrict
         const uint32_t t_a = tmem_base + (li & 1) * 128, t_d = tmem_base + ((li + 1) & 1) * 128;
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {
-          const uint32_t a = t_a + (ks >> 1) * 32 + (ks & 1) * 8;
+          const uint32_t a = t_a + ks * 16;  // [8 hi words | 8 lo words] per 16-column chunk
           const uint64_t bh = umma_desc(w_hi + ks * 2 * lbo, lbo, 128), bl = umma_desc(w_lo + ks * 2 * lbo, lbo, 128);
           umma_f16_ts(t_d, a, bh, idn, ks == 0 ? 0u : 1u);
-          umma_f16_ts(t_d, a + 16, bh, idn, 1u);
+          umma_f16_ts(t_d, a + 8, bh, idn, 1u);
           umma_f16_ts(t_d, a, bl, idn, 1u);
         }
         umma_commit(bar_d);
@@ -349,7 +380,7 @@ k_encoder_tc(const float* __restrict__ X, int64_t ldx, const int32_t* __restrict
     }
   }
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem_base, 256);
+  if (warp == 8) tmem_dealloc(tmem_base, 256);
 }
 
 // ---- host side: pack the tail weights
@@ -414,7 +445,7 @@ inline int enc_tail_build(EncTail& t, const NetW& net, const tc_detail::PMap& pm
   }
   t.Lq = net.Lq; t.L = net.L; t.S = net.S;
   if (cudaFuncSetAttribute(k_encoder_tc, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)((size_t)kEncStages * kEncStageBytes + 256 + 1024)) != cudaSuccess) {
+                           (int)((size_t)kEncStages * kEncStageBytes + 4096 + 1024)) != cudaSuccess) {
     g_tc_error = "cudaFuncSetAttribute(k_encoder_tc) failed";
     return MRVI_ERR_CUDA;
   }
@@ -426,7 +457,7 @@ inline void enc_full_tc_launch(const EncTc& enc, const EncTail& tail, const floa
                                int G, const CellBuf& cb, cudaStream_t st) {
   const int grid = (int)((n + 127) / 128);
   const int vec_ok = ((ldx % 4) == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
-  k_encoder_tc<<<grid, kEncThreads, enc.smem_bytes, st>>>(X, ldx, sid, n, G, enc, tail, cb, vec_ok);
+  k_encoder_tc<<<grid, kEnc2Threads, (size_t)kEncStages * kEncStageBytes + 4096 + 1024, st>>>(X, ldx, sid, n, G, enc, tail, cb, vec_ok);
 }
 
 }  // namespace mrvi

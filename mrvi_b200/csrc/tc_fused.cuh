@@ -102,6 +102,25 @@ __device__ __forceinline__ float sqrt_approx(float x) {
 __device__ __forceinline__ float h2f_lo(uint32_t w) { return __half2float(__ushort_as_half((unsigned short)(w & 0xFFFFu))); }
 __device__ __forceinline__ float h2f_hi(uint32_t w) { return __half2float(__ushort_as_half((unsigned short)(w >> 16))); }
 
+// ---- packed fp32x2 helpers (FFMA2 / FMUL2 / FADD2 halve the issue slots of the fp32 epilogue math)
+__device__ __forceinline__ float2 gelu_fast2(float2 x) {
+  const float2 c1 = make_float2(0.7978845608028654f, 0.7978845608028654f);
+  const float2 c2 = make_float2(0.7978845608028654f * 0.044715f, 0.7978845608028654f * 0.044715f);
+  const float2 u = __fmul2_rn(x, x);
+  const float2 p = __ffma2_rn(u, c2, c1);
+  const float2 y = __fmul2_rn(x, p);
+  const float2 t = make_float2(tanh_approx(y.x), tanh_approx(y.y));
+  const float2 hx = __fmul2_rn(x, make_float2(0.5f, 0.5f));
+  return __ffma2_rn(hx, t, hx);
+}
+// (hi, lo) f16 split of a pair (see split2): the two remainders come from one FADD2
+__device__ __forceinline__ void split2v(float2 a, uint32_t& hi, uint32_t& lo) {
+  const float2 ah = make_float2(__uint_as_float(__float_as_uint(a.x) & 0xFFFFE000u), __uint_as_float(__float_as_uint(a.y) & 0xFFFFE000u));
+  const float2 r = __fadd2_rn(a, make_float2(-ah.x, -ah.y));
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(ah.y), "f"(ah.x));
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(r.y), "f"(r.x));
+}
+
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   uint32_t* r = reinterpret_cast<uint32_t*>(v);
   asm volatile(
@@ -131,15 +150,20 @@ __device__ __noinline__ float exact_d2(const uint8_t* zh, const uint8_t* zl, int
 // place per 32-column chunk as [16 hi words | 16 lo words].  g_s / b_s: shared-memory LN vectors.
 __device__ __forceinline__ void ep128(uint32_t t_lane, int half, int r, int wg, const float* g_s, const float* b_s,
                                       float2* xch) {
-  float s1 = 0.f, s2 = 0.f;
+  float2 a1 = make_float2(0.f, 0.f), a2 = make_float2(0.f, 0.f);
 #pragma unroll 1
   for (int pp = 0; pp < 2; ++pp) {
     float v[32];
     tmem_ld32(t_lane + (2 * half + pp) * 32, v);
     tmem_ld_wait();
 #pragma unroll
-    for (int i = 0; i < 32; ++i) { s1 += v[i]; s2 = fmaf(v[i], v[i], s2); }
+    for (int i = 0; i < 16; ++i) {
+      const float2 x = make_float2(v[2 * i], v[2 * i + 1]);
+      a1 = __fadd2_rn(a1, x);
+      a2 = __ffma2_rn(x, x, a2);
+    }
   }
+  float s1 = a1.x + a1.y, s2 = a2.x + a2.y;
   xch[half * 128 + r] = make_float2(s1, s2);
   wg_sync(wg);
   const float2 o = xch[(half ^ 1) * 128 + r];
@@ -147,7 +171,7 @@ __device__ __forceinline__ void ep128(uint32_t t_lane, int half, int r, int wg, 
   const float mean = s1 * (1.0f / 128);
   const float var = fmaxf(fmaf(s2, 1.0f / 128, -mean * mean), 0.f);
   const float rstd = rsqrt_approx(var + kLnEps);
-  const float nb = -mean * rstd;
+  const float2 rs2 = make_float2(rstd, rstd), nb2 = make_float2(-mean * rstd, -mean * rstd);
 #pragma unroll 1
   for (int pp = 0; pp < 2; ++pp) {
     const int p = 2 * half + pp;
@@ -159,12 +183,12 @@ __device__ __forceinline__ void ep128(uint32_t t_lane, int half, int r, int wg, 
     for (int q = 0; q < 8; ++q) {
       const float4 g4 = *reinterpret_cast<const float4*>(g_s + p * 32 + 4 * q);
       const float4 b4 = *reinterpret_cast<const float4*>(b_s + p * 32 + 4 * q);
-      const float y0 = gelu_fast(fmaf(fmaf(v[4 * q], rstd, nb), g4.x, b4.x));
-      const float y1 = gelu_fast(fmaf(fmaf(v[4 * q + 1], rstd, nb), g4.y, b4.y));
-      const float y2 = gelu_fast(fmaf(fmaf(v[4 * q + 2], rstd, nb), g4.z, b4.z));
-      const float y3 = gelu_fast(fmaf(fmaf(v[4 * q + 3], rstd, nb), g4.w, b4.w));
-      split2(y0, y1, out[2 * q], out[16 + 2 * q]);
-      split2(y2, y3, out[2 * q + 1], out[16 + 2 * q + 1]);
+      float2 x0 = __ffma2_rn(make_float2(v[4 * q], v[4 * q + 1]), rs2, nb2);
+      float2 x1 = __ffma2_rn(make_float2(v[4 * q + 2], v[4 * q + 3]), rs2, nb2);
+      x0 = gelu_fast2(__ffma2_rn(x0, make_float2(g4.x, g4.y), make_float2(b4.x, b4.y)));
+      x1 = gelu_fast2(__ffma2_rn(x1, make_float2(g4.z, g4.w), make_float2(b4.z, b4.w)));
+      split2v(x0, out[2 * q], out[16 + 2 * q]);
+      split2v(x1, out[2 * q + 1], out[16 + 2 * q + 1]);
     }
     tmem_st32(t_lane + p * 32, out);
   }
@@ -178,9 +202,14 @@ __device__ __forceinline__ void ep32(uint32_t t_lane32, int half, int r, int wg,
   float v[16];
   tmem_ld16(t_lane32 + half * 16, v);
   tmem_ld_wait();
-  float s1 = 0.f, s2 = 0.f;
+  float2 a1 = make_float2(0.f, 0.f), a2 = make_float2(0.f, 0.f);
 #pragma unroll
-  for (int i = 0; i < 16; ++i) { s1 += v[i]; s2 = fmaf(v[i], v[i], s2); }
+  for (int i = 0; i < 8; ++i) {
+    const float2 x = make_float2(v[2 * i], v[2 * i + 1]);
+    a1 = __fadd2_rn(a1, x);
+    a2 = __ffma2_rn(x, x, a2);
+  }
+  float s1 = a1.x + a1.y, s2 = a2.x + a2.y;
   xch[half * 128 + r] = make_float2(s1, s2);
   wg_sync(wg);
   const float2 o = xch[(half ^ 1) * 128 + r];
@@ -188,16 +217,18 @@ __device__ __forceinline__ void ep32(uint32_t t_lane32, int half, int r, int wg,
   const float mean = s1 * (1.0f / 32);
   const float var = fmaxf(fmaf(s2, 1.0f / 32, -mean * mean), 0.f);
   const float rstd = rsqrt_approx(var + kLnEps);
-  const float nb = -mean * rstd;
+  const float2 rs2 = make_float2(rstd, rstd), nb2 = make_float2(-mean * rstd, -mean * rstd);
 #pragma unroll
   for (int c = 0; c < 2; ++c) {
     uint32_t h[4], l[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int i0 = c * 8 + 2 * j, i1 = i0 + 1;
-      const float y0 = gelu_fast(fmaf(fmaf(v[i0], rstd, nb), g_s[half * 16 + i0], b_s[half * 16 + i0]));
-      const float y1 = gelu_fast(fmaf(fmaf(v[i1], rstd, nb), g_s[half * 16 + i1], b_s[half * 16 + i1]));
-      split2(y0, y1, h[j], l[j]);
+      const int i0 = c * 8 + 2 * j;
+      const float2 gg = *reinterpret_cast<const float2*>(g_s + half * 16 + i0);
+      const float2 bb = *reinterpret_cast<const float2*>(b_s + half * 16 + i0);
+      float2 x = __ffma2_rn(make_float2(v[i0], v[i0 + 1]), rs2, nb2);
+      x = gelu_fast2(__ffma2_rn(x, gg, bb));
+      split2v(x, h[j], l[j]);
     }
     *reinterpret_cast<uint4*>(row_h + (half * 2 + c) * 2048) = make_uint4(h[0], h[1], h[2], h[3]);
     *reinterpret_cast<uint4*>(row_l + (half * 2 + c) * 2048) = make_uint4(l[0], l[1], l[2], l[3]);
@@ -338,12 +369,13 @@ k_chain_fused_tc(const __grid_constant__ TcNet tc, CellBuf cb, int64_t n_cells, 
 
     // ================= attention features of head `half` -> A1 chunks 2*half, 2*half+1 =================
     {
-      float kvl[16];
+      float2 kv2[8];  // kv * log2(e), pairs
       const float4* kp = reinterpret_cast<const float4*>(tc.kvl + (size_t)ss * 16);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const float4 t4 = __ldg(kp + q);
-        kvl[4 * q] = t4.x; kvl[4 * q + 1] = t4.y; kvl[4 * q + 2] = t4.z; kvl[4 * q + 3] = t4.w;
+        kv2[2 * q] = make_float2(t4.x, t4.y);
+        kv2[2 * q + 1] = make_float2(t4.z, t4.w);
       }
       const float rmax = __ldg(tc.kvref + ss * 2), rmin = __ldg(tc.kvref + ss * 2 + 1);
       const float* qp = cb.q_tok + cell * 16;
@@ -354,14 +386,16 @@ k_chain_fused_tc(const __grid_constant__ TcNet tc, CellBuf cb, int64_t n_cells, 
         for (int e = 0; e < 2; ++e) {
           const float t = fmaf(a_h, __ldg(qp + it * 2 + e), b_h);
           const float off = -t * (t >= 0.f ? rmax : rmin);  // exponent <= 0 for every j
-          float den = 0.f, num = 0.f;
+          const float2 t2 = make_float2(t, t), off2 = make_float2(off, off);
+          float2 den = make_float2(0.f, 0.f), num = make_float2(0.f, 0.f);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float ex = ex2_approx(fmaf(t, kvl[j], off));
-            den += ex;
-            num = fmaf(ex, kvl[j], num);
+          for (int j = 0; j < 8; ++j) {
+            const float2 a = __ffma2_rn(t2, kv2[j], off2);
+            const float2 ex = make_float2(ex2_approx(a.x), ex2_approx(a.y));
+            den = __fadd2_rn(den, ex);
+            num = __ffma2_rn(ex, kv2[j], num);
           }
-          mm[e] = num * rcp_approx(den);  // = log2(e) * m[h,i]; 1/log2(e) is folded into B1 / B2a
+          mm[e] = (num.x + num.y) * rcp_approx(den.x + den.y);  // = log2(e) * m[h,i]; 1/log2(e) is folded into B1 / B2a
         }
         uint32_t hw, lw;
         split2(mm[0], mm[1], hw, lw);
