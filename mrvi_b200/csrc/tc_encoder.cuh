@@ -20,7 +20,7 @@ namespace mrvi {
 
 constexpr int kEncMaxLayers = 1 + 2 * kMaxBlocks;
 constexpr int kEncLayerBytes = 2 * 128 * 128 * 2;  // hi | lo of a [128 x 128] f16 operand
-constexpr int kEncHeadBytes = 2 * 32 * 128 * 2;    // hi | lo of the [32 x 128] mean head
+constexpr int kEncHeadMaxN = 96;                   // mean head [u | z_base] columns, padded to a multiple of 32
 
 struct EncTail {
   const float *gamma0, *beta0, *gamma1, *beta1, *sample_effect;  // [S][128]
@@ -29,12 +29,14 @@ struct EncTail {
   const float* lg[kEncMaxLayers];    // LayerNorm scale [128] (null for the conditional layer)
   const float* lb[kEncMaxLayers];
   int n_layers;                      // 1 + 2 * n_blocks
-  const uint8_t* whead;              // mean head [32 x 128] hi | lo
-  const float* bhead;                // [Lq]
+  const uint8_t* whead;              // head [Nh x 128] hi | lo:  h -> [u (Lq) | z_base (L)]  (z_base folded: W_mean . W_zb)
+  const float* bhead;                // [Nh]  (b_mean ; b_mean . W_zb + b_zb)
+  int Nh;                            // padded head width (32, 64 or 96)
   const float *uln_g, *uln_b;        // [Lq]
   const float* wq;                   // [Lq][16]   DenseGeneral_0 (query tokens)
-  const float *wzb, *bzb;            // [Lq][L], [L]  qz/Dense_0 (null when isomorphic)
+  int has_zbase;                     // 0: isomorphic u/z (z_base = u)
   int Lq, L, S;
+  int sm_count;
   bool ready;
 };
 
@@ -132,47 +134,68 @@ __device__ __forceinline__ void enc_ep(uint32_t t_d, uint32_t t_res, int half, i
   tmem_st_wait();
 }
 
-constexpr int kEnc2Threads = 320;  // 8 producer / epilogue warps + MMA warp + loader warp
+// ------------------------------------------------------------------------------------------
+// Persistent, warp-specialised encoder: ONE CTA per SM loops over 128-cell tiles.
+//   warps 0-7   producers: stream X (coalesced LDG.128, two K blocks of register prefetch that runs across
+//               tile boundaries), log1p, (hi, lo) split, K-major stores        -> HBM is busy all the time
+//   warps 8-15  tail epilogues of the PREVIOUS tile (two threads per row), concurrently with the stream
+//   warp 16     phase-1 MMA issuer (accumulator double-buffered in TMEM: ACC[tile & 1])
+//   warp 17     tail MMA issuer (A operand from TMEM)          warp 18 / 19   TMA loaders (W0 blocks / layer weights)
+// One CTA per SM also halves the number of concurrently streamed rows (DRAM row-buffer locality):
+// measured 3.45 TB/s for phase 1 alone with 148 CTAs versus 1.4 TB/s effective with two CTAs per SM.
+// TMEM: ACC0 [0,128)  ACC1 [128,256)  T0 [256,384)  T1 [384,512).
+// ------------------------------------------------------------------------------------------
+constexpr int kEncPStages = 4;
+constexpr int kEncPThreads = 640;
+constexpr size_t kEncPSmem = (size_t)kEncPStages * kEncStageBytes + kEncLayerBytes + 4096 + 1024;
 
-__global__ void __launch_bounds__(kEnc2Threads, 2)
+__global__ void __launch_bounds__(kEncPThreads, 1)
 k_encoder_tc(const float* __restrict__ X, int64_t ldx, const int32_t* __restrict__ sample_idx, int64_t n_cells, int G,
              EncTc enc, const __grid_constant__ EncTail tail, CellBuf cb, int x_vec_ok) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kEncStages * kEncStageBytes);
-  uint64_t* full = bars;                    // [stages] producers (128) + B expect_tx (1)
-  uint64_t* empty = bars + kEncStages;      // [stages] tcgen05.commit
-  uint64_t* acc_bar = bars + 2 * kEncStages;
-  uint64_t* bar_a = acc_bar + 1;            // tail: activation of the next layer is in TMEM (128 arrivals)
-  uint64_t* bar_d = acc_bar + 2;            // tail: layer MMAs committed
-  uint64_t* bar_w = acc_bar + 3;            // tail: layer weights landed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 4);
+  // no-swizzle UMMA operands and bulk copies need 16-byte alignment only; keeping the plain array (no integer
+  // re-alignment) lets the compiler see the shared address space (LDS/STS instead of generic LD/ST)
+  extern __shared__ __align__(1024) uint8_t smem_tc[];
+  uint8_t* const smem = smem_tc;
+  uint8_t* wbuf = smem + (size_t)kEncPStages * kEncStageBytes;              // tail layer weights (hi | lo)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(wbuf + kEncLayerBytes);
+  uint64_t* full = bars;                       // [stages] producers (256) + W0 expect_tx (1)
+  uint64_t* empty = full + kEncPStages;        // [stages] tcgen05.commit
+  uint64_t* acc_full = empty + kEncPStages;    // [2] phase-1 accumulator of a tile complete
+  uint64_t* acc_free = acc_full + 2;           // [2] accumulator region may be overwritten
+  uint64_t* bar_a = acc_free + 2;              // tail: next layer's activation is in TMEM (256 arrivals)
+  uint64_t* bar_d = bar_a + 1;                 // tail: layer MMAs complete
+  uint64_t* bar_w = bar_d + 1;                 // tail: layer weights landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_w + 1);
+  float2* xch = reinterpret_cast<float2*>(tmem_slot + 4);                   // [2][128] partial LayerNorm sums
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nkb = enc.n_kblocks;
-  const int64_t cell0 = (int64_t)blockIdx.x * 128;
   const int NL = tail.n_layers;
+  const int64_t n_tiles = (n_cells + 127) / 128;
+  const int64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
   if (tid == 0) {
-    for (int s = 0; s < kEncStages; ++s) { mbar_init(full + s, 257); mbar_init(empty + s, 1); }
-    mbar_init(acc_bar, 1);
+    for (int s = 0; s < kEncPStages; ++s) { mbar_init(full + s, 257); mbar_init(empty + s, 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(acc_full + b, 1); mbar_init(acc_free + b, 1); }
     mbar_init(bar_a, 256);
     mbar_init(bar_d, 1);
     mbar_init(bar_w, 1);
     fence_mbar_init();
   }
-  if (warp == 8) tmem_alloc(tmem_slot, 256);
+  if (warp == 16) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  float2* xch = reinterpret_cast<float2*>(tmem_slot + 4);  // [2][128] partial LayerNorm sums
-  uint8_t* wbuf = smem;  // tail weights overlay pipeline stages 0-1 (66 KB) once phase 1 has drained
 
   if (warp < 8) {
-    // ------------------------------------------------------------ phase 1 producers (256 threads, 2 (row, chunk) pairs each)
+    // ------------------------------------------------------------ producers: flat loop over (tile, K block)
     const int rsub = lane >> 2, chunk = lane & 3;
-    float4 cur[4], nxt[4];
-    auto load = [&](int kb, float4 (&dst)[4]) {
+    const int64_t total = my_tiles * nkb;
+    float4 cur[4], nxt[4], nx2[4];
+    auto load = [&](int64_t g, float4 (&dst)[4]) {
+      const int64_t ti = g / nkb;
+      const int kb = (int)(g - ti * nkb);
+      const int64_t cell0 = ((int64_t)blockIdx.x + ti * gridDim.x) * 128;
 #pragma unroll
       for (int p = 0; p < 2; ++p) {
         const int row = warp * 16 + p * 8 + rsub;
@@ -196,12 +219,10 @@ k_encoder_tc(const float* __restrict__ X, int64_t ldx, const int32_t* __restrict
         dst[2 * p + 1] = b;
       }
     };
-    // two K blocks of register prefetch ahead of the block being converted (memory-level parallelism:
-    // 3 x 16 KB of loads in flight per CTA)
-    float4 nx2[4];
-    auto convert = [&](int kb, const float4 (&src)[4]) {
-      const int s = kb % kEncStages;
-      if (kb >= kEncStages) mbar_wait(empty + s, ((kb / kEncStages) - 1) & 1);
+    auto convert = [&](int64_t g, const float4 (&src)[4]) {
+      const int s = (int)(g % kEncPStages);
+      const int64_t use = g / kEncPStages;
+      if (use > 0) mbar_wait(empty + s, (uint32_t)((use - 1) & 1));
       uint8_t* stage = smem + s * kEncStageBytes;
 #pragma unroll
       for (int p = 0; p < 2; ++p) {
@@ -218,172 +239,223 @@ k_encoder_tc(const float* __restrict__ X, int64_t ldx, const int32_t* __restrict
       fence_proxy_async();
       mbar_arrive(full + s);
     };
-    load(0, cur);
-    if (nkb > 1) load(1, nxt);
-    for (int kb = 0; kb < nkb; kb += 3) {
-      if (kb + 2 < nkb) load(kb + 2, nx2);
-      convert(kb, cur);
-      if (kb + 1 < nkb) {
-        if (kb + 3 < nkb) load(kb + 3, cur);
-        convert(kb + 1, nxt);
+    if (total > 0) load(0, cur);
+    if (total > 1) load(1, nxt);
+    for (int64_t g = 0; g < total; g += 3) {
+      if (g + 2 < total) load(g + 2, nx2);
+      convert(g, cur);
+      if (g + 1 < total) {
+        if (g + 3 < total) load(g + 3, cur);
+        convert(g + 1, nxt);
       }
-      if (kb + 2 < nkb) {
-        if (kb + 4 < nkb) load(kb + 4, nxt);
-        convert(kb + 2, nx2);
+      if (g + 2 < total) {
+        if (g + 4 < total) load(g + 4, nxt);
+        convert(g + 2, nx2);
       }
     }
-    // ------------------------------------------------------------ phase 2 epilogues: thread (row, half), row = TMEM lane
-    const int row = tid & 127, half = tid >> 7;
-    const int64_t cell = cell0 + row;
-    const bool valid = cell < n_cells;
-    int sid = valid ? sample_idx[cell] : 0;
-    sid = min(max(sid, 0), tail.S - 1);
+  } else if (warp < 16) {
+    // ------------------------------------------------------------ tail epilogues: thread (row, half), row = TMEM lane
+    const int et = tid - 256;
+    const int row = et & 127, half = et >> 7;
     const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
-    const uint32_t t_reg[2] = {tmem_base + lane_off, tmem_base + 128 + lane_off};
-    mbar_wait(acc_bar, 0);
-    tc_fence_after();
-    // ConditionalNormalization_0 + gelu on H1 = D / 2^8 + b0          (reference _module.py:190-195)
-    enc_ep<2>(t_reg[0], 0u, half, row, xch, 1.0f / kEncWScale, enc.b0, tail.gamma0 + (size_t)sid * 128,
-              tail.beta0 + (size_t)sid * 128, nullptr);
-    tc_fence_before();
-    mbar_arrive(bar_a);
-    for (int li = 0; li < NL; ++li) {
-      mbar_wait(bar_d, li & 1);
+    int64_t c = 0;  // running layer counter (phases of bar_a / bar_d / bar_w)
+    for (int64_t ti = 0; ti < my_tiles; ++ti) {
+      const int64_t cell = ((int64_t)blockIdx.x + ti * gridDim.x) * 128 + row;
+      const bool valid = cell < n_cells;
+      int sid = valid ? sample_idx[cell] : 0;
+      sid = min(max(sid, 0), tail.S - 1);
+      const uint32_t t_acc = tmem_base + (uint32_t)(ti & 1) * 128 + lane_off;
+      const uint32_t t_T[2] = {tmem_base + 256 + lane_off, tmem_base + 384 + lane_off};
+      mbar_wait(acc_full + (ti & 1), (uint32_t)((ti >> 1) & 1));
       tc_fence_after();
-      const uint32_t t_d = t_reg[(li + 1) & 1], t_a = t_reg[li & 1];
-      if (li == 0) {        // Dense_1 -> ConditionalNormalization_1 + gelu, + sample_effect   (reference _module.py:190-199)
-        enc_ep<2>(t_d, 0u, half, row, xch, 1.0f, tail.bl[0], tail.gamma1 + (size_t)sid * 128, tail.beta1 + (size_t)sid * 128,
-                  tail.sample_effect + (size_t)sid * 128);
-      } else if (li & 1) {  // ResnetBlock Dense_0: relu(LN(.)) + h                            (reference _components.py:41-49)
-        enc_ep<1>(t_d, t_a, half, row, xch, 1.0f, tail.bl[li], tail.lg[li], tail.lb[li], nullptr);
-      } else {              // ResnetBlock Dense_out: relu(LN(.))                               (reference _components.py:49-51)
-        enc_ep<1>(t_d, 0u, half, row, xch, 1.0f, tail.bl[li], tail.lg[li], tail.lb[li], nullptr);
-      }
+      // ConditionalNormalization_0 + gelu on H1 = D / 2^8 + b0          (reference _module.py:190-195)
+      enc_ep<2>(t_acc, 0u, half, row, xch, 1.0f / kEncWScale, enc.b0, tail.gamma0 + (size_t)sid * 128,
+                tail.beta0 + (size_t)sid * 128, nullptr);
       tc_fence_before();
       mbar_arrive(bar_a);
-    }
-    // ---- mean head: u, LN(u), query tokens, z_base                                          (reference _components.py:95)
-    mbar_wait(bar_d, NL & 1);
-    tc_fence_after();
-    if (half == 0) {
-      float u[32];
-      tmem_ld32(t_reg[(NL + 1) & 1], u);
-      tmem_ld_wait();
-      const int Lq = tail.Lq, L = tail.L;
-      float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-      for (int l = 0; l < 32; ++l) {
-        u[l] = (l < Lq) ? u[l] + __ldg(tail.bhead + l) : 0.f;
-        s1 += u[l];
-        s2 = fmaf(u[l], u[l], s2);
+      for (int li = 0; li < NL; ++li, ++c) {
+        mbar_wait(bar_d, (uint32_t)(c & 1));
+        tc_fence_after();
+        const uint32_t t_d = t_T[li & 1], t_a = t_T[(li + 1) & 1];  // A region of an odd layer = T[(li-1)&1]
+        if (li == 0) {        // Dense_1 -> ConditionalNormalization_1 + gelu, + sample_effect   (reference _module.py:190-199)
+          enc_ep<2>(t_d, 0u, half, row, xch, 1.0f, tail.bl[0], tail.gamma1 + (size_t)sid * 128, tail.beta1 + (size_t)sid * 128,
+                    tail.sample_effect + (size_t)sid * 128);
+        } else if (li & 1) {  // ResnetBlock Dense_0: relu(LN(.)) + h                            (reference _components.py:41-49)
+          enc_ep<1>(t_d, t_a, half, row, xch, 1.0f, tail.bl[li], tail.lg[li], tail.lb[li], nullptr);
+        } else {              // ResnetBlock Dense_out: relu(LN(.))                               (reference _components.py:49-51)
+          enc_ep<1>(t_d, 0u, half, row, xch, 1.0f, tail.bl[li], tail.lg[li], tail.lb[li], nullptr);
+        }
+        tc_fence_before();
+        mbar_arrive(bar_a);
       }
-      const float mean = s1 / (float)Lq;
-      const float var = fmaxf(s2 / (float)Lq - mean * mean, 0.f);
-      const float rstd = 1.0f / sqrtf(var + kLnEps);
-      float ul[32];
+      // ---- mean head: u, LN(u), query tokens, z_base                                          (reference _components.py:95)
+      mbar_wait(bar_d, (uint32_t)(c & 1));
+      ++c;
+      tc_fence_after();
+      const int Lq = tail.Lq, L = tail.L;
+      if (half == 0) {
+        // u = D[:, 0:Lq] + b ; LN(u) ; query tokens = LN(u) . Wq            (reference _module.py:142, _components.py:195-197)
+        float u[32];
+        tmem_ld32(t_T[NL & 1], u);
+        tmem_ld_wait();
+        float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-      for (int l = 0; l < 32; ++l)
-        ul[l] = (l < Lq) ? (u[l] - mean) * (rstd * __ldg(tail.uln_g + l)) + __ldg(tail.uln_b + l) : 0.f;
-      if (valid) {
+        for (int l = 0; l < 32; ++l) {
+          u[l] = (l < Lq) ? u[l] + __ldg(tail.bhead + l) : 0.f;
+          s1 += u[l];
+          s2 = fmaf(u[l], u[l], s2);
+        }
+        const float mean = s1 / (float)Lq;
+        const float var = fmaxf(s2 / (float)Lq - mean * mean, 0.f);
+        const float rstd = 1.0f / sqrtf(var + kLnEps);
+        if (valid) {
+          float qt[16];
 #pragma unroll
-        for (int l = 0; l < 32; ++l)
-          if (l < Lq) { cb.u[cell * Lq + l] = u[l]; cb.u_ln[cell * Lq + l] = ul[l]; }
-        float qt[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) qt[i] = 0.f;
-#pragma unroll
-        for (int l = 0; l < 32; ++l)
-          if (l < Lq) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) qt[i] = fmaf(ul[l], __ldg(tail.wq + l * 16 + i), qt[i]);
-          }
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          reinterpret_cast<float4*>(cb.q_tok + cell * 16)[i] = make_float4(qt[4 * i], qt[4 * i + 1], qt[4 * i + 2], qt[4 * i + 3]);
-        if (tail.wzb != nullptr) {
-          for (int j = 0; j < L; ++j) {
-            float a = __ldg(tail.bzb + j);
-#pragma unroll
-            for (int l = 0; l < 32; ++l)
-              if (l < Lq) a = fmaf(u[l], __ldg(tail.wzb + l * L + j), a);
-            cb.zbase[cell * L + j] = a;
-          }
-        } else {
+          for (int i = 0; i < 16; ++i) qt[i] = 0.f;
 #pragma unroll
           for (int l = 0; l < 32; ++l)
-            if (l < Lq) cb.zbase[cell * L + l] = u[l];
+            if (l < Lq) {
+              const float ul = (u[l] - mean) * (rstd * __ldg(tail.uln_g + l)) + __ldg(tail.uln_b + l);
+              cb.u[cell * Lq + l] = u[l];
+              cb.u_ln[cell * Lq + l] = ul;
+              const float4* wr = reinterpret_cast<const float4*>(tail.wq + l * 16);
+#pragma unroll
+              for (int i4 = 0; i4 < 4; ++i4) {
+                const float4 w = __ldg(wr + i4);
+                qt[4 * i4] = fmaf(ul, w.x, qt[4 * i4]); qt[4 * i4 + 1] = fmaf(ul, w.y, qt[4 * i4 + 1]);
+                qt[4 * i4 + 2] = fmaf(ul, w.z, qt[4 * i4 + 2]); qt[4 * i4 + 3] = fmaf(ul, w.w, qt[4 * i4 + 3]);
+              }
+              if (!tail.has_zbase) cb.zbase[cell * L + l] = u[l];
+            }
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            reinterpret_cast<float4*>(cb.q_tok + cell * 16)[i] = make_float4(qt[4 * i], qt[4 * i + 1], qt[4 * i + 2], qt[4 * i + 3]);
+        }
+      } else if (tail.has_zbase) {
+        // z_base = D[:, Lq:Lq+L] + b   (reference _module.py:166-168, folded into the head GEMM)
+        for (int c0 = 0; c0 < tail.Nh; c0 += 32) {
+          float v[32];
+          tmem_ld32(t_T[NL & 1] + c0, v);
+          tmem_ld_wait();
+          if (valid) {
+#pragma unroll
+            for (int q = 0; q < 32; ++q) {
+              const int j = c0 + q - Lq;
+              if (j >= 0 && j < L) cb.zbase[cell * L + j] = v[q] + __ldg(tail.bhead + c0 + q);
+            }
+          }
         }
       }
+      tc_fence_before();
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // head's TMEM reads are done before the next tile reuses T
     }
-    tc_fence_before();
-  } else if (warp == 8) {
-    // ------------------------------------------------------------ MMA issuer
+  } else if (warp == 16) {
+    // ------------------------------------------------------------ phase-1 MMA issuer
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_f16(128);
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % kEncStages;
-        mbar_wait(full + s, (kb / kEncStages) & 1);
-        tc_fence_after();
-        const uint32_t a_h = smem_u32(smem + s * kEncStageBytes), a_l = a_h + kEncAHalf;
-        const uint32_t b_h = a_h + 2 * kEncAHalf, b_l = b_h + 4 * 2048;
+      int64_t g = 0;
+      for (int64_t ti = 0; ti < my_tiles; ++ti) {
+        const uint32_t t_acc = tmem_base + (uint32_t)(ti & 1) * 128;
+        if (ti >= 2) { mbar_wait(acc_free + (ti & 1), (uint32_t)(((ti >> 1) - 1) & 1)); tc_fence_after(); }
+        for (int kb = 0; kb < nkb; ++kb, ++g) {
+          const int s = (int)(g % kEncPStages);
+          mbar_wait(full + s, (uint32_t)((g / kEncPStages) & 1));
+          tc_fence_after();
+          const uint32_t a_h = smem_u32(smem + s * kEncStageBytes), a_l = a_h + kEncAHalf;
+          const uint32_t b_h = a_h + 2 * kEncAHalf, b_l = b_h + 4 * 2048;
 #pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {
-          const uint64_t ah = umma_desc(a_h + ks * 2 * kEncALbo, kEncALbo, 128);
-          const uint64_t al = umma_desc(a_l + ks * 2 * kEncALbo, kEncALbo, 128);
-          const uint64_t bh = umma_desc(b_h + ks * 2 * 2048, 2048, 128);
-          const uint64_t bl = umma_desc(b_l + ks * 2 * 2048, 2048, 128);
-          umma_f16(tmem_base, ah, bh, idesc, (kb | ks) ? 1u : 0u);
-          umma_f16(tmem_base, al, bh, idesc, 1u);
-          umma_f16(tmem_base, ah, bl, idesc, 1u);
+          for (int ks = 0; ks < 2; ++ks) {
+            const uint64_t ah = umma_desc(a_h + ks * 2 * kEncALbo, kEncALbo, 128);
+            const uint64_t al = umma_desc(a_l + ks * 2 * kEncALbo, kEncALbo, 128);
+            const uint64_t bh = umma_desc(b_h + ks * 2 * 2048, 2048, 128);
+            const uint64_t bl = umma_desc(b_l + ks * 2 * 2048, 2048, 128);
+            umma_f16(t_acc, ah, bh, idesc, (kb | ks) ? 1u : 0u);
+            umma_f16(t_acc, al, bh, idesc, 1u);
+            umma_f16(t_acc, ah, bl, idesc, 1u);
+          }
+          umma_commit(empty + s);
         }
-        umma_commit(empty + s);
-      }
-      umma_commit(acc_bar);
-      // tail layers: A from TMEM region li % 2, D to region (li + 1) % 2
-      const uint32_t s_wb = smem_u32(wbuf);
-      for (int li = 0; li <= NL; ++li) {
-        const int N = li < NL ? 128 : 32;
-        const uint32_t idn = umma_idesc_f16(N), lbo = (uint32_t)N * 16;
-        const uint32_t w_hi = s_wb, w_lo = s_wb + (uint32_t)N * 128 * 2;
-        mbar_wait(bar_w, li & 1);
-        mbar_wait(bar_a, li & 1);
-        tc_fence_after();
-        const uint32_t t_a = tmem_base + (li & 1) * 128, t_d = tmem_base + ((li + 1) & 1) * 128;
-#pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {
-          const uint32_t a = t_a + ks * 16;  // [8 hi words | 8 lo words] per 16-column chunk
-          const uint64_t bh = umma_desc(w_hi + ks * 2 * lbo, lbo, 128), bl = umma_desc(w_lo + ks * 2 * lbo, lbo, 128);
-          umma_f16_ts(t_d, a, bh, idn, ks == 0 ? 0u : 1u);
-          umma_f16_ts(t_d, a + 8, bh, idn, 1u);
-          umma_f16_ts(t_d, a, bl, idn, 1u);
-        }
-        umma_commit(bar_d);
+        umma_commit(acc_full + (ti & 1));
       }
     }
-  } else {
-    // ------------------------------------------------------------ weight loader (TMA bulk copies)
+  } else if (warp == 17) {
+    // ------------------------------------------------------------ tail MMA issuer: A from TMEM
     if (lane == 0) {
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % kEncStages;
-        if (kb >= kEncStages) mbar_wait(empty + s, ((kb / kEncStages) - 1) & 1);
+      const uint32_t s_wb = smem_u32(wbuf);
+      int64_t c = 0;
+      for (int64_t ti = 0; ti < my_tiles; ++ti) {
+        for (int li = 0; li <= NL; ++li, ++c) {
+          const int N = li < NL ? 128 : tail.Nh;
+          const uint32_t idn = umma_idesc_f16(N), lbo = (uint32_t)N * 16;
+          const uint32_t w_hi = s_wb, w_lo = s_wb + (uint32_t)N * 128 * 2;
+          mbar_wait(bar_w, (uint32_t)(c & 1));
+          mbar_wait(bar_a, (uint32_t)(c & 1));
+          tc_fence_after();
+          const uint32_t t_a = li == 0 ? tmem_base + (uint32_t)(ti & 1) * 128 : tmem_base + 256 + (uint32_t)((li - 1) & 1) * 128;
+          const uint32_t t_d = tmem_base + 256 + (uint32_t)(li & 1) * 128;
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {
+            const uint32_t a = t_a + ks * 16;  // [8 hi words | 8 lo words] per 16-column chunk
+            const uint64_t bh = umma_desc(w_hi + ks * 2 * lbo, lbo, 128), bl = umma_desc(w_lo + ks * 2 * lbo, lbo, 128);
+            umma_f16_ts(t_d, a, bh, idn, ks == 0 ? 0u : 1u);
+            umma_f16_ts(t_d, a + 8, bh, idn, 1u);
+            umma_f16_ts(t_d, a, bl, idn, 1u);
+          }
+          umma_commit(bar_d);
+          if (li == 0) umma_commit(acc_free + (ti & 1));  // the accumulator region has been consumed
+        }
+      }
+    }
+  } else if (warp == 18) {
+    // ------------------------------------------------------------ W0 loader (TMA bulk copies)
+    if (lane == 0) {
+      const int64_t total = my_tiles * nkb;
+      for (int64_t g = 0; g < total; ++g) {
+        const int s = (int)(g % kEncPStages);
+        const int64_t use = g / kEncPStages;
+        const int kb = (int)(g % nkb);
+        if (use > 0) mbar_wait(empty + s, (uint32_t)((use - 1) & 1));
         mbar_expect_tx(full + s, kEncBBytes);
         bulk_g2s(smem + s * kEncStageBytes + 2 * kEncAHalf, enc.w0img + (size_t)kb * kEncBBytes, kEncBBytes, full + s);
       }
-      mbar_wait(acc_bar, 0);  // phase 1 MMAs have drained: stages 0-1 become the tail weight buffer
-      for (int li = 0; li <= NL; ++li) {
-        if (li > 0) mbar_wait(bar_d, (li - 1) & 1);  // previous layer no longer reads the buffer
-        const uint32_t bytes = li < NL ? kEncLayerBytes : kEncHeadBytes;
-        const uint8_t* src = li < NL ? tail.wl[li] : tail.whead;
-        mbar_expect_tx(bar_w, bytes);
-        for (uint32_t o = 0; o < bytes; o += 16384) bulk_g2s(wbuf + o, src + o, 16384, bar_w);
+    }
+  } else {
+    // ------------------------------------------------------------ tail weight loader (TMA bulk copies)
+    if (lane == 0) {
+      int64_t c = 0;
+      for (int64_t ti = 0; ti < my_tiles; ++ti) {
+        for (int li = 0; li <= NL; ++li, ++c) {
+          if (c > 0) mbar_wait(bar_d, (uint32_t)((c - 1) & 1));  // previous layer no longer reads the buffer
+          const uint32_t bytes = li < NL ? kEncLayerBytes : (uint32_t)(2 * tail.Nh * 128 * 2);
+          const uint8_t* src = li < NL ? tail.wl[li] : tail.whead;
+          mbar_expect_tx(bar_w, bytes);
+          for (uint32_t o = 0; o < bytes; o += 8192) bulk_g2s(wbuf + o, src + o, 8192, bar_w);
+        }
       }
     }
   }
   __syncthreads();
-  if (warp == 8) tmem_dealloc(tmem_base, 256);
+  if (warp == 16) tmem_dealloc(tmem_base, 512);
 }
 
 // ---- host side: pack the tail weights
+inline uint32_t enc_pack_hilo_d(std::vector<uint8_t>& img, const std::vector<double>& W /*[K=128][N]*/, int N, int Npad) {
+  const uint32_t off = (uint32_t)img.size();
+  const size_t half_elems = (size_t)Npad * 128;
+  img.resize(off + 2 * half_elems * 2, 0);
+  __half* hi = reinterpret_cast<__half*>(img.data() + off);
+  __half* lo = hi + half_elems;
+  for (int k = 0; k < 128; ++k)
+    for (int n = 0; n < N; ++n) {
+      const float w = (float)W[(size_t)k * N + n];
+      const __half h = __float2half_rn(w);
+      const size_t e = (size_t)(k / 8) * ((size_t)Npad * 8) + (size_t)n * 8 + (k % 8);
+      hi[e] = h;
+      lo[e] = __float2half_rn((float)(W[(size_t)k * N + n] - (double)__half2float(h)));
+    }
+  return off;
+}
+
 inline uint32_t enc_pack_hilo(std::vector<uint8_t>& img, const float* W /*[K=128][N]*/, int N, int Npad) {
   // canonical K-major [Npad x 128] f16, hi image then lo image
   const uint32_t off = (uint32_t)img.size();
@@ -414,7 +486,36 @@ inline int enc_tail_build(EncTail& t, const NetW& net, const tc_detail::PMap& pm
     offs.push_back(enc_pack_hilo(img, P(pm, rb + "/Dense_0/kernel"), 128, 128));
     offs.push_back(enc_pack_hilo(img, P(pm, rb + "/Dense_1/kernel"), 128, 128));
   }
-  const uint32_t off_head = enc_pack_hilo(img, P(pm, "qu/NormalDistOutputNN_0/Dense_0/kernel"), net.Lq, 32);
+  // head: h -> [u | z_base]; z_base = u W_zb + b_zb = h (W_mean W_zb) + (b_mean W_zb + b_zb), folded in float64
+  const int Lq = net.Lq, L = net.L;
+  const int n_head = Lq + (net.has_zbase ? L : 0);
+  const int Nh = ((n_head + 31) / 32) * 32;
+  if (Nh > kEncHeadMaxN) return 0;
+  std::vector<double> Wh((size_t)128 * n_head, 0.0);
+  std::vector<float> bh(Nh, 0.f);
+  {
+    const float* Wm = P(pm, "qu/NormalDistOutputNN_0/Dense_0/kernel");  // [128][Lq]
+    const float* bm = P(pm, "qu/NormalDistOutputNN_0/Dense_0/bias");
+    for (int k = 0; k < 128; ++k)
+      for (int l = 0; l < Lq; ++l) Wh[(size_t)k * n_head + l] = Wm[(size_t)k * Lq + l];
+    for (int l = 0; l < Lq; ++l) bh[l] = bm[l];
+    if (net.has_zbase) {
+      const float* Wz = P(pm, "qz/Dense_0/kernel");  // [Lq][L]
+      const float* bz = P(pm, "qz/Dense_0/bias");
+      for (int k = 0; k < 128; ++k)
+        for (int j = 0; j < L; ++j) {
+          double a = 0.0;
+          for (int l = 0; l < Lq; ++l) a += (double)Wm[(size_t)k * Lq + l] * Wz[(size_t)l * L + j];
+          Wh[(size_t)k * n_head + Lq + j] = a;
+        }
+      for (int j = 0; j < L; ++j) {
+        double a = bz[j];
+        for (int l = 0; l < Lq; ++l) a += (double)bm[l] * Wz[(size_t)l * L + j];
+        bh[Lq + j] = (float)a;
+      }
+    }
+  }
+  const uint32_t off_head = enc_pack_hilo_d(img, Wh, n_head, Nh);
   const uint8_t* dimg = nullptr;
   int err;
   if ((err = tc_upload(arena, img.data(), img.size(), (const void**)&dimg))) return err;
@@ -429,23 +530,19 @@ inline int enc_tail_build(EncTail& t, const NetW& net, const tc_detail::PMap& pm
     t.bl[1 + 2 * b] = rb.d0.b; t.lg[1 + 2 * b] = rb.ln0.scale; t.lb[1 + 2 * b] = rb.ln0.bias;
     t.bl[2 + 2 * b] = rb.dout.b; t.lg[2 + 2 * b] = rb.ln1.scale; t.lb[2 + 2 * b] = rb.ln1.bias;
   }
-  t.bhead = net.enc_mean.b;
+  t.Nh = Nh;
+  t.has_zbase = net.has_zbase;
+  if ((err = tc_upload(arena, bh.data(), bh.size() * sizeof(float), (const void**)&t.bhead))) return err;
   t.uln_g = net.u_ln.scale; t.uln_b = net.u_ln.bias;
   // query-token and z_base weights as dense [Lq][16] / [Lq][L] fp32 (the packed fp32 copies are padded)
   std::vector<float> wq((size_t)net.Lq * 16);
   const float* wqs = P(pm, "qz/AttentionBlock_0/DenseGeneral_0/kernel");
   for (size_t i = 0; i < wq.size(); ++i) wq[i] = wqs[i];
   if ((err = tc_upload(arena, wq.data(), wq.size() * sizeof(float), (const void**)&t.wq))) return err;
-  t.wzb = nullptr; t.bzb = nullptr;
-  if (net.has_zbase) {
-    const float* w = P(pm, "qz/Dense_0/kernel");
-    const float* b = P(pm, "qz/Dense_0/bias");
-    if ((err = tc_upload(arena, w, (size_t)net.Lq * net.L * sizeof(float), (const void**)&t.wzb))) return err;
-    if ((err = tc_upload(arena, b, (size_t)net.L * sizeof(float), (const void**)&t.bzb))) return err;
-  }
   t.Lq = net.Lq; t.L = net.L; t.S = net.S;
+  { int dev = 0, sms = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); t.sm_count = sms; }
   if (cudaFuncSetAttribute(k_encoder_tc, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)((size_t)kEncStages * kEncStageBytes + 4096 + 1024)) != cudaSuccess) {
+                           (int)kEncPSmem) != cudaSuccess) {
     g_tc_error = "cudaFuncSetAttribute(k_encoder_tc) failed";
     return MRVI_ERR_CUDA;
   }
@@ -455,9 +552,11 @@ inline int enc_tail_build(EncTail& t, const NetW& net, const tc_detail::PMap& pm
 
 inline void enc_full_tc_launch(const EncTc& enc, const EncTail& tail, const float* X, int64_t ldx, const int32_t* sid, int64_t n,
                                int G, const CellBuf& cb, cudaStream_t st) {
-  const int grid = (int)((n + 127) / 128);
+  const int64_t n_tiles = (n + 127) / 128;
+  const int grid = (int)std::min<int64_t>(n_tiles, tail.sm_count);
+  if (grid == 0) return;
   const int vec_ok = ((ldx % 4) == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
-  k_encoder_tc<<<grid, kEnc2Threads, (size_t)kEncStages * kEncStageBytes + 4096 + 1024, st>>>(X, ldx, sid, n, G, enc, tail, cb, vec_ok);
+  k_encoder_tc<<<grid, kEncPThreads, kEncPSmem, st>>>(X, ldx, sid, n, G, enc, tail, cb, vec_ok);
 }
 
 }  // namespace mrvi

@@ -281,8 +281,10 @@ __global__ void __launch_bounds__(kFusedThreads, 1)
 k_chain_fused_tc(const __grid_constant__ TcNet tc, CellBuf cb, int64_t n_cells, int S, int L, int Lq,
                  float* __restrict__ z_out, float* __restrict__ cell_out, GroupPlan gp, int64_t n_tiles,
                  int cells_per_tile, int64_t tiles_per_cta) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // no-swizzle UMMA operands and bulk copies need 16-byte alignment only; keeping the plain array (no integer
+  // re-alignment) lets the compiler see the shared address space (LDS/STS instead of generic LD/ST)
+  extern __shared__ __align__(1024) uint8_t smem_tc[];
+  uint8_t* const smem = smem_tc;
   const FusedSmemMap sm = fused_smem_map(tc.wimg_bytes, tc.K1, tc.K3, L);
   FusedCtrl* ctrl = reinterpret_cast<FusedCtrl*>(smem + sm.ctrl);
   const int tid = threadIdx.x, wg = tid >> 8, wt = tid & 255, half = wt >> 7, r = wt & 127, warp_q = (wt >> 5) & 3;

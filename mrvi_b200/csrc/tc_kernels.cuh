@@ -322,8 +322,10 @@ __device__ __forceinline__ void issue_gemm(uint32_t d_tmem, uint32_t a_h, uint32
 __global__ void __launch_bounds__(kTcThreads, 2)
 k_chain_tc(const __grid_constant__ TcNet tc, CellBuf cb, int64_t n_cells, int S, int L, int Lq,
            float* __restrict__ z_out, int64_t n_tiles, int cells_per_tile, int tiles_per_cell) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // no-swizzle UMMA operands and bulk copies need 16-byte alignment only; keeping the plain array (no integer
+  // re-alignment) lets the compiler see the shared address space (LDS/STS instead of generic LD/ST)
+  extern __shared__ __align__(1024) uint8_t smem_tc[];
+  uint8_t* const smem = smem_tc;
   const TcSmemMap sm = tc_smem_map(tc.wimg_bytes, tc.K1, tc.K3);
   uint64_t* bar_w = reinterpret_cast<uint64_t*>(smem + sm.bars);
   uint64_t* bar_mma = bar_w + 1;
@@ -782,8 +784,10 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __global__ void __launch_bounds__(kEncThreads, 2)
 k_enc_gemm_tc(const float* __restrict__ X, int64_t ldx, int64_t n_cells, int G, EncTc enc, float* __restrict__ H1,
               int x_vec_ok) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // no-swizzle UMMA operands and bulk copies need 16-byte alignment only; keeping the plain array (no integer
+  // re-alignment) lets the compiler see the shared address space (LDS/STS instead of generic LD/ST)
+  extern __shared__ __align__(1024) uint8_t smem_tc[];
+  uint8_t* const smem = smem_tc;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kEncStages * kEncStageBytes);
   uint64_t* full = bars;                    // [stages] producers (128) + B expect_tx (1)
   uint64_t* empty = bars + kEncStages;      // [stages] tcgen05.commit
