@@ -511,13 +511,38 @@ k_chain_fused_tc(const __grid_constant__ TcNet tc, CellBuf cb, int64_t n_cells, 
     if (!need_dist) continue;
 
     // ================= centre per cell, norms, (hi, lo) Gram operands =================
-    for (int idx = wt; idx < cells_per_tile * Kz; idx += 256) {
-      const int cl = idx / Kz, l = idx - cl * Kz;
-      float sum = 0.f;
-      for (int q = 0; q < S; ++q) sum += zf[(cl * S + q) * zld + l];
-      mean_s[cl * Kz + l] = sum / (float)S;
+    {
+      // per-cell column means of the residual tile, all 256 threads: nseg threads share one (cell, column)
+      const int O = cells_per_tile * Kz;                 // outputs
+      if (O >= 256) {                                    // small S: one thread per output, few rows each
+        for (int idx = wt; idx < O; idx += 256) {
+          const int cl = idx / Kz, l = idx - cl * Kz;
+          float sum = 0.f;
+          for (int q = 0; q < S; ++q) sum += zf[(cl * S + q) * zld + l];
+          mean_s[idx] = sum / (float)S;
+        }
+        wg_sync(wg);
+      } else {
+        const int nseg = 256 / O;                        // 2, 4 or 8 row segments per output
+        const int o = wt % O, seg = wt / O;
+        const int cl = o / Kz, l = o - cl * Kz;
+        const int per = (S + nseg - 1) / nseg;
+        float sum = 0.f;
+        if (seg < nseg) {
+          const int q1 = min(S, (seg + 1) * per);
+          for (int q = seg * per; q < q1; ++q) sum += zf[(cl * S + q) * zld + l];
+        }
+        float* part = reinterpret_cast<float*>(xch);     // [nseg][O] <= 256 floats (xch is free here)
+        if (seg < nseg) part[seg * O + o] = sum;
+        wg_sync(wg);
+        if (wt < O) {
+          float t = 0.f;
+          for (int k = 0; k < nseg; ++k) t += part[k * O + wt];
+          mean_s[wt] = t / (float)S;
+        }
+        wg_sync(wg);
+      }
     }
-    wg_sync(wg);
     {
       const float* mrow = mean_s + (row_in_tile ? lc : 0) * Kz;
       float nrm_p = 0.f;
@@ -591,19 +616,23 @@ k_chain_fused_tc(const __grid_constant__ TcNet tc, CellBuf cb, int64_t n_cells, 
       uint32_t flagged = 0u;
       // fast path (warp-uniform): the whole chunk lies inside every lane's cell and every row is valid
       const bool full = __all_sync(0xffffffffu, valid && c * 32 >= c0 && c * 32 + 32 <= c0 + S);
+      const float2 ni2 = make_float2(n_i, n_i), m2 = make_float2(-2.0f, -2.0f), thr2 = make_float2(-1.0f / 4096.0f, -1.0f / 4096.0f);
 #pragma unroll
       for (int q4 = 0; q4 < 8; ++q4) {
         const float4 nj = *reinterpret_cast<const float4*>(nrm_s + c * 32 + 4 * q4);
-        const float njv[4] = {nj.x, nj.y, nj.z, nj.w};
+        const float2 njp[2] = {make_float2(nj.x, nj.y), make_float2(nj.z, nj.w)};
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int q = 4 * q4 + e, j = c * 32 + q;          // column = tile row of the other sample
-          const bool in = full ? (j != r) : (valid && (unsigned)(j - c0) < (unsigned)S && j != r);
-          const float sn = n_i + njv[e];
-          const float d2 = fmaf(-2.0f, g[q], sn);
-          if (in && d2 < sn * (1.0f / 4096.0f)) flagged |= 1u << q;  // cancellation dominated
-          const float d = sqrt_approx(fmaxf(d2, 0.f));
-          g[q] = in ? d : 0.f;
+        for (int e2 = 0; e2 < 2; ++e2) {
+          const int q = 4 * q4 + 2 * e2, j = c * 32 + q;     // columns j, j+1 = tile rows of the other samples
+          const float2 sn = __fadd2_rn(ni2, njp[e2]);
+          const float2 d2 = __ffma2_rn(make_float2(g[q], g[q + 1]), m2, sn);
+          const float2 tt = __ffma2_rn(sn, thr2, d2);        // < 0: cancellation dominated
+          const bool in0 = full ? (j != r) : (valid && (unsigned)(j - c0) < (unsigned)S && j != r);
+          const bool in1 = full ? (j + 1 != r) : (valid && (unsigned)(j + 1 - c0) < (unsigned)S && j + 1 != r);
+          if (in0 && tt.x < 0.f) flagged |= 1u << q;
+          if (in1 && tt.y < 0.f) flagged |= 2u << q;
+          g[q] = in0 ? sqrt_approx(fmaxf(d2.x, 0.f)) : 0.f;
+          g[q + 1] = in1 ? sqrt_approx(fmaxf(d2.y, 0.f)) : 0.f;
         }
       }
       if (flagged) {  // rare: near-duplicate samples -> exact direct-difference distance
@@ -633,7 +662,10 @@ k_chain_fused_tc(const __grid_constant__ TcNet tc, CellBuf cb, int64_t n_cells, 
         tmem_ld32(t_acc_lane + c * 32, acc);
         tmem_ld_wait();
 #pragma unroll
-        for (int q = 0; q < 32; ++q) acc[q] += g[q];
+        for (int q = 0; q < 16; ++q) {
+          const float2 t = __fadd2_rn(make_float2(acc[2 * q], acc[2 * q + 1]), make_float2(g[2 * q], g[2 * q + 1]));
+          acc[2 * q] = t.x; acc[2 * q + 1] = t.y;
+        }
         tmem_st32(t_acc_lane + c * 32, reinterpret_cast<uint32_t*>(acc));
       } else if (gp.n_keys > 0 && valid) {  // mixed tile: straight to the float64 sums
         for (int k = 0; k < gp.n_keys; ++k) {
