@@ -85,7 +85,11 @@ def _mlp_shapes(prefix: str, n_in: int, n_hidden: int, n_layers: int, n_out: int
     out[f"{prefix}/Dense_0/bias"] = (n_out,)
 
 
-def expected_param_shapes(dims: MrviDims) -> "OrderedDict[str, tuple]":
+#: parameters read only by the sampled paths (use_mean=False / normalize_distances=True); optional at load time
+OPTIONAL_PARAMS = ("qu/NormalDistOutputNN_0/Dense_1/kernel", "qu/NormalDistOutputNN_0/Dense_1/bias")
+
+
+def expected_param_shapes(dims: MrviDims, with_scale_head: bool = True) -> "OrderedDict[str, tuple]":
     """Name -> shape of every parameter the path reads, in a fixed order."""
     G, S, H, Lq, L = dims.n_input, dims.n_sample, dims.encoder_n_hidden, dims.n_latent_q, dims.n_latent
     E, C, nh, hd = dims.n_latent_sample, dims.n_channels, dims.n_heads, dims.head_dim
@@ -105,6 +109,9 @@ def expected_param_shapes(dims: MrviDims) -> "OrderedDict[str, tuple]":
         d = H
     o["qu/NormalDistOutputNN_0/Dense_0/kernel"] = (H, Lq)
     o["qu/NormalDistOutputNN_0/Dense_0/bias"] = (Lq,)
+    if with_scale_head:  # softplus scale head of q(u|x) (`_components.py:96-97`): only the sampled paths read it
+        o["qu/NormalDistOutputNN_0/Dense_1/kernel"] = (H, Lq)
+        o["qu/NormalDistOutputNN_0/Dense_1/bias"] = (Lq,)
     # ---- qz = EncoderUZ (`_module.py:114-170`) + AttentionBlock (`_components.py:165-230`)
     o["qz/u_ln/scale"] = (Lq,)
     o["qz/u_ln/bias"] = (Lq,)
@@ -190,6 +197,8 @@ def validate_params(flat: Mapping[str, np.ndarray], dims: MrviDims) -> "OrderedD
     """Check every expected parameter is present with the right shape; return them in schema order."""
     out: "OrderedDict[str, np.ndarray]" = OrderedDict()
     for name, shape in expected_param_shapes(dims).items():
+        if name not in flat and name in OPTIONAL_PARAMS:
+            continue
         if name not in flat:
             raise KeyError(f"missing parameter {name!r} (expected shape {shape})")
         a = np.ascontiguousarray(np.asarray(flat[name]), dtype=np.float32)
@@ -211,9 +220,11 @@ def init_params(dims: MrviDims, seed: int = 0, jitter: float = 0.1, embed_std: f
     LayerNorm scale/bias with N(0, jitter^2) so that no parameter is at a value (0 or 1) that would
     hide a missing term in a kernel.  There is no trained checkpoint in this environment.
     """
-    rng = np.random.default_rng(seed)
+    main_rng = np.random.default_rng(seed)
+    opt_rng = np.random.default_rng([seed, 1])  # own stream: adding the optional heads leaves every other draw unchanged
     out: "OrderedDict[str, np.ndarray]" = OrderedDict()
     for name, shape in expected_param_shapes(dims).items():
+        rng = opt_rng if name in OPTIONAL_PARAMS else main_rng
         leaf = name.rsplit("/", 1)[1]
         if leaf == "embedding":
             if "gamma_conditional" in name:

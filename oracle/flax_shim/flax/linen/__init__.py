@@ -86,7 +86,7 @@ class Module:
         return np.zeros(shape)
 
     def make_rng(self, name):
-        raise RuntimeError("the shimmed path is deterministic (use_mean=True, eval mode)")
+        return name  # the stream name; numpyro.distributions.NOISE_PROVIDER turns it into explicit draws
 
     def _ensure_setup(self):
         if not self._setup_done and hasattr(self, "setup"):

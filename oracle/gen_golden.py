@@ -76,16 +76,58 @@ def nest(flat):
     return tree
 
 
+def _tree_with_scale_head(flat):
+    tree = nest(flat)
+    # the reference also evaluates the (unused under use_mean) scale head of q(u|x): it needs parameters
+    H, Lq = flat["qu/NormalDistOutputNN_0/Dense_0/kernel"].shape
+    tree["qu"]["NormalDistOutputNN_0"].setdefault("Dense_1", {"kernel": np.zeros((H, Lq)), "bias": np.zeros(Lq)})
+    return tree
+
+
+def reference_sampled(flat, dims, vae_kwargs, X, sid, noise_u, noise_base):
+    """Sampled paths through the reference's own ``MrVAE.inference(use_mean=False, mc_samples=...)``
+    (`_module.py:308-343`), with the draws of ``qu.rsample`` supplied explicitly (numpyro shim NOISE_PROVIDER):
+
+    * z_s: for each counterfactual sample s, ``inference(x, sample_index, mc_samples=mc, cf_sample=s)["z"]``
+      with draws ``noise_u[s]`` (mc, n, Lq); stacked on axis -2 and transposed as `_model.py:352, 414`
+      -> (n, mc, S, L);
+    * baseline: ``inference(x, sample_index, mc_samples=2*mc)["z"]`` (own sample) with draws ``noise_base``,
+      then the arithmetic of `_model.py:535-540` (l2 between the two halves, mean / var over mc)."""
+    components, module = load_reference_modules()
+    npd = components.dist  # the shim's numpyro.distributions module object the reference source holds
+    assert module.dist is npd
+
+    vae = module.MrVAE(n_input=dims.n_input, n_sample=dims.n_sample, n_batch=2, n_labels=1, n_continuous_cov=0,
+                       training=False, **vae_kwargs)
+    variables = {"params": _tree_with_scale_head(flat)}
+    x = np.asarray(X, dtype=np.float64)
+    sample_index = np.asarray(sid, dtype=np.float64).reshape(-1, 1)
+    mc = noise_u.shape[1]
+    zs = []
+    try:
+        for s in range(dims.n_sample):
+            npd.NOISE_PROVIDER = lambda key, shape, s=s: {"u": noise_u[s]}[key]
+            cf = np.full((x.shape[0], 1), s)
+            out = vae.apply(variables, method=vae.inference, x=x, sample_index=sample_index, cf_sample=cf,
+                            use_mean=False, mc_samples=mc)
+            zs.append(np.asarray(out["z"]))  # (mc, n, L)
+        z = np.stack(zs, axis=-2).transpose(1, 0, 2, 3)  # (n, mc, S, L)
+        npd.NOISE_PROVIDER = lambda key, shape: {"u": noise_base}[key]
+        zb = np.asarray(vae.apply(variables, method=vae.inference, x=x, sample_index=sample_index,
+                                  use_mean=False, mc_samples=2 * mc)["z"])
+    finally:
+        npd.NOISE_PROVIDER = None
+    first, second = zb[:mc], zb[mc:]
+    l2 = np.sqrt(np.sum((first - second) ** 2, axis=2)).T
+    return z, l2.mean(axis=1), l2.var(axis=1)
+
+
 def reference_z(flat, dims, vae_kwargs, X, sid):
     """z[b, s, :] by running the reference's MrVAE.inference for every counterfactual sample."""
     _, module = load_reference_modules()
     vae = module.MrVAE(n_input=dims.n_input, n_sample=dims.n_sample, n_batch=2, n_labels=1, n_continuous_cov=0,
                        training=False, **vae_kwargs)
-    tree = nest(flat)
-    # the reference also evaluates the (unused under use_mean) scale head of q(u|x): give it parameters
-    H, Lq = flat["qu/NormalDistOutputNN_0/Dense_0/kernel"].shape
-    tree["qu"]["NormalDistOutputNN_0"]["Dense_1"] = {"kernel": np.zeros((H, Lq)), "bias": np.zeros(Lq)}
-    variables = {"params": tree}
+    variables = {"params": _tree_with_scale_head(flat)}
     x = np.asarray(X, dtype=np.float64)
     sample_index = np.asarray(sid, dtype=np.float64).reshape(-1, 1)  # scvi loader hands floats, (B, 1)
     zs = []
@@ -94,6 +136,30 @@ def reference_z(flat, dims, vae_kwargs, X, sid):
         out = vae.apply(variables, method=vae.inference, x=x, sample_index=sample_index, cf_sample=cf, use_mean=True)
         zs.append(np.asarray(out["z"]))
     return np.stack(zs, axis=1)  # out_axes=-2  ->  (cell, sample, latent)
+
+
+SAMPLED_CASES = {
+    # name: (MrviDims kwargs, MrVAE kwargs, n_cells, mc_samples, seeds)
+    "sampled_S4_mc3": (dict(n_input=100, n_sample=4), dict(), 24, 3, (10, 11)),
+    "sampled_iso_S6_mc2": (dict(n_input=40, n_sample=6, n_latent=10, n_latent_u=10), dict(n_latent=10), 16, 2, (12, 13)),
+}
+
+
+def make_sampled_case(name):
+    sys.path.insert(0, ROOT)
+    import mrvi_b200
+
+    dk, vk, n, mc, (pseed, xseed) = SAMPLED_CASES[name]
+    dims = mrvi_b200.MrviDims(**dk)
+    flat = mrvi_b200.init_params(dims, seed=pseed)
+    # shrink the scale head's bias so that q(u|x) has a trained-model-like spread (softplus(-2) ~ 0.13)
+    flat["qu/NormalDistOutputNN_0/Dense_1/bias"] = flat["qu/NormalDistOutputNN_0/Dense_1/bias"] - 2.0
+    X = mrvi_b200.synthetic_counts(n, dims.n_input, seed=xseed)
+    rng = np.random.default_rng(xseed)
+    sid = rng.integers(0, dims.n_sample, n).astype(np.int32)
+    noise_u = rng.standard_normal((dims.n_sample, mc, n, dims.n_latent_q))
+    noise_base = rng.standard_normal((2 * mc, n, dims.n_latent_q))
+    return dims, vk, flat, X, sid, noise_u, noise_base
 
 
 def make_case(name):
@@ -121,6 +187,13 @@ def main():
         np.savez_compressed(os.path.join(out_dir, f"{name}.npz"), X=X, sid=sid, z=z.astype(np.float64), d=d.astype(np.float64),
                             **{"param|" + k.replace("/", "|"): v for k, v in flat.items()})
         print(f"{name}: z {z.shape}, max|z| {np.abs(z).max():.4f}, median d {np.median(d):.4f}")
+    for name in SAMPLED_CASES:
+        dims, vk, flat, X, sid, noise_u, noise_base = make_sampled_case(name)
+        z, mu, var = reference_sampled(flat, dims, vk, X, sid, noise_u, noise_base)
+        np.savez_compressed(os.path.join(out_dir, f"{name}.npz"), X=X, sid=sid, noise_u=noise_u, noise_base=noise_base,
+                            z=z, base_mean=mu, base_var=var,
+                            **{"param|" + k.replace("/", "|"): v for k, v in flat.items()})
+        print(f"{name}: sampled z {z.shape}, baseline mean {mu.mean():.4f} var {var.mean():.4f}")
 
 
 if __name__ == "__main__":

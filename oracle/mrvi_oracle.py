@@ -105,9 +105,8 @@ def conditional_normalization(h, sid, p, prefix):
     return gamma * h + beta
 
 
-def encoder_xu_mean(p, x, sid):
-    """_EncoderXU `_module.py:182-202` + NormalDistOutputNN mean head `_components.py:86-97`.
-    Returns qu.mean, i.e. u under use_mean=True (`_module.py:312-314`)."""
+def _encoder_xu_trunk(p, x, sid):
+    """_EncoderXU `_module.py:182-200` up to the last ResnetBlock of NormalDistOutputNN (`_components.py:92-94`)."""
     h = np.log1p(x)
     for i in range(2):
         h = dense(h, p, f"qu/Dense_{i}")
@@ -119,7 +118,25 @@ def encoder_xu_mean(p, x, sid):
     while f"{nd}/ResnetBlock_{i}/Dense_0/kernel" in p:
         h = resnet_block(h, p, f"{nd}/ResnetBlock_{i}", relu, relu)
         i += 1
-    return dense(h, p, f"{nd}/Dense_0")
+    return h
+
+
+def encoder_xu_mean(p, x, sid):
+    """_EncoderXU `_module.py:182-202` + NormalDistOutputNN mean head `_components.py:86-97`.
+    Returns qu.mean, i.e. u under use_mean=True (`_module.py:312-314`)."""
+    return dense(_encoder_xu_trunk(p, x, sid), p, "qu/NormalDistOutputNN_0/Dense_0")
+
+
+def softplus(v):
+    return np.logaddexp(v, 0.0)
+
+
+def encoder_xu(p, x, sid):
+    """q(u|x) = Normal(mean, scale): mean head and `softplus(Dense(h)) + scale_eps` head, scale_eps = 1e-5
+    (`_components.py:95-97`)."""
+    h = _encoder_xu_trunk(p, x, sid)
+    nd = "qu/NormalDistOutputNN_0"
+    return dense(h, p, f"{nd}/Dense_0"), softplus(dense(h, p, f"{nd}/Dense_1")) + p[f"{nd}/Dense_0/bias"].dtype.type(1e-5)
 
 
 def multi_head_attention(q_in, kv_in, p, prefix):
@@ -255,3 +272,82 @@ def local_sample_distances(flat, X, sample_idx, group_labels=None, keep_cell=Tru
             "means": np.stack([sums[key][c] / dtype(counts[c]) for c in cats], axis=0),
         }
     return out
+
+
+# --------------------------------------------------------------------------- sampled paths
+# use_mean=False / normalize_distances=True.  The reference draws its noise from JAX threefry streams that
+# cannot be reproduced without jax; here the standard-normal draws are INPUTS, so that the same draws can be
+# handed to the CUDA path and the two compared exactly.  Shapes follow the reference's own sampling calls.
+
+
+def _qz_any(p, u, s_idx, noise_eps=None):
+    """z = z_base + eps for rows with arbitrary leading shape (`_module.py:320-331`); with use_map=False
+    eps = loc + (softplus(raw) + 1e-3) * noise (`_module.py:326-329`)."""
+    lead = u.shape[:-1]
+    u2 = u.reshape(-1, u.shape[-1])
+    s2 = np.broadcast_to(s_idx, lead).reshape(-1)
+    z_base, eps = encoder_uz(p, u2, s2)
+    L = z_base.shape[-1]
+    if eps.shape[-1] == 2 * L:
+        loc, raw = eps[:, :L], eps[:, L:]
+        if noise_eps is None:
+            raise ValueError("use_map=False needs noise_eps for the sampled path")
+        eps = loc + (softplus(raw) + loc.dtype.type(1e-3)) * noise_eps.reshape(-1, L)
+    return (z_base + eps).reshape(*lead, L)
+
+
+def sampled_counterfactual_z(flat, x, sid, noise_u, noise_eps=None, dtype=np.float64):
+    """``mapped_inference_fn(..., use_mean=False, mc_samples=mc)`` (`_model.py:326-365, 406-414`).
+
+    The vmapped call for counterfactual sample s owns its own "u" PRNG stream (`_model.py:136-159`), so it
+    draws its own ``u = qu.rsample(rng_s, (mc,))`` of shape (mc, n, Lq) (`_module.py:315-318`):
+    ``noise_u[s]`` stands for those draws, ``noise_eps[s]`` (mc, n, L) for the "eps" stream when use_map=False.
+    Returns (n, mc, S, L): ``out_axes=-2`` then the transpose of `_model.py:414`."""
+    p = cast_params(flat, dtype)
+    x = np.asarray(x, dtype=dtype)
+    sid = np.asarray(sid).astype(np.int64).reshape(-1)
+    noise_u = np.asarray(noise_u, dtype=dtype)
+    S = p["qz/Embed_0/embedding"].shape[0]
+    mean, scale = encoder_xu(p, x, sid)
+    zs = []
+    for s in range(S):
+        u = mean[None] + scale[None] * noise_u[s]  # (mc, n, Lq)
+        cf = np.full(x.shape[0], s, dtype=np.int64)
+        zs.append(_qz_any(p, u, cf[None, :], None if noise_eps is None else np.asarray(noise_eps, dtype=dtype)[s]))
+    z = np.stack(zs, axis=2)  # (mc, n, S, L)
+    return z.transpose(1, 0, 2, 3)
+
+
+def pairwise_distances_mc(z, norm="l2"):
+    """``jax.vmap(jax.vmap(_compute_distance))`` over (cell, mc_sample) (`_model.py:572-573`)."""
+    n, mc = z.shape[:2]
+    return pairwise_distances(z.reshape(n * mc, *z.shape[2:]), norm).reshape(n, mc, z.shape[2], z.shape[2])
+
+
+def local_baseline_dists(flat, x, sid, noise_base, noise_eps=None, dtype=np.float64):
+    """``_compute_local_baseline_dists`` (`_model.py:508-540`): 2*mc draws of z for the cell's OWN sample,
+    l2 distance between draw m and draw m+mc, mean and (population) variance over m.  ``noise_base``:
+    (2*mc, n, Lq)."""
+    p = cast_params(flat, dtype)
+    x = np.asarray(x, dtype=dtype)
+    sid = np.asarray(sid).astype(np.int64).reshape(-1)
+    noise_base = np.asarray(noise_base, dtype=dtype)
+    mean, scale = encoder_xu(p, x, sid)
+    u = mean[None] + scale[None] * noise_base
+    z = _qz_any(p, u, sid[None, :], None if noise_eps is None else np.asarray(noise_eps, dtype=dtype))
+    mc = noise_base.shape[0] // 2
+    a, b = z[:mc], z[mc:]
+    l2 = np.sqrt(((a - b) ** 2).sum(axis=2)).T  # (n, mc)
+    return l2.mean(axis=1), l2.var(axis=1)
+
+
+def sampled_local_sample_distances(flat, X, sample_idx, noise_u, noise_base=None, normalize=False, dtype=np.float64):
+    """The ``sampled_distances`` / ``normalized_distances`` inputs of ``compute_local_statistics``
+    (`_model.py:430-450`): (n, mc, S, S) sampled distances, or their per-cell z-score against the local
+    baseline averaged over mc, (n, S, S)."""
+    z = sampled_counterfactual_z(flat, X, sample_idx, noise_u, dtype=dtype)
+    d = pairwise_distances_mc(z)
+    if not normalize:
+        return d
+    mu, var = local_baseline_dists(flat, X, sample_idx, noise_base, dtype=dtype)
+    return ((d - mu[:, None, None, None]) / np.sqrt(var)[:, None, None, None]).mean(axis=1)

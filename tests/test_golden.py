@@ -11,7 +11,9 @@ import mrvi_b200
 from oracle import gen_golden as gg
 from oracle import mrvi_oracle as orc
 
-GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+_ALL = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+GOLDEN = [p for p in _ALL if not os.path.basename(p).startswith("sampled_")]
+SAMPLED = [p for p in _ALL if os.path.basename(p).startswith("sampled_")]
 
 
 def _load(path):
@@ -22,6 +24,33 @@ def _load(path):
 
 def test_golden_files_exist():
     assert {os.path.basename(p)[:-4] for p in GOLDEN} == set(gg.CASES)
+    assert {os.path.basename(p)[:-4] for p in SAMPLED} == set(gg.SAMPLED_CASES)
+
+
+def _load_sampled(path):
+    z = np.load(path)
+    flat = {k[len("param|"):].replace("|", "/"): z[k] for k in z.files if k.startswith("param|")}
+    return flat, z
+
+
+@pytest.mark.parametrize("path", SAMPLED, ids=[os.path.basename(p)[:-4] for p in SAMPLED])
+def test_oracle_sampled_paths_match_reference_source_goldens(path):
+    """use_mean=False / normalize_distances=True: the reference's own inference(use_mean=False,
+    mc_samples) executed on the shim with explicit draws vs the oracle restatement."""
+    flat, g = _load_sampled(path)
+    z = orc.sampled_counterfactual_z(flat, g["X"], g["sid"], g["noise_u"])
+    assert z.shape == g["z"].shape and np.abs(z - g["z"]).max() < 1e-12
+    mu, var = orc.local_baseline_dists(flat, g["X"], g["sid"], g["noise_base"])
+    assert np.abs(mu - g["base_mean"]).max() < 1e-12 and np.abs(var - g["base_var"]).max() < 1e-12
+
+
+@pytest.mark.skipif(not gg.reference_available(), reason="/root/reference only exists in the build container")
+@pytest.mark.parametrize("name", list(gg.SAMPLED_CASES))
+def test_sampled_goldens_regenerate_from_reference_source(name):
+    dims, vk, flat, X, sid, noise_u, noise_base = gg.make_sampled_case(name)
+    z, mu, var = gg.reference_sampled(flat, dims, vk, X, sid, noise_u, noise_base)
+    stored = np.load(os.path.join(os.path.dirname(__file__), "golden", f"{name}.npz"))
+    assert np.abs(z - stored["z"]).max() < 1e-13 and np.abs(mu - stored["base_mean"]).max() < 1e-13
 
 
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
