@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define MRVI_B200_ABI_VERSION 1
+#define MRVI_B200_ABI_VERSION 2
 
 typedef struct MrviHandle MrviHandle;
 
@@ -140,6 +140,35 @@ int mrvi_run_host_csr(MrviHandle* h, int64_t n_cells, const int64_t* indptr, con
 int mrvi_distances_device(MrviHandle* h, int64_t n_cells, const float* z, int32_t n_keys,
                           const int32_t* const* group_codes, const int32_t* n_groups,
                           int32_t norm, float* cell_out, double* const* group_sums, void* stream);
+
+/*
+ * The sampled paths of the same method: get_local_sample_distances(use_mean=False) and
+ * (normalize_distances=True), i.e. the "sampled_distances" / "normalized_distances" / "sampled_representations"
+ * inputs of compute_local_statistics (src/mrvi/_model.py:406-450, 508-540), with every buffer in HOST memory.
+ *
+ * For every cell, mc_samples draws of u ~ q(u|x) are taken PER COUNTERFACTUAL SAMPLE (each vmapped call owns a PRNG
+ * stream, _model.py:136-159, _module.py:315-318), z_s is evaluated on each draw and the S x S distances are formed
+ * per (cell, draw).  With normalize != 0 they are z-scored per cell against the local baseline -- mean and variance
+ * of the distance between 2*mc_samples paired draws of z for the cell's own sample (_model.py:508-540) -- and
+ * averaged over the draws (_model.py:447-450; norm must be MRVI_NORM_L2 then, _model.py:436-439).
+ *
+ *   u_noise     [S][mc][n_cells][Lq] float32 standard-normal draws, or NULL: generated on the device by
+ *               Philox4x32-10 from (seed, cell index, draw, sample) -- independent of chunking and sharding;
+ *               cell_offset is the global index of cell 0 (a shard passes its offset so that shards reproduce
+ *               the single-GPU result)
+ *   base_noise  [2*mc][n_cells][Lq] draws of the baseline (normalize != 0 only), or NULL as above
+ *   cell_out    normalize ? [n_cells, S, S] : [n_cells, mc, S, S]   float32 or NULL
+ *   group_sums  normalize ? [n_groups[k], S, S] : [n_groups[k], mc, S, S]   float64, OVERWRITTEN
+ *   z_out       [n_cells, mc, S, L] float32 or NULL ("sampled_representations")
+ * JAX's threefry streams are not reproduced: with explicit draws the result is exact (oracle parity), against the
+ * reference itself it is statistical.  use_map=0 models (sampled eps) return MRVI_ERR_UNSUPPORTED.
+ */
+int mrvi_run_sampled_host(MrviHandle* h, int64_t n_cells, const float* X, int64_t ldx,
+                          const int32_t* sample_idx, int32_t mc_samples, uint64_t seed, int64_t cell_offset,
+                          const float* u_noise, const float* base_noise, int32_t n_keys,
+                          const int32_t* const* group_codes, const int32_t* n_groups, int32_t norm,
+                          int32_t normalize, float* cell_out, double* const* group_sums,
+                          int64_t* const* group_counts, float* z_out, int64_t chunk_cells);
 
 /* Timing taps: device milliseconds spent in each stage of the most recent mrvi_run_* call
  * (CUDA events on the launching stream; valid after that stream is synchronised).

@@ -12,7 +12,7 @@ import numpy as np
 
 from ._params import MrviDims
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 PRECISION_FP32 = 0
 PRECISION_TC = 1
 NORMS = {"l2": 0, "l1": 1, "linf": 2}
@@ -30,6 +30,7 @@ EXPORTED_SYMBOLS = (
     "mrvi_run_device",
     "mrvi_run_host",
     "mrvi_run_host_csr",
+    "mrvi_run_sampled_host",
     "mrvi_distances_device",
     "mrvi_last_stage_ms",
 )
@@ -81,6 +82,9 @@ def load_library():
     lib.mrvi_run_host_csr.restype = C.c_int
     lib.mrvi_run_host_csr.argtypes = [vp, i64, vp, vp, vp, vp, i32, C.POINTER(vp), C.POINTER(i32), i32, vp,
                                       C.POINTER(vp), C.POINTER(vp), vp, vp, i64]
+    lib.mrvi_run_sampled_host.restype = C.c_int
+    lib.mrvi_run_sampled_host.argtypes = [vp, i64, vp, i64, vp, i32, C.c_uint64, i64, vp, vp, i32, C.POINTER(vp),
+                                          C.POINTER(i32), i32, i32, vp, C.POINTER(vp), C.POINTER(vp), vp, i64]
     lib.mrvi_distances_device.restype = C.c_int
     lib.mrvi_distances_device.argtypes = [vp, i64, vp, i32, C.POINTER(vp), C.POINTER(i32), i32, vp,
                                           C.POINTER(vp), vp]
@@ -222,6 +226,62 @@ class Handle:
             out["z"] = z
         if want_u:
             out["u"] = u
+        return out
+
+    # ---- sampled paths (use_mean=False / normalize_distances=True), host buffers
+    def run_sampled_host(self, X: np.ndarray, sample_idx: np.ndarray, mc_samples: int, seed: int = 0,
+                         cell_offset: int = 0, u_noise: Optional[np.ndarray] = None,
+                         base_noise: Optional[np.ndarray] = None, group_codes: Sequence[np.ndarray] = (),
+                         n_groups: Sequence[int] = (), norm: str = "l2", normalize: bool = False,
+                         keep_cell: bool = True, want_z: bool = False, chunk_cells: int = 0):
+        """``mrvi_run_sampled_host``: distances on ``mc_samples`` draws of u per (cell, counterfactual sample).
+        ``u_noise`` (S, mc, n, Lq) / ``base_noise`` (2 mc, n, Lq): explicit standard-normal draws (tests); default
+        is the device Philox generator keyed by ``seed`` and the global cell index ``cell_offset + i``."""
+        if norm not in NORMS:
+            raise ValueError(f"norm {norm} not supported")
+        d = self.dims
+        if hasattr(X, "toarray") and not isinstance(X, np.ndarray):
+            X = X.toarray()
+        if X.dtype != np.float32 or X.ndim != 2 or X.strides[1] != 4 or X.strides[0] % 4 != 0:
+            X = np.ascontiguousarray(X, dtype=np.float32)
+        n = X.shape[0]
+        if X.shape[1] != d.n_input:
+            raise ValueError(f"X has {X.shape[1]} genes, model expects {d.n_input}")
+        ldx = d.n_input if n <= 1 else X.strides[0] // 4
+        sid = np.ascontiguousarray(sample_idx, dtype=np.int32).reshape(-1)
+        if sid.shape[0] != n:
+            raise ValueError("sample_idx length does not match X")
+        if n and (sid.min() < 0 or sid.max() >= d.n_sample):
+            raise ValueError("sample_idx outside [0, n_sample)")
+        mc, S, L, Lq = int(mc_samples), d.n_sample, d.n_latent, d.n_latent_q
+        if u_noise is not None:
+            u_noise = np.ascontiguousarray(u_noise, dtype=np.float32)
+            if u_noise.shape != (S, mc, n, Lq):
+                raise ValueError(f"u_noise must have shape {(S, mc, n, Lq)}")
+        if base_noise is not None:
+            base_noise = np.ascontiguousarray(base_noise, dtype=np.float32)
+            if base_noise.shape != (2 * mc, n, Lq):
+                raise ValueError(f"base_noise must have shape {(2 * mc, n, Lq)}")
+        codes = [np.ascontiguousarray(c, dtype=np.int32).reshape(-1) for c in group_codes]
+        out = {}
+        cell_shape = (n, S, S) if normalize else (n, mc, S, S)
+        cell = np.empty(cell_shape, dtype=np.float32) if keep_cell else None
+        sums = [np.zeros((g, S, S) if normalize else (g, mc, S, S), dtype=np.float64) for g in n_groups]
+        counts = [np.zeros((g,), dtype=np.int64) for g in n_groups]
+        z = np.empty((n, mc, S, L), dtype=np.float32) if want_z else None
+        _check(load_library().mrvi_run_sampled_host(
+            self._h, n, X.ctypes.data, ldx, sid.ctypes.data, mc, int(seed) & (2 ** 64 - 1), int(cell_offset),
+            u_noise.ctypes.data if u_noise is not None else None,
+            base_noise.ctypes.data if base_noise is not None else None, len(codes),
+            _ptr_array([c.ctypes.data for c in codes]), _i32_array(n_groups), NORMS[norm], int(bool(normalize)),
+            cell.ctypes.data if keep_cell else None, _ptr_array([s.ctypes.data for s in sums]),
+            _ptr_array([c.ctypes.data for c in counts]), z.ctypes.data if want_z else None, int(chunk_cells)))
+        if keep_cell:
+            out["cell"] = cell
+        out["group_sums"] = sums
+        out["group_counts"] = counts
+        if want_z:
+            out["z"] = z
         return out
 
     def last_stage_ms(self):

@@ -29,6 +29,9 @@ from ._xr import DataArray, Dataset
 _PRECISIONS = {"fp32": _capi.PRECISION_FP32, "tc": _capi.PRECISION_TC}
 
 
+_SAMPLED_INPUTS = ("sampled_representations", "sampled_distances", "normalized_distances")
+
+
 def _identity(x):
     return x
 
@@ -56,10 +59,12 @@ class MrVI:
         ``"fp32"`` (FFMA, parity 1e-5) or ``"tc"`` (tcgen05 tensor cores, parity 1e-3).
     device
         CUDA device index.
+    seed
+        Seed of the sampled paths' noise generator (see ``self.seed``).
     """
 
     def __init__(self, adata, params: Mapping, sample_key: str = "sample", sample_order: Optional[Sequence] = None,
-                 precision: str = "fp32", device: int = 0, dims: Optional[MrviDims] = None):
+                 precision: str = "fp32", device: int = 0, dims: Optional[MrviDims] = None, seed: int = 0):
         if precision not in _PRECISIONS:
             raise ValueError(f"precision must be one of {sorted(_PRECISIONS)}, not {precision!r}")
         self.adata = adata
@@ -81,6 +86,10 @@ class MrVI:
             raise ValueError(f"adata has {adata.n_vars} genes, parameters expect {self.dims.n_input}")
         self.precision = precision
         self.device = int(device)
+        #: seed of the device Philox generator of the sampled paths (use_mean=False / normalize_distances=True).
+        #: Draws depend on (seed, cell index, draw, sample) only, so results are reproducible and independent of
+        #: chunking / sharding; the reference's JAX threefry streams are NOT reproduced (statistical parity).
+        self.seed = int(seed)
         self.is_trained_ = True
         self._handle = _capi.Handle(self.dims, self.params, device=self.device, precision=_PRECISIONS[precision])
         self.last_stage_ms: dict = {}
@@ -141,12 +150,11 @@ class MrVI:
             raise ValueError(f"norm {norm} not supported")
 
         reqs = _parse_local_statistics_requirements(reductions)
-        if reqs.needs_sampled_representations or reqs.needs_sampled_distances or reqs.needs_normalized_distances:
+        sampled = [r for r in reductions if r.input in _SAMPLED_INPUTS]
+        if sampled:
             if reqs.needs_normalized_distances and norm != "l2":
                 raise ValueError(f"Norm must be 'l2' when using normalized distances. Got {norm}.")
-            raise NotImplementedError(
-                "sampled / normalized distances (use_mean=False, normalize_distances=True) depend on the JAX PRNG "
-                "streams of the reference and are not part of the B200 path yet (SURVEY.md section 8(f)-1)")
+            return self._compute_with_sampled(reductions, reqs, adata, indices, batch_size, use_vmap, norm, mc_samples)
 
         idx = np.arange(adata.n_obs) if indices is None else np.asarray(indices).astype(int).reshape(-1)
         sample_codes = self._sample_codes(adata)[idx]
@@ -196,6 +204,68 @@ class MrVI:
                         "sample_y": self.sample_order},
                 name="sample_distances",
             )
+        return Dataset(final)
+
+    def _compute_with_sampled(self, reductions, reqs, adata, indices, batch_size, use_vmap, norm, mc_samples):
+        """Reductions over the sampled inputs (reference `_model.py:405-450`): ``mc_samples`` draws of u per
+        (cell, counterfactual sample) on the device (`mrvi_run_sampled_host`).  Mean-path reductions in the same
+        request go through the usual call."""
+        sampled = [r for r in reductions if r.input in _SAMPLED_INPUTS]
+        if any(not _is_identity_fn(r.fn) for r in sampled):
+            raise NotImplementedError("user reduction functions on sampled inputs are not part of the B200 path")
+        if any(r.input == "sampled_representations" and r.group_by is not None for r in sampled):
+            raise NotImplementedError("grouped reductions of sampled representations are not part of the B200 path")
+        results = {}
+        mean_reds = [r for r in reductions if r.input not in _SAMPLED_INPUTS]
+        if mean_reds:
+            ds = self.compute_local_statistics(mean_reds, adata=adata, indices=indices, batch_size=batch_size,
+                                               use_vmap=use_vmap, norm=norm, mc_samples=mc_samples)
+            results.update(ds.data_vars)
+        idx = np.arange(adata.n_obs) if indices is None else np.asarray(indices).astype(int).reshape(-1)
+        sample_codes = self._sample_codes(adata)[idx]
+        Xh = dense_float32(adata.X) if indices is None else dense_float32(adata.X[idx])
+        cell_names = self.adata.obs_names[idx].values
+        mc = int(mc_samples)
+        want_z = any(r.input == "sampled_representations" for r in sampled)
+        for normalize in (False, True):
+            fam = "normalized_distances" if normalize else "sampled_distances"
+            ung = [r for r in sampled if r.input == fam and r.group_by is None]
+            grp = [r for r in sampled if r.input == fam and r.group_by is not None]
+            z_here = want_z and not normalize
+            if not ung and not grp and not z_here:
+                continue
+            plans = [self._group_codes(adata, r.group_by, idx) for r in grp]
+            res = self._handle.run_sampled_host(Xh, sample_codes, mc, seed=self.seed, group_codes=[p[0] for p in plans],
+                                                n_groups=[len(p[1]) for p in plans], norm=norm, normalize=normalize,
+                                                keep_cell=bool(ung), want_z=z_here)
+            mc_dims = [] if normalize else ["mc_sample"]
+            mc_coords = {} if normalize else {"mc_sample": np.arange(mc)}
+            for r in ung:
+                results[r.name] = DataArray(
+                    res["cell"], dims=["cell_name", *mc_dims, "sample_x", "sample_y"],
+                    coords={"cell_name": cell_names, **mc_coords, "sample_x": self.sample_order,
+                            "sample_y": self.sample_order}, name="sample_distances")
+            for gi, r in enumerate(grp):
+                codes, cats, counts = plans[gi]
+                present = np.bincount(codes[codes >= 0], minlength=len(cats))
+                for c, p in zip(cats, present):
+                    if p == 0:
+                        raise KeyError(c)
+                shape = (-1,) + (1,) * (res["group_sums"][gi].ndim - 1)
+                means = (res["group_sums"][gi] / counts.reshape(shape).astype(np.float64)).astype(np.float32)
+                results[r.name] = DataArray(
+                    means, dims=[f"{r.group_by}_name", *mc_dims, "sample_x", "sample_y"],
+                    coords={f"{r.group_by}_name": np.asarray(cats), **mc_coords, "sample_x": self.sample_order,
+                            "sample_y": self.sample_order}, name="sample_distances")
+            if z_here:
+                for r in sampled:
+                    if r.input == "sampled_representations":
+                        results[r.name] = DataArray(
+                            res["z"], dims=["cell_name", "mc_sample", "sample", "latent_dim"],
+                            coords={"cell_name": cell_names, "sample": self.sample_order}, name="sample_representations")
+        final = OrderedDict()
+        for r in list(reqs.ungrouped_reductions) + list(reqs.grouped_reductions):
+            final[r.name] = results[r.name]
         return Dataset(final)
 
     def _wrap_dists(self, d, cell_names):

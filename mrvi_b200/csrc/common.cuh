@@ -49,6 +49,7 @@ struct NetW {
   const float* sample_effect;  // [S][H]
   ResnetW enc_blocks[kMaxBlocks];
   DenseW enc_mean;  // H -> Lq
+  DenseW enc_scale; // H -> Lq, softplus head of q(u|x) (reference _components.py:96); w == nullptr when not supplied
   // ---- qz (EncoderUZ + AttentionBlock)
   LnW u_ln;
   DenseW q_tok;   // Lq -> E, no bias   (DenseGeneral_0)
@@ -71,6 +72,12 @@ struct CellBuf {
   float* u_ln;   // [n][Lq]   LayerNorm(u)                (reference _module.py:142)
   float* q_tok;  // [n][E]    DenseGeneral((E,1))(u_ln)   (reference _components.py:195-197)
   float* zbase;  // [n][L]    Dense(L)(u) or u            (reference _module.py:166-170)
+  // ---- sampled paths only (use_mean=False / normalize_distances=True, reference _module.py:315-318)
+  float* u_scale;              // [n][Lq] scale of q(u|x), written by the encoder when non-null
+  int per_row;                 // 1: u_ln / q_tok / zbase are indexed by ROW (cell * rows_per_cell + s): every
+                               //    (cell, s) row carries its own draw of u
+  const int32_t* cell_sample;  // non-null: all rows of cell c use the per-sample tables of sample cell_sample[c]
+                               //    (the local baseline of reference _model.py:508-540 evaluates the cell's own sample)
 };
 
 // Group-reduction plan for one chunk of cells (device pointers).

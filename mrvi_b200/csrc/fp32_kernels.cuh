@@ -307,6 +307,17 @@ k_encoder_fp32(const __grid_constant__ NetW net, const float* __restrict__ X, in
   cta_dense(cur, ldh, net.enc_mean, nxt, ldh, kTM);
   __syncthreads();
   const int Lq = net.Lq, Lq4 = net.enc_mean.ld;
+  if (cb.u_scale != nullptr && net.enc_scale.w != nullptr) {
+    // scale head: softplus(Dense(h)) + 1e-5  (reference _components.py:96-97), only for the sampled paths
+    cta_dense(cur, ldh, net.enc_scale, hid, ldhid, kTM);
+    __syncthreads();
+    for (int idx = tid; idx < TM * Lq; idx += kThreads) {
+      const int r = idx / Lq, c = idx % Lq;
+      const float v = hid[(size_t)r * ldhid + c];
+      cb.u_scale[(cell0 + r) * Lq + c] = (v > 20.f ? v : log1pf(expf(v))) + 1e-5f;
+    }
+    __syncthreads();
+  }
   // u_ln = LayerNorm(u; scale, bias) -> cur[:, 0:Lq4]
   cta_ln_rows<0>(nxt, ldh, kTM, Lq, Lq4, net.u_ln.scale, net.u_ln.bias, nullptr, nullptr, nullptr,
                  nullptr, 0, cur, ldh);
@@ -335,14 +346,16 @@ k_encoder_fp32(const __grid_constant__ NetW net, const float* __restrict__ X, in
 // Stage 2: q(z | u, s) for kTM consecutive (cell, s) rows per CTA.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads)
-k_qz_fp32(const __grid_constant__ NetW net, CellBuf cb, int64_t n_cells, float* __restrict__ z_out,
+k_qz_fp32(const __grid_constant__ NetW net, CellBuf cb, int64_t n_cells, int rows_per_cell, float* __restrict__ z_out,
           int lda_att, int ldhid, int ldm, int ldc) {
   extern __shared__ __align__(16) float smem[];
   float* att = smem;                                  // [kTM][lda_att]  attention output (E*C cols)
   float* hid = att + (size_t)kTM * lda_att;           // [kTM][ldhid]    resnet hidden (+ skip)
   float* mbuf = hid + (size_t)kTM * ldhid;            // [kTM][ldm]      M-wide block outputs
   float* cbuf = mbuf + (size_t)kTM * ldm;             // [kTM][ldc]      concat [u_ln, eps_] / final output
-  const int S = net.S, E = net.E, C = net.C, nh = net.nh, hd = net.C, Lq = net.Lq, L = net.L;
+  // rows_per_cell = S on the mean path (row -> (cell, s)); the sampled paths re-map rows through cb.per_row /
+  // cb.cell_sample (see CellBuf)
+  const int S = rows_per_cell, E = net.E, C = net.C, nh = net.nh, hd = net.C, Lq = net.Lq, L = net.L;
   const int64_t row0 = (int64_t)blockIdx.x * kTM;
   const int64_t n_rows = n_cells * S;
   const int tid = threadIdx.x;
@@ -353,12 +366,13 @@ k_qz_fp32(const __grid_constant__ NetW net, CellBuf cb, int64_t n_cells, float* 
     const int64_t row = row0 + r;
     const bool valid = row < n_rows;
     const int64_t cell = valid ? row / S : 0;
-    const int s = valid ? (int)(row % S) : 0;
+    const int s = valid ? (cb.cell_sample ? cb.cell_sample[cell] : (int)(row % S)) : 0;
+    const int64_t fi = cb.per_row ? (valid ? row : 0) : cell;
     const float* ktab = net.ktab + (size_t)s * E * nh * hd;
     const float* vtab = net.vtab + (size_t)s * E * nh * hd;
     const float inv_sqrt_d = 1.0f / sqrtf((float)hd);
     for (int i = q4; i < E; i += 4) {
-      const float qt = valid ? cb.q_tok[cell * E + i] : 0.f;
+      const float qt = valid ? cb.q_tok[fi * E + i] : 0.f;
       float o[kMaxHeadDim];
 #pragma unroll
       for (int c = 0; c < kMaxHeadDim; ++c) o[c] = (c < C) ? __ldg(net.bo + c) : 0.f;
@@ -423,7 +437,7 @@ k_qz_fp32(const __grid_constant__ NetW net, CellBuf cb, int64_t n_cells, float* 
       const int64_t row = row0 + r;
       float v = 0.f;
       if (row < n_rows) {
-        if (c < Lq) v = cb.u_ln[(row / S) * Lq + c];
+        if (c < Lq) v = cb.u_ln[(cb.per_row ? row : row / S) * Lq + c];
         else if (c < W) v = att[(size_t)r * lda_att + (c - Lq)];
       }
       cbuf[(size_t)r * ldc + c] = v;
@@ -449,7 +463,7 @@ k_qz_fp32(const __grid_constant__ NetW net, CellBuf cb, int64_t n_cells, float* 
   for (int idx = tid; idx < kTM * L; idx += kThreads) {
     const int r = idx / L, c = idx % L;
     const int64_t row = row0 + r;
-    if (row < n_rows) z_out[row * L + c] = cb.zbase[(row / S) * L + c] + hid[(size_t)r * ldhid + c];
+    if (row < n_rows) z_out[row * L + c] = cb.zbase[(cb.per_row ? row : row / S) * L + c] + hid[(size_t)r * ldhid + c];
   }
 }
 

@@ -17,6 +17,7 @@
 #include "tc_kernels.cuh"
 #include "tc_encoder.cuh"
 #include "tc_fused.cuh"
+#include "sampled_kernels.cuh"
 
 namespace mrvi {
 
@@ -251,6 +252,10 @@ static int build_net(MrviHandle* h, const ParamTable& pt) {
   for (int b = 0; b < d.encoder_n_layers; ++b)
     if ((err = pack_resnet(h, pt, "qu/NormalDistOutputNN_0/ResnetBlock_" + std::to_string(b), H, H, &n.enc_blocks[b]))) return err;
   if ((err = pack_dense(h, pt, "qu/NormalDistOutputNN_0/Dense_0", H, Lq, true, &n.enc_mean))) return err;
+  n.enc_scale = DenseW{};
+  if (pt.has("qu/NormalDistOutputNN_0/Dense_1/kernel")) {  // optional: only the sampled paths read the scale head
+    if ((err = pack_dense(h, pt, "qu/NormalDistOutputNN_0/Dense_1", H, Lq, true, &n.enc_scale))) return err;
+  }
   if ((err = pack_ln(h, pt, "qz/u_ln", Lq, &n.u_ln))) return err;
   const std::string ab = "qz/AttentionBlock_0";
   if ((err = pack_dense(h, pt, ab + "/DenseGeneral_0", Lq, E, false, &n.q_tok))) return err;  // kernel (Lq,E,1)
@@ -354,10 +359,11 @@ static int launch_encoder(MrviHandle* h, const float* X, int64_t ldx, const int3
   return 0;
 }
 
-static int launch_qz(MrviHandle* h, int64_t n, float* z, cudaStream_t st) {
-  const int64_t rows = n * h->net.S;
+static int launch_qz(MrviHandle* h, const CellBuf& cb, int64_t n, int rows_per_cell, float* z, cudaStream_t st) {
+  const int64_t rows = n * rows_per_cell;
+  if (rows == 0) return 0;
   const int grid = (int)((rows + kTM - 1) / kTM);
-  k_qz_fp32<<<grid, kThreads, h->qz_smem, st>>>(h->net, h->cb, n, z, h->qz_lda, h->qz_ldhid, h->qz_ldm, h->qz_ldc);
+  k_qz_fp32<<<grid, kThreads, h->qz_smem, st>>>(h->net, cb, n, rows_per_cell, z, h->qz_lda, h->qz_ldhid, h->qz_ldm, h->qz_ldc);
   LAUNCH_CHECK();
   return 0;
 }
@@ -478,7 +484,7 @@ static int run_device_impl(MrviHandle* h, int64_t n, const float* X, int64_t ldx
         if ((err = tc_launch_qz(h->tc, h->net, m, h->cb, z, st))) return err;
         LAUNCH_CHECK();
       } else {
-        if ((err = launch_qz(h, m, z, st))) return err;
+        if ((err = launch_qz(h, h->cb, m, net.S, z, st))) return err;
       }
     }
     if (time_stages) cudaEventRecord(e2, st);
@@ -490,6 +496,193 @@ static int run_device_impl(MrviHandle* h, int64_t n, const float* X, int64_t ldx
     }
     if (time_stages) cudaEventRecord(e3, st);
   }
+  return 0;
+}
+
+
+// ------------------------------------------------------------------------------------------
+// sampled paths: see sampled_kernels.cuh
+// q(z|u,s) chain (+ distances / group sums) over n (virtual) cells whose rows carry their own features
+static int chain_and_dist(MrviHandle* h, const CellBuf& cb, int64_t n, int norm, float* z_out, float* z_scratch,
+                          float* cell_out, const GroupPlan& gp, cudaStream_t st) {
+  const NetW& net = h->net;
+  const bool need_dist = cell_out != nullptr || gp.n_keys > 0;
+  int err;
+  if (h->precision == MRVI_PRECISION_TC && need_dist && h->tc.fused_smem_bytes && tc_fused_supported(h->tc, net.S, norm)) {
+    tc_launch_fused(h->tc, net, n, cb, z_out, cell_out, gp, st);
+    LAUNCH_CHECK();
+    return 0;
+  }
+  float* z = z_out ? z_out : z_scratch;
+  if (h->precision == MRVI_PRECISION_TC) {
+    if ((err = tc_launch_qz(h->tc, net, n, cb, z, st))) return err;
+    LAUNCH_CHECK();
+  } else if ((err = launch_qz(h, cb, n, net.S, z, st))) return err;
+  if (need_dist && (err = launch_dist(h, z, n, norm, cell_out, gp, st))) return err;
+  return 0;
+}
+
+static int run_sampled_host_impl(MrviHandle* h, int64_t n_cells, const float* X, int64_t ldx, const int32_t* sample_idx,
+                                 int mc, uint64_t seed, int64_t cell_offset, const float* u_noise, const float* base_noise,
+                                 int n_keys, const int32_t* const* group_codes, const int32_t* n_groups, int norm,
+                                 int normalize, float* cell_out, double* const* group_sums, int64_t* const* group_counts,
+                                 float* z_out, int64_t chunk_cells) {
+  int err;
+  if ((err = validate_run(h, n_cells, X, ldx, sample_idx, n_keys, group_codes, n_groups, norm, group_sums))) return err;
+  if (mc <= 0 || mc > 4096) return fail(MRVI_ERR_INVALID_ARG, "mc_samples must be in [1, 4096]");
+  if (normalize && norm != MRVI_NORM_L2) return fail(MRVI_ERR_INVALID_ARG, "Norm must be 'l2' when using normalized distances");
+  if (!h->dims.use_map) return fail(MRVI_ERR_UNSUPPORTED, "sampled paths with use_map=False (sampled eps) are not implemented");
+  if (h->net.enc_scale.w == nullptr)
+    return fail(MRVI_ERR_PARAM, "missing parameter 'qu/NormalDistOutputNN_0/Dense_1/kernel' (scale head of q(u|x), needed by the sampled paths)");
+  if (h->net.Lq > kMaxLq) return fail(MRVI_ERR_UNSUPPORTED, "n_latent_u > %d", kMaxLq);
+  CUDA_TRY(cudaSetDevice(h->device));
+  const NetW& net = h->net;
+  const int S = net.S, L = net.L, G = net.G, Lq = net.Lq, E = net.E;
+  const int64_t SS = (int64_t)S * S;
+  for (int k = 0; k < n_keys; ++k) {
+    for (int64_t i = 0; i < n_cells; ++i) {
+      const int g = group_codes[k][i];
+      if (g < -1 || g >= n_groups[k])
+        return fail(MRVI_ERR_INVALID_ARG, "group key %d: code %d of cell %lld outside [-1, %d)", k, g, (long long)i, n_groups[k]);
+    }
+    if ((int64_t)n_groups[k] * (normalize ? 1 : mc) > (1 << 24)) return fail(MRVI_ERR_UNSUPPORTED, "n_groups * mc_samples too large");
+    if (group_counts && group_counts[k]) {
+      for (int g = 0; g < n_groups[k]; ++g) group_counts[k][g] = 0;
+      for (int64_t i = 0; i < n_cells; ++i) if (group_codes[k][i] >= 0) group_counts[k][group_codes[k][i]]++;
+    }
+  }
+  const int gmul = normalize ? 1 : mc;  // group sums keep the mc axis unless normalised
+  // ---- chunk: virtual cells (cell, draw) must fit the handle's sort / workspace buffers; bound staging to ~1.5 GiB
+  const int64_t per_cell = (int64_t)mc * S * (Lq + E + L + L + S) * 4 + (int64_t)G * 4 + (int64_t)2 * mc * (Lq + E + 2 * L) * 4;
+  int64_t ch = std::max<int64_t>(1, std::min<int64_t>(h->chunk_cells / mc, (1536ll << 20) / per_cell));
+  if (chunk_cells > 0) ch = std::min(ch, chunk_cells);
+  ch = std::min<int64_t>(ch, std::max<int64_t>(n_cells, 1));
+  if (h->chunk_cells / mc < 1) return fail(MRVI_ERR_UNSUPPORTED, "mc_samples=%d too large for the workspace", mc);
+  const int64_t nvmax = ch * mc;
+
+  DeviceArena ws;  // everything of this call; released on return
+  cudaStream_t st = nullptr;
+  float *dX, *d_scale, *d_mu, *d_var, *d_zb, *d_z, *d_dv = nullptr, *d_cell = nullptr, *d_unoise = nullptr, *d_bnoise = nullptr;
+  int32_t *d_sid, *d_codes[kMaxKeys] = {}, *d_vcodes[kMaxKeys] = {};
+  double* d_sums[kMaxKeys] = {};
+  CellBuf rcb{}, bcb{};
+  CUDA_TRY(ws.alloc((void**)&dX, ch * G * sizeof(float)));
+  CUDA_TRY(ws.alloc((void**)&d_sid, ch * sizeof(int32_t)));
+  CUDA_TRY(ws.alloc((void**)&d_scale, ch * Lq * sizeof(float)));
+  CUDA_TRY(ws.alloc((void**)&rcb.u_ln, nvmax * S * Lq * sizeof(float)));
+  CUDA_TRY(ws.alloc((void**)&rcb.q_tok, nvmax * S * E * sizeof(float)));
+  CUDA_TRY(ws.alloc((void**)&rcb.zbase, nvmax * S * L * sizeof(float)));
+  rcb.per_row = 1;
+  CUDA_TRY(ws.alloc((void**)&d_z, nvmax * S * L * sizeof(float)));
+  if (normalize) {
+    CUDA_TRY(ws.alloc((void**)&bcb.u_ln, ch * 2 * mc * Lq * sizeof(float)));
+    CUDA_TRY(ws.alloc((void**)&bcb.q_tok, ch * 2 * mc * E * sizeof(float)));
+    CUDA_TRY(ws.alloc((void**)&bcb.zbase, ch * 2 * mc * L * sizeof(float)));
+    bcb.per_row = 1;
+    bcb.cell_sample = d_sid;
+    CUDA_TRY(ws.alloc((void**)&d_zb, ch * 2 * mc * L * sizeof(float)));
+    CUDA_TRY(ws.alloc((void**)&d_mu, ch * sizeof(float)));
+    CUDA_TRY(ws.alloc((void**)&d_var, ch * sizeof(float)));
+    CUDA_TRY(ws.alloc((void**)&d_dv, nvmax * SS * sizeof(float)));
+    if (cell_out) CUDA_TRY(ws.alloc((void**)&d_cell, ch * SS * sizeof(float)));
+  } else if (cell_out) {
+    CUDA_TRY(ws.alloc((void**)&d_cell, nvmax * SS * sizeof(float)));
+  }
+  for (int k = 0; k < n_keys; ++k) {
+    CUDA_TRY(ws.alloc((void**)&d_codes[k], ch * sizeof(int32_t)));
+    if (!normalize) CUDA_TRY(ws.alloc((void**)&d_vcodes[k], nvmax * sizeof(int32_t)));
+    CUDA_TRY(ws.alloc((void**)&d_sums[k], (size_t)n_groups[k] * gmul * SS * sizeof(double)));
+    CUDA_TRY(cudaMemsetAsync(d_sums[k], 0, (size_t)n_groups[k] * gmul * SS * sizeof(double), st));
+  }
+  if (u_noise) {
+    CUDA_TRY(ws.alloc((void**)&d_unoise, (size_t)S * mc * n_cells * Lq * sizeof(float)));
+    CUDA_TRY(cudaMemcpyAsync(d_unoise, u_noise, (size_t)S * mc * n_cells * Lq * sizeof(float), cudaMemcpyHostToDevice, st));
+  }
+  if (normalize && base_noise) {
+    CUDA_TRY(ws.alloc((void**)&d_bnoise, (size_t)2 * mc * n_cells * Lq * sizeof(float)));
+    CUDA_TRY(cudaMemcpyAsync(d_bnoise, base_noise, (size_t)2 * mc * n_cells * Lq * sizeof(float), cudaMemcpyHostToDevice, st));
+  }
+  int32_t ng_eff[kMaxKeys];
+  for (int k = 0; k < n_keys; ++k) ng_eff[k] = n_groups[k] * gmul;
+  if (n_keys > 0) CUDA_TRY(cudaMemcpyAsync(h->n_groups_dev, ng_eff, n_keys * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+
+  h->ev_used = 0;
+  CUDA_TRY(cudaEventRecord(h->ev_call[0], st));
+  for (int64_t lo = 0; lo < n_cells; lo += ch) {
+    const int64_t m = std::min(ch, n_cells - lo), nv = m * mc;
+    CUDA_TRY(cudaMemcpy2DAsync(dX, (size_t)G * sizeof(float), X + lo * ldx, (size_t)ldx * sizeof(float), (size_t)G * sizeof(float),
+                               (size_t)m, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_sid, sample_idx + lo, m * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    for (int k = 0; k < n_keys; ++k)
+      CUDA_TRY(cudaMemcpyAsync(d_codes[k], group_codes[k] + lo, m * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    // ---- q(u|x): mean and scale (fp32 tail; the G -> H contraction on the tensor cores in TC mode)
+    CellBuf ecb = h->cb;
+    ecb.u_scale = d_scale;
+    {
+      const float* h1 = nullptr;
+      if (h->precision == MRVI_PRECISION_TC && h->enc_tc.ready) {
+        enc_tc_launch(h->enc_tc, dX, G, m, G, h->h1buf, st);
+        LAUNCH_CHECK();
+        h1 = h->h1buf;
+      }
+      k_encoder_fp32<<<(unsigned)((m + kTM - 1) / kTM), kThreads, h->enc_smem, st>>>(h->net, dX, G, d_sid, m, ecb, h->enc_ldh,
+                                                                                    h->enc_ldhid, (G % 4) == 0, h1);
+      LAUNCH_CHECK();
+    }
+    // ---- draws of u and the per-row chain inputs for the (cell, draw, sample) rows
+    {
+      const int64_t rows = nv * S;
+      k_sample_rows<<<(unsigned)((rows + 127) / 128), 128, 0, st>>>(h->net, ecb.u, d_scale, m, mc, S, d_unoise, lo, n_cells,
+                                                                   cell_offset + lo, seed, 0u, rcb.u_ln, rcb.q_tok, rcb.zbase);
+      LAUNCH_CHECK();
+    }
+    float* dz_out = z_out ? d_z : nullptr;
+    if (!normalize) {
+      GroupPlan gp;
+      const int32_t* vptr[kMaxKeys];
+      for (int k = 0; k < n_keys; ++k) {
+        k_virtual_codes<<<(unsigned)((nv + 255) / 256), 256, 0, st>>>(d_codes[k], m, mc, n_groups[k], d_vcodes[k]);
+        LAUNCH_CHECK();
+        vptr[k] = d_vcodes[k];
+      }
+      if ((err = plan_groups(h, nv, n_keys, vptr, 0, ng_eff, d_sums, &gp, st))) return err;
+      if ((err = chain_and_dist(h, rcb, nv, norm, dz_out, d_z, d_cell, gp, st))) return err;
+      if (cell_out)
+        CUDA_TRY(cudaMemcpyAsync(cell_out + lo * mc * SS, d_cell, nv * SS * sizeof(float), cudaMemcpyDeviceToHost, st));
+    } else {
+      // local baseline: 2 mc draws for the cell's own sample (reference _model.py:508-540)
+      const int64_t brow = m * 2 * mc;
+      k_sample_rows<<<(unsigned)((brow + 127) / 128), 128, 0, st>>>(h->net, ecb.u, d_scale, m, 2 * mc, 1, d_bnoise, lo, n_cells,
+                                                                   cell_offset + lo, seed, 1u, bcb.u_ln, bcb.q_tok, bcb.zbase);
+      LAUNCH_CHECK();
+      if (h->precision == MRVI_PRECISION_TC) {
+        if ((err = tc_launch_qz(h->tc, net, m, bcb, d_zb, st, 2 * mc))) return err;
+        LAUNCH_CHECK();
+      } else if ((err = launch_qz(h, bcb, m, 2 * mc, d_zb, st))) return err;
+      k_baseline_stats<<<(unsigned)((m + 7) / 8), 256, 0, st>>>(d_zb, m, mc, L, d_mu, d_var);
+      LAUNCH_CHECK();
+      GroupPlan none;
+      memset(&none, 0, sizeof(none));
+      if ((err = chain_and_dist(h, rcb, nv, norm, dz_out, d_z, d_dv, none, st))) return err;
+      GroupPlan gp;
+      const int32_t* cptr[kMaxKeys];
+      for (int k = 0; k < n_keys; ++k) cptr[k] = d_codes[k];
+      if ((err = plan_groups(h, m, n_keys, cptr, 0, ng_eff, d_sums, &gp, st))) return err;
+      const int eb = (int)((SS + 255) / 256);
+      int64_t target = std::max<int64_t>(1, (int64_t)h->sm_count * 8 / eb);
+      const int cpw = (int)std::max<int64_t>(1, (m + target - 1) / target);
+      dim3 grid((unsigned)((m + cpw - 1) / cpw), (unsigned)eb);
+      k_normalize_mc<<<grid, 256, 0, st>>>(d_dv, d_mu, d_var, m, mc, (int)SS, d_cell, gp, cpw);
+      LAUNCH_CHECK();
+      if (cell_out) CUDA_TRY(cudaMemcpyAsync(cell_out + lo * SS, d_cell, m * SS * sizeof(float), cudaMemcpyDeviceToHost, st));
+    }
+    if (z_out) CUDA_TRY(cudaMemcpyAsync(z_out + lo * mc * S * L, d_z, nv * S * L * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));  // staging buffers are single: finish the chunk before the next upload
+  }
+  CUDA_TRY(cudaEventRecord(h->ev_call[1], st));
+  for (int k = 0; k < n_keys; ++k)
+    CUDA_TRY(cudaMemcpyAsync(group_sums[k], d_sums[k], (size_t)n_groups[k] * gmul * SS * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
   return 0;
 }
 
@@ -758,6 +951,15 @@ int mrvi_run_host_csr(MrviHandle* h, int64_t n_cells, const int64_t* indptr, con
   if (!indptr) return fail(MRVI_ERR_INVALID_ARG, "indptr is null");
   return run_host_impl(h, n_cells, nullptr, h ? h->dims.n_input : 0, indptr, indices, data, sample_idx, n_keys, group_codes, n_groups,
                        norm, cell_out, group_sums, group_counts, z_out, u_out, chunk_cells);
+}
+
+int mrvi_run_sampled_host(MrviHandle* h, int64_t n_cells, const float* X, int64_t ldx, const int32_t* sample_idx,
+                          int32_t mc_samples, uint64_t seed, int64_t cell_offset, const float* u_noise, const float* base_noise,
+                          int32_t n_keys, const int32_t* const* group_codes, const int32_t* n_groups, int32_t norm,
+                          int32_t normalize, float* cell_out, double* const* group_sums, int64_t* const* group_counts,
+                          float* z_out, int64_t chunk_cells) {
+  return run_sampled_host_impl(h, n_cells, X, ldx, sample_idx, mc_samples, seed, cell_offset, u_noise, base_noise, n_keys,
+                               group_codes, n_groups, norm, normalize, cell_out, group_sums, group_counts, z_out, chunk_cells);
 }
 
 int mrvi_last_stage_ms(MrviHandle* h, float out_ms[4]) {

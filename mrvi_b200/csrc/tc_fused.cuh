@@ -368,6 +368,9 @@ k_chain_fused_tc(const __grid_constant__ TcNet tc, CellBuf cb, int64_t n_cells, 
     const int64_t cell = valid ? (gp.order ? (int64_t)gp.order[pos] : pos) : 0;
     const int code = (valid && gp.n_keys) ? gp.comp_sorted[pos] : -2;
     const int ss = valid ? s : 0;
+    // sampled paths: every (cell, s) row carries its own draw of u (CellBuf::per_row); z_base then differs
+    // between the rows of a cell and no longer cancels in the distances
+    const int64_t fi = cb.per_row ? (valid ? cell * S + s : 0) : cell;
 
     // ================= attention features of head `half` -> A1 chunks 2*half, 2*half+1 =================
     {
@@ -380,7 +383,7 @@ k_chain_fused_tc(const __grid_constant__ TcNet tc, CellBuf cb, int64_t n_cells, 
         kv2[2 * q + 1] = make_float2(t4.z, t4.w);
       }
       const float rmax = __ldg(tc.kvref + ss * 2), rmin = __ldg(tc.kvref + ss * 2 + 1);
-      const float* qp = cb.q_tok + cell * 16;
+      const float* qp = cb.q_tok + fi * 16;
 #pragma unroll 1
       for (int it = 0; it < 8; ++it) {  // one packed word (two features) per iteration
         float mm[2];
@@ -411,7 +414,7 @@ k_chain_fused_tc(const __grid_constant__ TcNet tc, CellBuf cb, int64_t n_cells, 
           *reinterpret_cast<uint4*>(row_a1l + c * 2048) = make_uint4(0u, 0u, 0u, 0u);
         }
       } else {          // A3 static part: columns 32.. = u_ln[0..Lq), then 1.0, then zeros
-        const float* ul = cb.u_ln + cell * Lq;
+        const float* ul = cb.u_ln + fi * Lq;
         for (int c = 4; c < tc.K3 / 8; ++c) {
           uint32_t hw[4], lw[4];
 #pragma unroll
@@ -493,11 +496,17 @@ k_chain_fused_tc(const __grid_constant__ TcNet tc, CellBuf cb, int64_t n_cells, 
       if (ncol == 16) tmem_ld16(t_lane + col0, v); else tmem_ld32(t_lane + col0, v);
       tmem_ld_wait();
       if (valid && z_out != nullptr) {
-        const float* zb = cb.zbase + cell * L;
+        const float* zb = cb.zbase + fi * L;
         float* dst = z_out + (cell * S + s) * (int64_t)L;
 #pragma unroll
         for (int l = 0; l < 32; ++l)
           if (l < ncol && col0 + l < L) dst[col0 + l] = __ldg(zb + col0 + l) + v[l];
+      }
+      if (cb.per_row && valid && need_dist) {
+        const float* zb = cb.zbase + fi * L;
+#pragma unroll
+        for (int l = 0; l < 32; ++l)
+          if (l < ncol && col0 + l < L) v[l] += __ldg(zb + col0 + l);
       }
       if (need_dist) {
         // A1/A3 are dead (GEMM5 done): overlay the fp32 residual tile on them

@@ -373,8 +373,9 @@ k_chain_tc(const __grid_constant__ TcNet tc, CellBuf cb, int64_t n_cells, int S,
       s = (int)(tile % tiles_per_cell) * kTcRows + tid;
       valid = s < S;
     }
-    const int64_t cc = valid ? cell : 0;
-    const int ss = valid ? s : 0;
+    // the sampled paths re-map rows: per-row features and / or the cell's own sample tables (see CellBuf)
+    const int64_t cc = valid ? (cb.per_row ? cell * S + s : cell) : 0;
+    const int ss = valid ? (cb.cell_sample ? __ldg(cb.cell_sample + cell) : s) : 0;
 
     // ---- attention features m[h*16+i] -> A1 = [m | 1 | 0...], A3 static part = [.. | u_ln | 1 | 0..]
     {
@@ -532,7 +533,7 @@ k_chain_tc(const __grid_constant__ TcNet tc, CellBuf cb, int64_t n_cells, int S,
       if (tc.N5 > 32) tmem_ld32(t_lane + 32, v + 32);
       tmem_ld_wait();
       if (valid && z_out != nullptr) {
-        const float* zb = cb.zbase + cell * L;
+        const float* zb = cb.zbase + cc * L;
         float* dst = z_out + (cell * S + s) * (int64_t)L;
 #pragma unroll
         for (int l = 0; l < 64; ++l)
@@ -728,8 +729,10 @@ inline int tc_build(TcNet& tc, const NetW& net, const MrviDims& d, const tc_deta
 }
 
 // launches the chain for n cells; per-cell inputs (q_tok, u_ln, zbase) must already be in cb
-inline int tc_launch_qz(const TcNet& tc, const NetW& net, int64_t n, const CellBuf& cb, float* z, cudaStream_t st) {
-  const int S = net.S;
+// rows_per_cell: 0 = net.S (mean path); the baseline of the sampled paths runs 2 * mc rows per cell
+inline int tc_launch_qz(const TcNet& tc, const NetW& net, int64_t n, const CellBuf& cb, float* z, cudaStream_t st,
+                        int rows_per_cell = 0) {
+  const int S = rows_per_cell > 0 ? rows_per_cell : net.S;
   int cpt = 1, tpc = 1;
   int64_t n_tiles;
   if (S <= kTcRows) { cpt = kTcRows / S; n_tiles = (n + cpt - 1) / cpt; }

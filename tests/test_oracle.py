@@ -131,3 +131,38 @@ def test_tensor_core_algebra_is_exact_without_rounding(dk):
     zb = orc.dense(u, p64, "qz/Dense_0") if dims.n_latent_u is not None else u
     res = tce.tc_chain_residual(p, u, None, None)[..., : dims.n_latent]
     assert np.abs(res - (z - zb[:, None, :])).max() / np.abs(z).max() < 5e-6
+
+
+def test_philox_mirror_known_answers():
+    """Random123 known-answer vectors for philox4x32-10 (the generator of the device noise, oracle/philox.py)."""
+    from oracle import philox
+
+    kat = [((0, 0, 0, 0), 0, (0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8)),
+           ((0xFFFFFFFF,) * 4, 0xFFFFFFFFFFFFFFFF, (0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD)),
+           ((0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344), (0x299F31D0 << 32) | 0xA4093822,
+            (0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1))]
+    for ctr, key, want in kat:
+        got = tuple(int(v) for v in philox.philox4x32_10(*ctr, key))
+        assert got == want
+    x = philox.u_noise(3000, 4, 2, 10, seed=7)
+    assert abs(float(x.mean())) < 5e-3 and abs(float(x.std()) - 1.0) < 5e-3
+
+
+def test_sampled_oracle_properties():
+    """Sampled paths: zero noise == mean path; the baseline statistics follow `_model.py:535-540`."""
+    dims = mrvi_b200.MrviDims(n_input=40, n_sample=5)
+    flat = mrvi_b200.init_params(dims, seed=2)
+    X = mrvi_b200.synthetic_counts(10, 40, seed=3)
+    sid = (np.arange(10) % 5).astype(np.int32)
+    z0 = orc.sampled_counterfactual_z(flat, X, sid, np.zeros((5, 2, 10, dims.n_latent_q)))
+    assert np.abs(z0[:, 0] - orc.counterfactual_z(flat, X, sid)).max() < 1e-13
+    rng = np.random.default_rng(0)
+    nb = rng.standard_normal((6, 10, dims.n_latent_q))
+    mu, var = orc.local_baseline_dists(flat, X, sid, nb)
+    assert mu.shape == (10,) and (mu > 0).all() and (var >= 0).all()
+    nu = rng.standard_normal((5, 3, 10, dims.n_latent_q))
+    d = orc.sampled_local_sample_distances(flat, X, sid, nu)
+    assert d.shape == (10, 3, 5, 5) and np.allclose(d, np.swapaxes(d, 2, 3))
+    dn = orc.sampled_local_sample_distances(flat, X, sid, nu, nb, normalize=True)
+    assert dn.shape == (10, 5, 5)
+    assert np.allclose(np.diagonal(dn, axis1=1, axis2=2), (-mu / np.sqrt(var))[:, None])
