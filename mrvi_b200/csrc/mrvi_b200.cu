@@ -17,6 +17,7 @@
 #include "tc_kernels.cuh"
 #include "tc_encoder.cuh"
 #include "tc_fused.cuh"
+#include "tc_dist.cuh"
 #include "sampled_kernels.cuh"
 
 namespace mrvi {
@@ -116,6 +117,7 @@ struct MrviHandle {
   TcNet tc{};
   EncTc enc_tc{};
   EncTail enc_tail{};
+  size_t dist_tc_smem = 0;  // k_dist_gram_tc (128 < S <= 256), 0 = unavailable
   float* h1buf = nullptr;  // [chunk][128] Dense_0 output of the tensor-core encoder GEMM
   // workspace for one chunk of cells
   int64_t chunk_cells = 0;
@@ -395,6 +397,11 @@ static int launch_dist_t(MrviHandle* h, const float* z, int64_t n, float* cell_o
 
 static int launch_dist(MrviHandle* h, const float* z, int64_t n, int norm, float* cell_out, const GroupPlan& gp, cudaStream_t st) {
   if (cell_out == nullptr && gp.n_keys == 0) return 0;
+  if (h->precision == MRVI_PRECISION_TC && h->dist_tc_smem && dist_tc_supported(h->net.S, h->net.L, norm)) {
+    dist_tc_launch(z, n, h->net.S, h->net.L, cell_out, gp, h->sm_count, h->dist_tc_smem, st);
+    LAUNCH_CHECK();
+    return 0;
+  }
   switch (norm) {
     case MRVI_NORM_L2: return launch_dist_t<0>(h, z, n, cell_out, gp, st);
     case MRVI_NORM_L1: return launch_dist_t<1>(h, z, n, cell_out, gp, st);
@@ -748,6 +755,8 @@ int mrvi_create(const MrviDims* dims, int32_t n_params, const char* const* names
     if ((err = enc_tc_build(h->enc_tc, h->net, pt.m, h->arena))) return fail(err, "%s", tc_error());
     if (h->enc_tc.ready) CUDA_TRY(h->arena.alloc((void**)&h->h1buf, (size_t)h->chunk_cells * 128 * sizeof(float)));
     if ((err = tc_fused_prepare(h->tc, h->dims.n_latent))) return fail(err, "%s", tc_error());
+    if (dist_tc_supported(h->net.S, h->net.L, MRVI_NORM_L2) && (err = dist_tc_prepare(h->net.L, h->net.S, &h->dist_tc_smem)))
+      return fail(err, "%s", tc_error());
     if (h->enc_tc.ready && !getenv("MRVI_B200_FP32_ENCODER_TAIL")) {
       if ((err = enc_tail_build(h->enc_tail, h->net, pt.m, h->arena))) return fail(err, "%s", tc_error());
     }

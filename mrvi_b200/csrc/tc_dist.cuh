@@ -1,0 +1,341 @@
+// Tensor-core pairwise distances for 128 < S <= 256 (BASELINE config 5: "large-S Gram stress").
+//
+// The fused chain kernel (tc_fused.cuh) holds one 128-row tile per warpgroup; a cell with more than 128
+// samples does not fit it, so the chain runs unfused (k_chain_tc writes z, 4 S L bytes per cell) and this
+// kernel forms the S x S matrix from z on the tensor cores instead of the fp32 direct-difference kernel:
+//
+//   * one persistent CTA per SM, 512 threads; a CTA owns a contiguous range of SORTED cell positions;
+//   * prep (all threads, two per sample row): z rows are re-centred on the cell's sample 0 (any per-cell
+//     shift cancels in the distances; it keeps the norms small), split into (hi, lo) f16 and stored as a
+//     K-major UMMA operand of 256 rows, double buffered so that the prep of cell p+1 overlaps the MMAs of p;
+//   * the matrix is covered by the three 128 x 128 blocks (0,0), (0,1), (1,1) -- D is symmetric, block (1,0)
+//     is written / accumulated as the transpose of (0,1).  Warpgroup g owns columns [64 g, 64 g + 64) of
+//     every block: it issues its own N = 64 MMAs (Zh Zh^T + Zh Zl^T + Zl Zh^T, fp32 accumulate in its half of
+//     a 128-column TMEM work region), waits on its own mbarrier and runs the epilogue with two threads per
+//     row, so the two warpgroups overlap each other's MMA latency without any cross-warpgroup barrier;
+//   * epilogue: d = sqrt(n_i + n_j - 2 g), exact direct-difference recompute when the squared distance is
+//     cancellation dominated (< 2^-12 (n_i + n_j)), diagonal forced to zero; rows go to cell_out and / or
+//     into three 128-column fp32 TMEM accumulators that live across the cells of a run of equal composite
+//     group code and are flushed with float64 atomics when the code changes (each warpgroup flushes its own
+//     columns; no lock).
+// TMEM: [0,128) work, [128,512) accumulators of the three blocks.
+#pragma once
+#include "tc_fused.cuh"
+
+namespace mrvi {
+
+constexpr int kDistTcThreads = 512;
+
+struct DistTcSmem {
+  uint32_t z[2];      // per buffer: zh | zl, each 256 rows x Kz f16, K-major, LBO = 4096
+  uint32_t part[2];   // per buffer: [256] fp32 squared norms of the (hi + lo) operand rows
+  uint32_t stage;     // raw fp32 z of the next cell ([S][L], landed by one bulk copy)
+  uint32_t ctrl;
+  uint32_t total;
+  int Kz;
+};
+
+__host__ __device__ inline DistTcSmem dist_tc_smem(int L, int S = 256) {
+  DistTcSmem m;
+  m.Kz = L <= 32 ? 32 : 64;
+  const uint32_t zb = 2u * 256u * (uint32_t)m.Kz * 2u;
+  uint32_t o = 0;
+  m.z[0] = o; o += zb;
+  m.z[1] = o; o += zb;
+  m.part[0] = o; o += 2048;
+  m.part[1] = o; o += 2048;
+  m.stage = o; o += (((uint32_t)S * (uint32_t)L * 4u) + 127u) & ~127u;
+  m.ctrl = o; o += 64;
+  m.total = o;
+  return m;
+}
+
+// exact squared distance of operand rows a and b (K-chunk stride 4096 bytes)
+__device__ __noinline__ float exact_d2_256(const uint8_t* zh, const uint8_t* zl, int a, int b, int L) {
+  float e = 0.f;
+  for (int k = 0; k < L; ++k) {
+    const uint32_t ko = (uint32_t)(k >> 3) * 4096u + (uint32_t)(k & 7) * 2u;
+    const float za = __half2float(*reinterpret_cast<const __half*>(zh + ko + a * 16)) +
+                     __half2float(*reinterpret_cast<const __half*>(zl + ko + a * 16));
+    const float zb = __half2float(*reinterpret_cast<const __half*>(zh + ko + b * 16)) +
+                     __half2float(*reinterpret_cast<const __half*>(zl + ko + b * 16));
+    const float df = zb - za;
+    e = fmaf(df, df, e);
+  }
+  return e;
+}
+
+__global__ void __launch_bounds__(kDistTcThreads, 1)
+k_dist_gram_tc(const float* __restrict__ z, int64_t n_cells, int S, int L, float* __restrict__ cell_out, GroupPlan gp,
+               int64_t cells_per_cta) {
+  extern __shared__ __align__(1024) uint8_t smem_tc[];
+  uint8_t* const smem = smem_tc;
+  const DistTcSmem sm = dist_tc_smem(L, S);
+  const int Kz = sm.Kz;
+  uint64_t* bar_mma = reinterpret_cast<uint64_t*>(smem + sm.ctrl);       // [2], one per warpgroup
+  uint64_t* bar_z = bar_mma + 2;                                         // raw z of the next cell landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + sm.ctrl + 32);
+  float* stage = reinterpret_cast<float*>(smem + sm.stage);
+  const uint32_t zcell_bytes = (uint32_t)S * (uint32_t)L * 4u;
+  // one bulk copy per cell needs 16-byte aligned, 16-byte multiple blocks; otherwise a cooperative copy
+  const bool use_tma = (zcell_bytes & 15u) == 0 && (reinterpret_cast<uintptr_t>(z) & 15) == 0;
+  uint32_t zphase = 0;
+  const int tid = threadIdx.x, wg = tid >> 8, wt = tid & 255, sub = wt >> 7, r = wt & 127, warp_q = (wt >> 5) & 3;
+  if (tid == 0) {
+    mbar_init(&bar_mma[0], 1);
+    mbar_init(&bar_mma[1], 1);
+    mbar_init(bar_z, 1);
+    fence_mbar_init();
+  }
+  if (tid < 32) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t lane_off = (uint32_t)(warp_q * 32) << 16;
+  const int colw = wg * 64 + sub * 32;                       // this thread's 32 columns inside a block
+  const uint32_t t_work = tmem_base + lane_off + colw;
+  const uint32_t t_acc0 = tmem_base + 128 + lane_off + colw;  // + 128 * block
+  const uint32_t idesc64 = umma_idesc_f16(64);
+  const bool issuer = wt == 0;
+  const uint32_t zbytes = 256u * (uint32_t)Kz * 2u;           // one of (zh, zl)
+  uint32_t phase = 0;
+
+  const int64_t p0 = (int64_t)blockIdx.x * cells_per_cta;
+  const int64_t p1 = min(n_cells, p0 + cells_per_cta);
+  if (p0 >= p1) {  // nothing to do (still release TMEM)
+    __syncthreads();
+    if (tid < 32) tmem_dealloc(tmem_base, 512);
+    return;
+  }
+  if (gp.n_keys > 0) {  // clear this thread's accumulator columns
+    uint32_t zz[32];
+#pragma unroll
+    for (int q = 0; q < 32; ++q) zz[q] = 0u;
+    for (int b = 0; b < 3; ++b) tmem_st32(t_acc0 + b * 128, zz);
+    tmem_st_wait();
+  }
+
+  // ---- raw z of the cell at sorted position p -> staging (async bulk copy, or a cooperative coalesced copy)
+  auto fetch = [&](int64_t p) {
+    const int64_t cell = gp.order ? (int64_t)gp.order[p] : p;
+    const float* src = z + cell * S * (int64_t)L;
+    if (use_tma) {
+      if (tid == 0) {
+        mbar_expect_tx(bar_z, zcell_bytes);
+        bulk_g2s(stage, src, zcell_bytes, bar_z);
+      }
+    } else {
+      for (int idx = tid; idx < S * L; idx += kDistTcThreads) stage[idx] = __ldg(src + idx);
+    }
+  };
+  auto fetch_wait = [&]() {
+    if (use_tma) { mbar_wait(bar_z, zphase); zphase ^= 1; }
+    else __syncthreads();
+  };
+  // ---- operand prep of the staged cell into buffer buf (all 512 threads)
+  auto prep = [&](int buf) {
+    const int row = tid >> 1, kh = tid & 1;   // the two K halves of a row sit in adjacent lanes
+    const bool vrow = row < S;
+    const float* zr = stage + (vrow ? row : 0) * L;
+    const float* z0 = stage;
+    uint8_t* zh = smem + sm.z[buf];
+    uint8_t* zl = zh + zbytes;
+    float nrm_p = 0.f;
+    const int nch = Kz >> 4;
+    for (int cc = 0; cc < nch; ++cc) {
+      const int c = kh * nch + cc;
+      uint32_t hw[4], lw[4];
+#pragma unroll
+      for (int j2 = 0; j2 < 4; ++j2) {
+        const int k0 = c * 8 + 2 * j2, k1 = k0 + 1;
+        const float a = (vrow && k0 < L) ? zr[k0] - z0[k0] : 0.f;
+        const float b = (vrow && k1 < L) ? zr[k1] - z0[k1] : 0.f;
+        split2(a, b, hw[j2], lw[j2]);
+        const float ar = h2f_lo(hw[j2]) + h2f_lo(lw[j2]), br = h2f_hi(hw[j2]) + h2f_hi(lw[j2]);
+        nrm_p = fmaf(ar, ar, nrm_p);
+        nrm_p = fmaf(br, br, nrm_p);
+      }
+      *reinterpret_cast<uint4*>(zh + c * 4096 + row * 16) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+      *reinterpret_cast<uint4*>(zl + c * 4096 + row * 16) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+    }
+    nrm_p += __shfl_xor_sync(0xffffffffu, nrm_p, 1);
+    if (kh == 0) reinterpret_cast<float*>(smem + sm.part[buf])[row] = nrm_p;
+  };
+
+  // ---- this warpgroup's N = 64 slice of Gram block (bi, bj) of buffer buf
+  auto issue_block = [&](int buf, int bi, int bj) {
+    const uint32_t s_zh = smem_u32(smem + sm.z[buf]), s_zl = s_zh + zbytes;
+    const uint32_t a_off = (uint32_t)bi * 128u * 16u, b_off = ((uint32_t)bj * 128u + (uint32_t)wg * 64u) * 16u;
+    const uint32_t d = tmem_base + wg * 64;
+    for (int ks = 0; ks < Kz / 16; ++ks) {
+      const uint32_t ko = (uint32_t)ks * 2u * 4096u;
+      const uint64_t ah = umma_desc(s_zh + a_off + ko, 4096, 128), al = umma_desc(s_zl + a_off + ko, 4096, 128);
+      const uint64_t bh = umma_desc(s_zh + b_off + ko, 4096, 128), bl = umma_desc(s_zl + b_off + ko, 4096, 128);
+      umma_f16(d, ah, bh, idesc64, ks == 0 ? 0u : 1u);
+      umma_f16(d, ah, bl, idesc64, 1u);
+      umma_f16(d, al, bh, idesc64, 1u);
+    }
+    umma_commit(&bar_mma[wg]);
+  };
+
+  // ---- flush this thread's accumulator columns of the three blocks into the float64 group sums
+  auto flush = [&](int64_t rep_cell) {
+#pragma unroll 1
+    for (int b = 0; b < 3; ++b) {
+      const int bi = b == 2 ? 1 : 0, bj = b == 0 ? 0 : 1;
+      float a[32];
+      tmem_ld32(t_acc0 + b * 128, a);
+      tmem_ld_wait();
+      const int i = bi * 128 + r;
+      if (i < S) {
+#pragma unroll 1
+        for (int k = 0; k < gp.n_keys; ++k) {
+          const int g = gp.codes[k][rep_cell];
+          if (g < 0) continue;
+          double* base = gp.sums[k] + (size_t)g * S * S;
+#pragma unroll
+          for (int q = 0; q < 32; ++q) {
+            const int j = bj * 128 + colw + q;
+            if (j < S && j != i) {
+              atomicAdd(base + (size_t)i * S + j, (double)a[q]);
+              if (b == 1) atomicAdd(base + (size_t)j * S + i, (double)a[q]);
+            }
+          }
+        }
+      }
+      uint32_t zz[32];
+#pragma unroll
+      for (int q = 0; q < 32; ++q) zz[q] = 0u;
+      tmem_st32(t_acc0 + b * 128, zz);
+    }
+    tmem_st_wait();
+  };
+
+  fetch(p0);
+  fetch_wait();
+  prep(0);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (p0 + 1 < p1) fetch(p0 + 1);
+
+  int cur_code = -1;
+  int64_t cur_cell = -1;
+  for (int64_t p = p0; p < p1; ++p) {
+    const int buf = (int)((p - p0) & 1);
+    const int64_t cell = gp.order ? (int64_t)gp.order[p] : p;
+    const int code = gp.n_keys ? gp.comp_sorted[p] : 0;
+    if (issuer) { tc_fence_after(); issue_block(buf, 0, 0); }
+    if (p + 1 < p1) { fetch_wait(); prep(buf ^ 1); }  // overlaps the MMAs of block (0,0)
+    if (gp.n_keys && cur_cell >= 0 && code != cur_code) flush(cur_cell);
+    cur_code = code; cur_cell = cell;
+    const uint8_t* zh = smem + sm.z[buf];
+    const uint8_t* zl = zh + zbytes;
+    const float* part = reinterpret_cast<const float*>(smem + sm.part[buf]);
+#pragma unroll 1
+    for (int b = 0; b < 3; ++b) {
+      const int bi = b == 2 ? 1 : 0, bj = b == 0 ? 0 : 1;
+      mbar_wait(&bar_mma[wg], phase); phase ^= 1;
+      tc_fence_after();
+      float g[32];
+      tmem_ld32(t_work, g);
+      tmem_ld_wait();
+      tc_fence_before();
+      wg_sync(wg);  // every thread of the warpgroup has read its work columns
+      if (b < 2 && issuer) { tc_fence_after(); issue_block(buf, b, 1); }  // next block: (0,1) then (1,1)
+      const int i = bi * 128 + r, jbase = bj * 128 + colw;
+      const float n_i = part[i];
+      uint32_t flagged = 0u;
+      // fast path (warp-uniform): every row of the warp and the whole chunk are inside the S x S matrix
+      const bool full = __all_sync(0xffffffffu, i < S) && jbase + 32 <= S;
+      const float2 ni2 = make_float2(n_i, n_i), m2 = make_float2(-2.0f, -2.0f), thr2 = make_float2(-1.0f / 4096.0f, -1.0f / 4096.0f);
+#pragma unroll
+      for (int q4 = 0; q4 < 8; ++q4) {
+        const float4 nj = *reinterpret_cast<const float4*>(part + jbase + 4 * q4);
+        const float2 njp[2] = {make_float2(nj.x, nj.y), make_float2(nj.z, nj.w)};
+#pragma unroll
+        for (int e2 = 0; e2 < 2; ++e2) {
+          const int q = 4 * q4 + 2 * e2, j = jbase + q;
+          const float2 sn = __fadd2_rn(ni2, njp[e2]);
+          const float2 d2 = __ffma2_rn(make_float2(g[q], g[q + 1]), m2, sn);
+          const float2 tt = __ffma2_rn(sn, thr2, d2);  // < 0: cancellation dominated
+          const bool in0 = full ? (j != i) : (i < S && j < S && j != i);
+          const bool in1 = full ? (j + 1 != i) : (i < S && j + 1 < S && j + 1 != i);
+          if (in0 && tt.x < 0.f) flagged |= 1u << q;
+          if (in1 && tt.y < 0.f) flagged |= 2u << q;
+          g[q] = in0 ? sqrt_approx(fmaxf(d2.x, 0.f)) : 0.f;
+          g[q + 1] = in1 ? sqrt_approx(fmaxf(d2.y, 0.f)) : 0.f;
+        }
+      }
+      if (flagged) {
+#pragma unroll
+        for (int q = 0; q < 32; ++q)
+          if ((flagged >> q) & 1u) g[q] = sqrtf(exact_d2_256(zh, zl, i, jbase + q, L));
+      }
+      if (cell_out != nullptr && i < S) {
+        float* dst = cell_out + ((size_t)cell * S + i) * S + jbase;
+        if ((S & 3) == 0) {
+#pragma unroll
+          for (int q4 = 0; q4 < 8; ++q4)
+            if (jbase + 4 * q4 < S)
+              *reinterpret_cast<float4*>(dst + 4 * q4) = make_float4(g[4 * q4], g[4 * q4 + 1], g[4 * q4 + 2], g[4 * q4 + 3]);
+        } else {
+#pragma unroll
+          for (int q = 0; q < 32; ++q) if (jbase + q < S) dst[q] = g[q];
+        }
+        if (b == 1) {  // block (1,0) = transpose of (0,1): lanes hold consecutive i -> coalesced 128-byte rows
+          float* dt = cell_out + (size_t)cell * S * S + i;
+#pragma unroll
+          for (int q = 0; q < 32; ++q) if (jbase + q < S) dt[(size_t)(jbase + q) * S] = g[q];
+        }
+      }
+      if (gp.n_keys > 0) {
+        float acc[32];
+        tmem_ld32(t_acc0 + b * 128, acc);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+          const float2 t = __fadd2_rn(make_float2(acc[2 * q], acc[2 * q + 1]), make_float2(g[2 * q], g[2 * q + 1]));
+          acc[2 * q] = t.x; acc[2 * q + 1] = t.y;
+        }
+        tmem_st32(t_acc0 + b * 128, reinterpret_cast<uint32_t*>(acc));
+        tmem_st_wait();
+      }
+    }
+    // buffer buf^1 (cell p+1) is complete, buffer buf and the staging area are free once BOTH warpgroups are here
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (p + 2 < p1) fetch(p + 2);  // lands during the epilogues of cell p+1
+  }
+  if (gp.n_keys && cur_cell >= 0) flush(cur_cell);
+  tc_fence_before();
+  __syncthreads();
+  if (tid < 32) tmem_dealloc(tmem_base, 512);
+}
+
+inline bool dist_tc_supported(int S, int L, int norm) { return norm == MRVI_NORM_L2 && S > 128 && S <= 256 && L <= 64; }
+
+inline int dist_tc_prepare(int L, int S, size_t* smem_bytes) {
+  const size_t bytes = dist_tc_smem(L, S).total;
+  if (bytes > 227 * 1024) { *smem_bytes = 0; return 0; }
+  if (cudaFuncSetAttribute(k_dist_gram_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) {
+    g_tc_error = "cudaFuncSetAttribute(k_dist_gram_tc) failed";
+    return MRVI_ERR_CUDA;
+  }
+  *smem_bytes = bytes;
+  return 0;
+}
+
+inline void dist_tc_launch(const float* z, int64_t n, int S, int L, float* cell_out, const GroupPlan& gp, int sm_count,
+                           size_t smem_bytes, cudaStream_t st) {
+  if (n == 0) return;
+  const int grid = (int)std::min<int64_t>(n, sm_count);
+  const int64_t cpc = (n + grid - 1) / grid;
+  k_dist_gram_tc<<<(int)((n + cpc - 1) / cpc), kDistTcThreads, smem_bytes, st>>>(z, n, S, L, cell_out, gp, cpc);
+}
+
+}  // namespace mrvi

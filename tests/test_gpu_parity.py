@@ -229,6 +229,49 @@ def test_tc_fused_near_duplicate_samples(built_library):
     h.close()
 
 
+@pytest.mark.parametrize("S,L,n", [(256, 50, 120), (200, 30, 90), (129, 10, 64), (252, 64, 40)])
+def test_tc_large_S_gram_kernel(built_library, S, L, n):
+    """128 < S <= 256 (BASELINE config 5): unfused chain + tensor-core Gram distance kernel (tc_dist.cuh).
+    Skewed groups with -1 codes over more cells than SMs' ranges are long, keep_cell and groupby outputs, exact
+    symmetry / zero diagonal, a duplicated and a near-duplicated sample (exact-recompute route), and the isolated
+    stage through `mrvi_distances_device`-equivalent arithmetic (distances of the returned z)."""
+    dims = mrvi_b200.MrviDims(n_input=48, n_sample=S, n_latent=L, n_latent_u=10 if L != 10 else None)
+    params = mrvi_b200.init_params(dims, seed=12)
+    emb = params["qz/Embed_0/embedding"]
+    emb[S - 1] = emb[2]                    # duplicate across the two 128-row blocks
+    emb[130 if S > 131 else 1] = emb[0] * (1 + 1e-3)
+    h = _capi.Handle(dims, params, device=0, precision=_capi.PRECISION_TC)
+    X, sid = _inputs(n, 48, S, seed=13)
+    rng = np.random.default_rng(2)
+    k0 = np.minimum(rng.zipf(1.7, size=n) - 1, 4).astype(np.int32)
+    k1 = rng.integers(-1, 2, size=n).astype(np.int32)
+    res = h.run_host(X, sid, [k0, k1], [5, 2], keep_cell=True, want_z=True)
+    dref = orc.pairwise_distances(orc.counterfactual_z(params, X, sid, dtype=np.float64))
+    scale = dref.max(axis=(1, 2), keepdims=True)
+    assert (np.abs(res["cell"] - dref) / scale).max() < TOL["tc"]
+    # (i, j) and (j, i) inside a diagonal block are separate Gram entries (different accumulation order of the
+    # split products): symmetric to the Gram error, far inside the tensor-core parity bar; the off-diagonal
+    # blocks are exact mirrors.  (fp32 mode is bit-symmetric, test_fp32_matches_oracle.)
+    asym = np.abs(res["cell"] - np.swapaxes(res["cell"], 1, 2))
+    assert (asym / scale).max() < 1e-4
+    assert np.array_equal(res["cell"][:, :128, 128:], np.swapaxes(res["cell"][:, 128:, :128], 1, 2))
+    assert np.all(np.diagonal(res["cell"], axis1=1, axis2=2) == 0)
+    assert np.all(res["cell"][:, 2, S - 1] == 0)
+    # the distance stage alone, against exact distances of the z the chain produced: Gram error only
+    dz = orc.pairwise_distances(res["z"].astype(np.float64))
+    # (pairs just above the 2^-12 exact-recompute threshold carry a relative error of ~2^-9 on a distance that is
+    #  itself ~2^-6 of the scale)
+    assert (np.abs(res["cell"] - dz) / scale).max() < 1e-4
+    for k, (codes, ng) in enumerate([(k0, 5), (k1, 2)]):
+        assert np.array_equal(res["group_counts"][k], np.bincount(codes[codes >= 0], minlength=ng))
+        from_cells = np.stack([res["cell"][codes == g].astype(np.float64).sum(0) for g in range(ng)])
+        assert np.allclose(res["group_sums"][k], from_cells, rtol=1e-5, atol=1e-5 * dref.max())
+    only = h.run_host(X, sid, [k0, k1], [5, 2], keep_cell=False, chunk_cells=50)
+    for k in range(2):
+        assert np.allclose(only["group_sums"][k], res["group_sums"][k], rtol=1e-5, atol=1e-5 * dref.max())
+    h.close()
+
+
 @pytest.mark.parametrize("precision,tol", [("fp32", 1e-5), ("tc", 1e-3)])
 def test_latent_representation_api(built_library, precision, tol):
     """get_latent_representation (reference `_model.py:221-271`): u, and z of each cell for its own sample."""
