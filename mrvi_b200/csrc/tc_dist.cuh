@@ -24,7 +24,8 @@
 
 namespace mrvi {
 
-constexpr int kDistTcThreads = 512;
+constexpr int kDistTcThreads = 544;   // 16 epilogue warps (2 warpgroups) + 1 warp that issues bulk copies and MMAs
+constexpr int kDistTcWorkers = 512;
 
 struct DistTcSmem {
   uint32_t z[2];      // per buffer: zh | zl, each 256 rows x Kz f16, K-major, LBO = 4096
@@ -74,7 +75,9 @@ k_dist_gram_tc(const float* __restrict__ z, int64_t n_cells, int S, int L, float
   const int Kz = sm.Kz;
   uint64_t* bar_mma = reinterpret_cast<uint64_t*>(smem + sm.ctrl);       // [2], one per warpgroup
   uint64_t* bar_z = bar_mma + 2;                                         // raw z of the next cell landed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + sm.ctrl + 32);
+  uint64_t* bar_free = bar_mma + 3;                                      // [2] work columns of warpgroup g drained
+  uint64_t* bar_ops = bar_mma + 5;                                       // operands of the next cell written
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + sm.ctrl + 48);
   float* stage = reinterpret_cast<float*>(smem + sm.stage);
   const uint32_t zcell_bytes = (uint32_t)S * (uint32_t)L * 4u;
   // one bulk copy per cell needs 16-byte aligned, 16-byte multiple blocks; otherwise a cooperative copy
@@ -85,6 +88,9 @@ k_dist_gram_tc(const float* __restrict__ z, int64_t n_cells, int S, int L, float
     mbar_init(&bar_mma[0], 1);
     mbar_init(&bar_mma[1], 1);
     mbar_init(bar_z, 1);
+    mbar_init(&bar_free[0], 256);
+    mbar_init(&bar_free[1], 256);
+    mbar_init(bar_ops, kDistTcWorkers);
     fence_mbar_init();
   }
   if (tid < 32) tmem_alloc(tmem_slot, 512);
@@ -97,7 +103,6 @@ k_dist_gram_tc(const float* __restrict__ z, int64_t n_cells, int S, int L, float
   const uint32_t t_work = tmem_base + lane_off + colw;
   const uint32_t t_acc0 = tmem_base + 128 + lane_off + colw;  // + 128 * block
   const uint32_t idesc64 = umma_idesc_f16(64);
-  const bool issuer = wt == 0;
   const uint32_t zbytes = 256u * (uint32_t)Kz * 2u;           // one of (zh, zl)
   uint32_t phase = 0;
 
@@ -108,7 +113,8 @@ k_dist_gram_tc(const float* __restrict__ z, int64_t n_cells, int S, int L, float
     if (tid < 32) tmem_dealloc(tmem_base, 512);
     return;
   }
-  if (gp.n_keys > 0) {  // clear this thread's accumulator columns
+  const bool worker = tid < kDistTcWorkers;
+  if (gp.n_keys > 0 && worker) {  // clear this thread's accumulator columns
     uint32_t zz[32];
 #pragma unroll
     for (int q = 0; q < 32; ++q) zz[q] = 0u;
@@ -116,22 +122,17 @@ k_dist_gram_tc(const float* __restrict__ z, int64_t n_cells, int S, int L, float
     tmem_st_wait();
   }
 
-  // ---- raw z of the cell at sorted position p -> staging (async bulk copy, or a cooperative coalesced copy)
-  auto fetch = [&](int64_t p) {
-    const int64_t cell = gp.order ? (int64_t)gp.order[p] : p;
-    const float* src = z + cell * S * (int64_t)L;
-    if (use_tma) {
-      if (tid == 0) {
-        mbar_expect_tx(bar_z, zcell_bytes);
-        bulk_g2s(stage, src, zcell_bytes, bar_z);
-      }
-    } else {
-      for (int idx = tid; idx < S * L; idx += kDistTcThreads) stage[idx] = __ldg(src + idx);
-    }
-  };
-  auto fetch_wait = [&]() {
+  // ---- raw z of the cell at sorted position p -> staging: one bulk copy by the issuer thread, or (unaligned
+  //      shapes) a cooperative coalesced copy by the workers right before the prep
+  auto cell_src = [&](int64_t p) { return z + (gp.order ? (int64_t)gp.order[p] : p) * S * (int64_t)L; };
+  auto workers_sync = [&]() { asm volatile("bar.sync 3, 512;" ::: "memory"); };
+  auto stage_ready = [&](int64_t p) {  // workers: staging holds cell p
     if (use_tma) { mbar_wait(bar_z, zphase); zphase ^= 1; }
-    else __syncthreads();
+    else {
+      const float* src = cell_src(p);
+      for (int idx = tid; idx < S * L; idx += kDistTcWorkers) stage[idx] = __ldg(src + idx);
+      workers_sync();
+    }
   };
   // ---- operand prep of the staged cell into buffer buf (all 512 threads)
   auto prep = [&](int buf) {
@@ -164,19 +165,21 @@ k_dist_gram_tc(const float* __restrict__ z, int64_t n_cells, int S, int L, float
   };
 
   // ---- this warpgroup's N = 64 slice of Gram block (bi, bj) of buffer buf
-  auto issue_block = [&](int buf, int bi, int bj) {
-    const uint32_t s_zh = smem_u32(smem + sm.z[buf]), s_zl = s_zh + zbytes;
-    const uint32_t a_off = (uint32_t)bi * 128u * 16u, b_off = ((uint32_t)bj * 128u + (uint32_t)wg * 64u) * 16u;
-    const uint32_t d = tmem_base + wg * 64;
+  // (descriptor of address a + off = descriptor of a + (off >> 4): the address field holds a >> 4 and cannot carry
+  //  out of its 14 bits for shared-memory addresses)
+  const uint64_t dbase0 = umma_desc(smem_u32(smem + sm.z[0]), 4096, 128), dbase1 = umma_desc(smem_u32(smem + sm.z[1]), 4096, 128);
+  auto issue_block = [&](int g_, int buf, int bi, int bj) {
+    const uint64_t dh = buf ? dbase1 : dbase0, dl = dh + (zbytes >> 4);
+    const uint32_t a16 = (uint32_t)bi * 128u, b16 = (uint32_t)bj * 128u + (uint32_t)g_ * 64u;  // row offsets, 16-byte units
+    const uint32_t d = tmem_base + g_ * 64;
     for (int ks = 0; ks < Kz / 16; ++ks) {
-      const uint32_t ko = (uint32_t)ks * 2u * 4096u;
-      const uint64_t ah = umma_desc(s_zh + a_off + ko, 4096, 128), al = umma_desc(s_zl + a_off + ko, 4096, 128);
-      const uint64_t bh = umma_desc(s_zh + b_off + ko, 4096, 128), bl = umma_desc(s_zl + b_off + ko, 4096, 128);
+      const uint32_t ko16 = (uint32_t)ks * 512u;  // two 4096-byte K chunks per 16-wide slice
+      const uint64_t ah = dh + a16 + ko16, al = dl + a16 + ko16, bh = dh + b16 + ko16, bl = dl + b16 + ko16;
       umma_f16(d, ah, bh, idesc64, ks == 0 ? 0u : 1u);
       umma_f16(d, ah, bl, idesc64, 1u);
       umma_f16(d, al, bh, idesc64, 1u);
     }
-    umma_commit(&bar_mma[wg]);
+    umma_commit(&bar_mma[g_]);
   };
 
   // ---- flush this thread's accumulator columns of the three blocks into the float64 group sums
@@ -212,14 +215,46 @@ k_dist_gram_tc(const float* __restrict__ z, int64_t n_cells, int S, int L, float
     tmem_st_wait();
   };
 
-  fetch(p0);
-  fetch_wait();
+  if (!worker) {
+    // ================= issuer warp: bulk copies of z and all MMAs (one thread) =================
+    if (tid == kDistTcWorkers) {
+      auto tma = [&](int64_t p) {
+        if (!use_tma) return;
+        mbar_expect_tx(bar_z, zcell_bytes);
+        bulk_g2s(stage, cell_src(p), zcell_bytes, bar_z);
+      };
+      uint32_t ops_phase = 0, free_phase = 1;  // a fresh mbarrier passes a wait on parity 1; both warpgroups' barriers advance together
+      tma(p0);
+      mbar_wait(bar_ops, ops_phase); ops_phase ^= 1;    // operands of p0 written, staging consumed
+      if (p0 + 1 < p1) tma(p0 + 1);
+      for (int64_t p = p0; p < p1; ++p) {
+        const int buf = (int)((p - p0) & 1);
+        for (int b = 0; b < 3; ++b) {
+#pragma unroll
+          for (int g_ = 0; g_ < 2; ++g_) {
+            mbar_wait(&bar_free[g_], free_phase);
+            tc_fence_after();
+            issue_block(g_, buf, b == 2 ? 1 : 0, b == 0 ? 0 : 1);
+          }
+          free_phase ^= 1;
+        }
+        if (p + 1 < p1) {
+          mbar_wait(bar_ops, ops_phase); ops_phase ^= 1;  // prep(p+1) done by every worker
+          if (p + 2 < p1) tma(p + 2);                     // lands while the workers run the epilogues of p
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+    return;
+  }
+
+  // ================= workers =================
+  stage_ready(p0);
   prep(0);
   fence_proxy_async();
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  if (p0 + 1 < p1) fetch(p0 + 1);
+  mbar_arrive(bar_ops);
+  workers_sync();
 
   int cur_code = -1;
   int64_t cur_cell = -1;
@@ -227,8 +262,12 @@ k_dist_gram_tc(const float* __restrict__ z, int64_t n_cells, int S, int L, float
     const int buf = (int)((p - p0) & 1);
     const int64_t cell = gp.order ? (int64_t)gp.order[p] : p;
     const int code = gp.n_keys ? gp.comp_sorted[p] : 0;
-    if (issuer) { tc_fence_after(); issue_block(buf, 0, 0); }
-    if (p + 1 < p1) { fetch_wait(); prep(buf ^ 1); }  // overlaps the MMAs of block (0,0)
+    if (p + 1 < p1) {  // overlaps the MMAs of block (0,0), which the issuer warp has already queued
+      stage_ready(p + 1);
+      prep(buf ^ 1);
+      fence_proxy_async();
+      mbar_arrive(bar_ops);
+    }
     if (gp.n_keys && cur_cell >= 0 && code != cur_code) flush(cur_cell);
     cur_code = code; cur_cell = cell;
     const uint8_t* zh = smem + sm.z[buf];
@@ -243,36 +282,62 @@ k_dist_gram_tc(const float* __restrict__ z, int64_t n_cells, int S, int L, float
       tmem_ld32(t_work, g);
       tmem_ld_wait();
       tc_fence_before();
-      wg_sync(wg);  // every thread of the warpgroup has read its work columns
-      if (b < 2 && issuer) { tc_fence_after(); issue_block(buf, b, 1); }  // next block: (0,1) then (1,1)
+      mbar_arrive(&bar_free[wg]);  // this thread has read its work columns: the issuer may queue the next block
       const int i = bi * 128 + r, jbase = bj * 128 + colw;
       const float n_i = part[i];
-      uint32_t flagged = 0u;
-      // fast path (warp-uniform): every row of the warp and the whole chunk are inside the S x S matrix
+      // warp-uniform cases: `full` = every row of the warp and the whole chunk lie inside the S x S matrix;
+      // `diag_chunk` = the chunk holds the diagonal entries of this warp's rows (diagonal blocks only)
       const bool full = __all_sync(0xffffffffu, i < S) && jbase + 32 <= S;
+      const bool diag_chunk = (b != 1) && ((colw >> 5) == warp_q);
       const float2 ni2 = make_float2(n_i, n_i), m2 = make_float2(-2.0f, -2.0f), thr2 = make_float2(-1.0f / 4096.0f, -1.0f / 4096.0f);
+      if (full && !diag_chunk) {
+        // fast path: no bounds, no diagonal; cancellation-dominated entries are only DETECTED here (min of tt)
+        float tmin = 0.f;
 #pragma unroll
-      for (int q4 = 0; q4 < 8; ++q4) {
-        const float4 nj = *reinterpret_cast<const float4*>(part + jbase + 4 * q4);
-        const float2 njp[2] = {make_float2(nj.x, nj.y), make_float2(nj.z, nj.w)};
+        for (int q4 = 0; q4 < 8; ++q4) {
+          const float4 nj = *reinterpret_cast<const float4*>(part + jbase + 4 * q4);
+          const float2 njp[2] = {make_float2(nj.x, nj.y), make_float2(nj.z, nj.w)};
 #pragma unroll
-        for (int e2 = 0; e2 < 2; ++e2) {
-          const int q = 4 * q4 + 2 * e2, j = jbase + q;
-          const float2 sn = __fadd2_rn(ni2, njp[e2]);
-          const float2 d2 = __ffma2_rn(make_float2(g[q], g[q + 1]), m2, sn);
-          const float2 tt = __ffma2_rn(sn, thr2, d2);  // < 0: cancellation dominated
-          const bool in0 = full ? (j != i) : (i < S && j < S && j != i);
-          const bool in1 = full ? (j + 1 != i) : (i < S && j + 1 < S && j + 1 != i);
-          if (in0 && tt.x < 0.f) flagged |= 1u << q;
-          if (in1 && tt.y < 0.f) flagged |= 2u << q;
-          g[q] = in0 ? sqrt_approx(fmaxf(d2.x, 0.f)) : 0.f;
-          g[q + 1] = in1 ? sqrt_approx(fmaxf(d2.y, 0.f)) : 0.f;
+          for (int e2 = 0; e2 < 2; ++e2) {
+            const int q = 4 * q4 + 2 * e2;
+            const float2 sn = __fadd2_rn(ni2, njp[e2]);
+            const float2 d2 = __ffma2_rn(make_float2(g[q], g[q + 1]), m2, sn);
+            const float2 tt = __ffma2_rn(sn, thr2, d2);  // < 0: cancellation dominated
+            tmin = fminf(tmin, fminf(tt.x, tt.y));
+            g[q] = sqrt_approx(fmaxf(d2.x, 0.f));
+            g[q + 1] = sqrt_approx(fmaxf(d2.y, 0.f));
+          }
         }
-      }
-      if (flagged) {
+        if (tmin < 0.f) {  // rare: near-duplicate samples -> exact direct-difference distance
 #pragma unroll
-        for (int q = 0; q < 32; ++q)
-          if ((flagged >> q) & 1u) g[q] = sqrtf(exact_d2_256(zh, zl, i, jbase + q, L));
+          for (int q = 0; q < 32; ++q)
+            if (g[q] * g[q] < (n_i + part[jbase + q]) * (1.0f / 4096.0f)) g[q] = sqrtf(exact_d2_256(zh, zl, i, jbase + q, L));
+        }
+      } else {
+        uint32_t flagged = 0u;
+#pragma unroll
+        for (int q4 = 0; q4 < 8; ++q4) {
+          const float4 nj = *reinterpret_cast<const float4*>(part + jbase + 4 * q4);
+          const float2 njp[2] = {make_float2(nj.x, nj.y), make_float2(nj.z, nj.w)};
+#pragma unroll
+          for (int e2 = 0; e2 < 2; ++e2) {
+            const int q = 4 * q4 + 2 * e2, j = jbase + q;
+            const float2 sn = __fadd2_rn(ni2, njp[e2]);
+            const float2 d2 = __ffma2_rn(make_float2(g[q], g[q + 1]), m2, sn);
+            const float2 tt = __ffma2_rn(sn, thr2, d2);
+            const bool in0 = i < S && j < S && j != i;
+            const bool in1 = i < S && j + 1 < S && j + 1 != i;
+            if (in0 && tt.x < 0.f) flagged |= 1u << q;
+            if (in1 && tt.y < 0.f) flagged |= 2u << q;
+            g[q] = in0 ? sqrt_approx(fmaxf(d2.x, 0.f)) : 0.f;
+            g[q + 1] = in1 ? sqrt_approx(fmaxf(d2.y, 0.f)) : 0.f;
+          }
+        }
+        if (flagged) {
+#pragma unroll
+          for (int q = 0; q < 32; ++q)
+            if ((flagged >> q) & 1u) g[q] = sqrtf(exact_d2_256(zh, zl, i, jbase + q, L));
+        }
       }
       if (cell_out != nullptr && i < S) {
         float* dst = cell_out + ((size_t)cell * S + i) * S + jbase;
@@ -304,16 +369,13 @@ k_dist_gram_tc(const float* __restrict__ z, int64_t n_cells, int S, int L, float
         tmem_st_wait();
       }
     }
-    // buffer buf^1 (cell p+1) is complete, buffer buf and the staging area are free once BOTH warpgroups are here
-    fence_proxy_async();
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    if (p + 2 < p1) fetch(p + 2);  // lands during the epilogues of cell p+1
+    // the exact-recompute route and the norms read buffer buf: every worker is done with cell p before the prep
+    // of cell p+2 overwrites it
+    workers_sync();
   }
   if (gp.n_keys && cur_cell >= 0) flush(cur_cell);
   tc_fence_before();
-  __syncthreads();
+  __syncthreads();  // joins the issuer warp
   if (tid < 32) tmem_dealloc(tmem_base, 512);
 }
 
