@@ -488,7 +488,8 @@ static int run_device_impl(MrviHandle* h, int64_t n, const float* X, int64_t ldx
     }
     if (need_z) {
       if (h->precision == MRVI_PRECISION_TC) {
-        if ((err = tc_launch_qz(h->tc, h->net, m, h->cb, z, st))) return err;
+        if (h->tc.fused_smem_bytes) tc_launch_fused_chain(h->tc, h->net, m, h->cb, z, st);  // two threads per row, 1 CTA / SM
+        else if ((err = tc_launch_qz(h->tc, h->net, m, h->cb, z, st))) return err;
         LAUNCH_CHECK();
       } else {
         if ((err = launch_qz(h, h->cb, m, net.S, z, st))) return err;
@@ -522,7 +523,8 @@ static int chain_and_dist(MrviHandle* h, const CellBuf& cb, int64_t n, int norm,
   }
   float* z = z_out ? z_out : z_scratch;
   if (h->precision == MRVI_PRECISION_TC) {
-    if ((err = tc_launch_qz(h->tc, net, n, cb, z, st))) return err;
+    if (h->tc.fused_smem_bytes) tc_launch_fused_chain(h->tc, net, n, cb, z, st);
+    else if ((err = tc_launch_qz(h->tc, net, n, cb, z, st))) return err;
     LAUNCH_CHECK();
   } else if ((err = launch_qz(h, cb, n, net.S, z, st))) return err;
   if (need_dist && (err = launch_dist(h, z, n, norm, cell_out, gp, st))) return err;

@@ -280,7 +280,7 @@ __device__ __forceinline__ void flush_acc(uint32_t t_acc_lane, int half, const G
 __global__ void __launch_bounds__(kFusedThreads, 1)
 k_chain_fused_tc(const __grid_constant__ TcNet tc, CellBuf cb, int64_t n_cells, int S, int L, int Lq,
                  float* __restrict__ z_out, float* __restrict__ cell_out, GroupPlan gp, int64_t n_tiles,
-                 int cells_per_tile, int64_t tiles_per_cta) {
+                 int cells_per_tile, int64_t tiles_per_cta, int tiles_per_cell) {
   // no-swizzle UMMA operands and bulk copies need 16-byte alignment only; keeping the plain array (no integer
   // re-alignment) lets the compiler see the shared address space (LDS/STS instead of generic LD/ST)
   extern __shared__ __align__(1024) uint8_t smem_tc[];
@@ -363,14 +363,16 @@ k_chain_fused_tc(const __grid_constant__ TcNet tc, CellBuf cb, int64_t n_cells, 
   const int64_t tile_begin = (int64_t)blockIdx.x * tiles_per_cta;
   const int64_t tile_end = min(n_tiles, tile_begin + tiles_per_cta);
   for (int64_t tile = tile_begin + wg; tile < tile_end; tile += 2) {
-    const int64_t pos = tile * cells_per_tile + lc;  // sorted position of this row's cell
-    const bool valid = row_in_tile && pos < n_cells;
+    // tiles_per_cell > 1 (S > 128, chain only: z_out, no distances): tile -> (cell, 128-row slice of its samples)
+    const int64_t pos = tiles_per_cell > 1 ? tile / tiles_per_cell : tile * cells_per_tile + lc;  // sorted position of this row's cell
+    const int sr = tiles_per_cell > 1 ? (int)(tile % tiles_per_cell) * kTcRows + r : s;
+    const bool valid = tiles_per_cell > 1 ? (sr < S && pos < n_cells) : (row_in_tile && pos < n_cells);
     const int64_t cell = valid ? (gp.order ? (int64_t)gp.order[pos] : pos) : 0;
     const int code = (valid && gp.n_keys) ? gp.comp_sorted[pos] : -2;
-    const int ss = valid ? s : 0;
+    const int ss = valid ? sr : 0;
     // sampled paths: every (cell, s) row carries its own draw of u (CellBuf::per_row); z_base then differs
     // between the rows of a cell and no longer cancels in the distances
-    const int64_t fi = cb.per_row ? (valid ? cell * S + s : 0) : cell;
+    const int64_t fi = cb.per_row ? (valid ? cell * S + sr : 0) : cell;
 
     // ================= attention features of head `half` -> A1 chunks 2*half, 2*half+1 =================
     {
@@ -495,28 +497,43 @@ k_chain_fused_tc(const __grid_constant__ TcNet tc, CellBuf cb, int64_t n_cells, 
       float v[32];
       if (ncol == 16) tmem_ld16(t_lane + col0, v); else tmem_ld32(t_lane + col0, v);
       tmem_ld_wait();
-      if (valid && z_out != nullptr) {
-        const float* zb = cb.zbase + fi * L;
-        float* dst = z_out + (cell * S + s) * (int64_t)L;
-#pragma unroll
-        for (int l = 0; l < 32; ++l)
-          if (l < ncol && col0 + l < L) dst[col0 + l] = __ldg(zb + col0 + l) + v[l];
-      }
-      if (cb.per_row && valid && need_dist) {
+      if (cb.per_row && valid) {
         const float* zb = cb.zbase + fi * L;
 #pragma unroll
         for (int l = 0; l < 32; ++l)
           if (l < ncol && col0 + l < L) v[l] += __ldg(zb + col0 + l);
       }
-      if (need_dist) {
-        // A1/A3 are dead (GEMM5 done): overlay the fp32 residual tile on them
+      // A1/A3 are dead (GEMM5 done): overlay the fp32 residual tile on them
 #pragma unroll
-        for (int l = 0; l < 32; ++l)
-          if (l < ncol && col0 + l < Kz) zf[r * zld + col0 + l] = (col0 + l < L && valid) ? v[l] : 0.f;
+      for (int l = 0; l < 32; ++l)
+        if (l < ncol && col0 + l < Kz) zf[r * zld + col0 + l] = (col0 + l < L && valid) ? v[l] : 0.f;
+      if (z_out != nullptr && half == 0) {  // row -> (output row, z_base row) for the coalesced copy below
+        long long* rowinfo = reinterpret_cast<long long*>(xch);  // xch is free between the epilogues and the centring
+        rowinfo[r] = valid ? (long long)(cell * S + sr) : -1ll;
+        rowinfo[128 + r] = (long long)fi;
       }
     }
     tc_fence_before();
     wg_sync(wg);
+    if (z_out != nullptr) {
+      // z = z_base + residual, written with fully coalesced 4-byte stores: consecutive threads walk the tile
+      // row-major (a thread-per-row store would touch 32 different rows, i.e. 32 sectors, per instruction)
+      const long long* rowinfo = reinterpret_cast<const long long*>(xch);
+      const bool add_zb = !cb.per_row;
+      int r2 = wt / L, l2 = wt - r2 * L;
+      const int dr = 256 / L, dl = 256 - dr * L;
+      while (r2 < 128) {
+        const long long orow = rowinfo[r2];
+        if (orow >= 0) {
+          float val = zf[r2 * zld + l2];
+          if (add_zb) val += __ldg(cb.zbase + rowinfo[128 + r2] * L + l2);
+          z_out[orow * L + l2] = val;
+        }
+        r2 += dr; l2 += dl;
+        if (l2 >= L) { l2 -= L; ++r2; }
+      }
+      wg_sync(wg);  // rowinfo (xch) and zf are reused right away
+    }
     if (!need_dist) continue;
 
     // ================= centre per cell, norms, (hi, lo) Gram operands =================
@@ -732,7 +749,23 @@ inline void tc_launch_fused(const TcNet& tc, const NetW& net, int64_t n, const C
   const int grid = (int)std::min<int64_t>((n_tiles + 1) / 2, tc.sm_count);
   const int64_t tiles_per_cta = (n_tiles + grid - 1) / grid;
   k_chain_fused_tc<<<grid, kFusedThreads, tc.fused_smem_bytes, st>>>(tc, cb, n, S, net.L, net.Lq, z_out, cell_out, gp,
-                                                                    n_tiles, cpt, tiles_per_cta);
+                                                                    n_tiles, cpt, tiles_per_cta, 1);
+}
+
+// chain only (z_out, no distances) through the same kernel, any S: for S > 128 a cell spans several 128-row tiles
+inline void tc_launch_fused_chain(const TcNet& tc, const NetW& net, int64_t n, const CellBuf& cb, float* z_out, cudaStream_t st) {
+  const int S = net.S;
+  int cpt = 1, tpc = 1;
+  int64_t n_tiles;
+  if (S <= kTcRows) { cpt = kTcRows / S; n_tiles = (n + cpt - 1) / cpt; }
+  else { tpc = (S + kTcRows - 1) / kTcRows; n_tiles = n * tpc; }
+  if (n_tiles == 0) return;
+  const int grid = (int)std::min<int64_t>((n_tiles + 1) / 2, tc.sm_count);
+  const int64_t tiles_per_cta = (n_tiles + grid - 1) / grid;
+  GroupPlan none;
+  memset(&none, 0, sizeof(none));
+  k_chain_fused_tc<<<grid, kFusedThreads, tc.fused_smem_bytes, st>>>(tc, cb, n, S, net.L, net.Lq, z_out, nullptr, none, n_tiles,
+                                                                    cpt, tiles_per_cta, tpc);
 }
 
 }  // namespace mrvi
