@@ -297,9 +297,10 @@ static int build_net(MrviHandle* h, const ParamTable& pt) {
 
 static int setup_workspace(MrviHandle* h) {
   const NetW& n = h->net;
-  // chunk: z buffer <= 256 MiB, <= 65536 cells, multiple of 128 cells
+  // chunk: z buffer <= 2 GiB (of 180 GB), <= 65536 cells, multiple of 128 cells.  Long chunks matter for the
+  // grouped reductions: every CTA flushes its run accumulators at least once per launch
   int64_t per_cell = (int64_t)n.S * n.L * sizeof(float);
-  int64_t ch = (256ll << 20) / per_cell;
+  int64_t ch = (2048ll << 20) / per_cell;
   if (ch > 65536) ch = 65536;
   ch = ch / 128 * 128;
   if (ch < 128) ch = 128;
@@ -972,6 +973,12 @@ int mrvi_run_sampled_host(MrviHandle* h, int64_t n_cells, const float* X, int64_
   return run_sampled_host_impl(h, n_cells, X, ldx, sample_idx, mc_samples, seed, cell_offset, u_noise, base_noise, n_keys,
                                group_codes, n_groups, norm, normalize, cell_out, group_sums, group_counts, z_out, chunk_cells);
 }
+
+#ifdef MRVI_DBG_DIST
+int mrvi_dbg_dist_read(long long* out, int n) {  // debug builds only (tools/dbg)
+  return (int)cudaMemcpyFromSymbol(out, mrvi::g_dbg_dist, sizeof(long long) * n);
+}
+#endif
 
 int mrvi_last_stage_ms(MrviHandle* h, float out_ms[4]) {
   if (!h || !out_ms) return fail(MRVI_ERR_INVALID_ARG, "null argument");

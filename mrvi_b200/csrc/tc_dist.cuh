@@ -20,15 +20,27 @@
 //     columns; no lock).
 // TMEM: [0,128) work, [128,512) accumulators of the three blocks.
 #pragma once
+#include "tc_encoder.cuh"
 #include "tc_fused.cuh"
 
 namespace mrvi {
 
-constexpr int kDistTcThreads = 544;   // 16 epilogue warps (2 warpgroups) + 1 warp that issues bulk copies and MMAs
+#ifdef MRVI_DBG_DIST
+// clock64 timeline of CTA 0 (tools/dbg): [cell][slot]
+__device__ long long g_dbg_dist[64 * 32];
+#define DBG_STAMP(cellidx, slot) do { if (blockIdx.x == 0 && (cellidx) < 64) g_dbg_dist[(cellidx) * 32 + (slot)] = clock64(); } while (0)
+#else
+#define DBG_STAMP(cellidx, slot) do { } while (0)
+#endif
+
+constexpr int kDistTcThreads = 576;   // 16 epilogue warps (2 warpgroups) + 2 issuer warps (one per warpgroup: MMAs; the first also the bulk copies)
 constexpr int kDistTcWorkers = 512;
 
+constexpr uint32_t kDistLbo = 4096 + 16;  // bytes between K chunks: 256 rows x 16 B + one row of padding, which makes the
+                                          // prep's 16-byte stores (8 chunks x 4 rows per warp) bank-conflict free
+
 struct DistTcSmem {
-  uint32_t z[2];      // per buffer: zh | zl, each 256 rows x Kz f16, K-major, LBO = 4096
+  uint32_t z[2];      // per buffer: zh | zl, each 256 rows x Kz f16, K-major, LBO = kDistLbo
   uint32_t part[2];   // per buffer: [256] fp32 squared norms of the (hi + lo) operand rows
   uint32_t stage;     // raw fp32 z of the next cell ([S][L], landed by one bulk copy)
   uint32_t ctrl;
@@ -39,7 +51,7 @@ struct DistTcSmem {
 __host__ __device__ inline DistTcSmem dist_tc_smem(int L, int S = 256) {
   DistTcSmem m;
   m.Kz = L <= 32 ? 32 : 64;
-  const uint32_t zb = 2u * 256u * (uint32_t)m.Kz * 2u;
+  const uint32_t zb = (2u * (uint32_t)(m.Kz >> 3) * kDistLbo + 127u) & ~127u;
   uint32_t o = 0;
   m.z[0] = o; o += zb;
   m.z[1] = o; o += zb;
@@ -51,19 +63,35 @@ __host__ __device__ inline DistTcSmem dist_tc_smem(int L, int S = 256) {
   return m;
 }
 
-// exact squared distance of operand rows a and b (K-chunk stride 4096 bytes)
-__device__ __noinline__ float exact_d2_256(const uint8_t* zh, const uint8_t* zl, int a, int b, int L) {
-  float e = 0.f;
-  for (int k = 0; k < L; ++k) {
-    const uint32_t ko = (uint32_t)(k >> 3) * 4096u + (uint32_t)(k & 7) * 2u;
-    const float za = __half2float(*reinterpret_cast<const __half*>(zh + ko + a * 16)) +
-                     __half2float(*reinterpret_cast<const __half*>(zl + ko + a * 16));
-    const float zb = __half2float(*reinterpret_cast<const __half*>(zh + ko + b * 16)) +
-                     __half2float(*reinterpret_cast<const __half*>(zl + ko + b * 16));
-    const float df = zb - za;
-    e = fmaf(df, df, e);
+// 32 Gram entries of one row -> distances, in place; returns min over the entries of (d^2 - 2^-12 (n_i + n_j)):
+// negative = some entry is cancellation dominated (the caller recomputes those exactly).  DIAG: entry q == lane is
+// the row's diagonal entry (forced to zero, excluded from the test).
+template <bool DIAG>
+__device__ __forceinline__ float dist_chunk_fast(float (&g)[32], const float* nrm_j, float n_i, int lane) {
+  const float2 ni2 = make_float2(n_i, n_i), m2 = make_float2(-2.0f, -2.0f), thr2 = make_float2(-1.0f / 4096.0f, -1.0f / 4096.0f);
+  float tmin = 0.f;
+#pragma unroll
+  for (int q4 = 0; q4 < 8; ++q4) {
+    const float4 nj = *reinterpret_cast<const float4*>(nrm_j + 4 * q4);
+    const float2 njp[2] = {make_float2(nj.x, nj.y), make_float2(nj.z, nj.w)};
+#pragma unroll
+    for (int e2 = 0; e2 < 2; ++e2) {
+      const int q = 4 * q4 + 2 * e2;
+      const float2 sn = __fadd2_rn(ni2, njp[e2]);
+      const float2 d2 = __ffma2_rn(make_float2(g[q], g[q + 1]), m2, sn);
+      const float2 tt = __ffma2_rn(sn, thr2, d2);  // < 0: cancellation dominated
+      float t0 = tt.x, t1 = tt.y;
+      float r0 = sqrt_approx(fmaxf(d2.x, 0.f)), r1 = sqrt_approx(fmaxf(d2.y, 0.f));
+      if (DIAG) {
+        const bool dg0 = q == lane, dg1 = q + 1 == lane;
+        t0 = dg0 ? 0.f : t0; t1 = dg1 ? 0.f : t1;
+        r0 = dg0 ? 0.f : r0; r1 = dg1 ? 0.f : r1;
+      }
+      tmin = fminf(tmin, fminf(t0, t1));
+      g[q] = r0; g[q + 1] = r1;
+    }
   }
-  return e;
+  return tmin;
 }
 
 __global__ void __launch_bounds__(kDistTcThreads, 1)
@@ -103,7 +131,7 @@ k_dist_gram_tc(const float* __restrict__ z, int64_t n_cells, int S, int L, float
   const uint32_t t_work = tmem_base + lane_off + colw;
   const uint32_t t_acc0 = tmem_base + 128 + lane_off + colw;  // + 128 * block
   const uint32_t idesc64 = umma_idesc_f16(64);
-  const uint32_t zbytes = 256u * (uint32_t)Kz * 2u;           // one of (zh, zl)
+  const uint32_t zbytes = (uint32_t)(Kz >> 3) * kDistLbo;     // one of (zh, zl)
   uint32_t phase = 0;
 
   const int64_t p0 = (int64_t)blockIdx.x * cells_per_cta;
@@ -134,50 +162,68 @@ k_dist_gram_tc(const float* __restrict__ z, int64_t n_cells, int S, int L, float
       workers_sync();
     }
   };
-  // ---- operand prep of the staged cell into buffer buf (all 512 threads)
+  // ---- operand prep of the staged cell into buffer buf (all 512 threads).  The nck = Kz / 8 chunks of a row sit in
+  // adjacent lanes: a thread keeps its chunk (so the reference row's chunk stays in registers), the row norm is a
+  // 2-3 step shuffle reduction, and with the padded chunk stride the 16-byte operand stores are conflict free.
   auto prep = [&](int buf) {
-    const int row = tid >> 1, kh = tid & 1;   // the two K halves of a row sit in adjacent lanes
-    const bool vrow = row < S;
-    const float* zr = stage + (vrow ? row : 0) * L;
-    const float* z0 = stage;
+    const int nck = Kz >> 3, lg = nck == 8 ? 3 : 2;
+    const int c = tid & (nck - 1), rr = tid >> lg, rows_per_pass = kDistTcWorkers >> lg;
     uint8_t* zh = smem + sm.z[buf];
     uint8_t* zl = zh + zbytes;
-    float nrm_p = 0.f;
-    const int nch = Kz >> 4;
-    for (int cc = 0; cc < nch; ++cc) {
-      const int c = kh * nch + cc;
+    float* nrm = reinterpret_cast<float*>(smem + sm.part[buf]);
+    float2 z0p[4];
+#pragma unroll
+    for (int j2 = 0; j2 < 4; ++j2) {
+      const int k0 = c * 8 + 2 * j2;
+      z0p[j2] = make_float2(k0 < L ? -stage[k0] : 0.f, k0 + 1 < L ? -stage[k0 + 1] : 0.f);
+    }
+    const bool even = (L & 1) == 0;
+#pragma unroll 2
+    for (int row = rr; row < 256; row += rows_per_pass) {
+      const bool vrow = row < S;
+      const float* zr = stage + (vrow ? row : 0) * L + c * 8;
       uint32_t hw[4], lw[4];
+      float2 n2 = make_float2(0.f, 0.f);
 #pragma unroll
       for (int j2 = 0; j2 < 4; ++j2) {
-        const int k0 = c * 8 + 2 * j2, k1 = k0 + 1;
-        const float a = (vrow && k0 < L) ? zr[k0] - z0[k0] : 0.f;
-        const float b = (vrow && k1 < L) ? zr[k1] - z0[k1] : 0.f;
-        split2(a, b, hw[j2], lw[j2]);
-        const float ar = h2f_lo(hw[j2]) + h2f_lo(lw[j2]), br = h2f_hi(hw[j2]) + h2f_hi(lw[j2]);
-        nrm_p = fmaf(ar, ar, nrm_p);
-        nrm_p = fmaf(br, br, nrm_p);
+        const int k0 = c * 8 + 2 * j2;
+        float2 a;
+        if (even) a = (vrow && k0 < L) ? *reinterpret_cast<const float2*>(zr + 2 * j2) : make_float2(0.f, 0.f);  // L even: k0 + 1 < L too
+        else a = make_float2((vrow && k0 < L) ? zr[2 * j2] : 0.f, (vrow && k0 + 1 < L) ? zr[2 * j2 + 1] : 0.f);
+        a = __fadd2_rn(a, vrow ? z0p[j2] : make_float2(0.f, 0.f));
+        split2v(a, hw[j2], lw[j2]);
+        n2 = __ffma2_rn(a, a, n2);  // (hi + lo differs from a by 2^-22 relative: the level of the omitted lo.lo term)
       }
-      *reinterpret_cast<uint4*>(zh + c * 4096 + row * 16) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-      *reinterpret_cast<uint4*>(zl + c * 4096 + row * 16) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+      *reinterpret_cast<uint4*>(zh + c * kDistLbo + row * 16) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+      *reinterpret_cast<uint4*>(zl + c * kDistLbo + row * 16) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+      float nr = n2.x + n2.y;
+      nr += __shfl_xor_sync(0xffffffffu, nr, 1);
+      nr += __shfl_xor_sync(0xffffffffu, nr, 2);
+      if (nck == 8) nr += __shfl_xor_sync(0xffffffffu, nr, 4);
+      if (c == 0) nrm[row] = nr;
     }
-    nrm_p += __shfl_xor_sync(0xffffffffu, nrm_p, 1);
-    if (kh == 0) reinterpret_cast<float*>(smem + sm.part[buf])[row] = nrm_p;
   };
 
   // ---- this warpgroup's N = 64 slice of Gram block (bi, bj) of buffer buf
   // (descriptor of address a + off = descriptor of a + (off >> 4): the address field holds a >> 4 and cannot carry
   //  out of its 14 bits for shared-memory addresses)
-  const uint64_t dbase0 = umma_desc(smem_u32(smem + sm.z[0]), 4096, 128), dbase1 = umma_desc(smem_u32(smem + sm.z[1]), 4096, 128);
+  const uint64_t dbase0 = umma_desc(smem_u32(smem + sm.z[0]), kDistLbo, 128), dbase1 = umma_desc(smem_u32(smem + sm.z[1]), kDistLbo, 128);
   auto issue_block = [&](int g_, int buf, int bi, int bj) {
-    const uint64_t dh = buf ? dbase1 : dbase0, dl = dh + (zbytes >> 4);
+    // only the 14-bit address field (low word) differs between the descriptors
+    const uint32_t hi = (uint32_t)(dbase0 >> 32);
+    const uint32_t lo_h = (uint32_t)(buf ? dbase1 : dbase0), lo_l = lo_h + (zbytes >> 4);
     const uint32_t a16 = (uint32_t)bi * 128u, b16 = (uint32_t)bj * 128u + (uint32_t)g_ * 64u;  // row offsets, 16-byte units
+    uint32_t ah = lo_h + a16, al = lo_l + a16, bh = lo_h + b16, bl = lo_l + b16;
     const uint32_t d = tmem_base + g_ * 64;
-    for (int ks = 0; ks < Kz / 16; ++ks) {
-      const uint32_t ko16 = (uint32_t)ks * 512u;  // two 4096-byte K chunks per 16-wide slice
-      const uint64_t ah = dh + a16 + ko16, al = dl + a16 + ko16, bh = dh + b16 + ko16, bl = dl + b16 + ko16;
-      umma_f16(d, ah, bh, idesc64, ks == 0 ? 0u : 1u);
-      umma_f16(d, ah, bl, idesc64, 1u);
-      umma_f16(d, al, bh, idesc64, 1u);
+    auto mk = [hi](uint32_t lo) { return ((uint64_t)hi << 32) | lo; };
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      if (ks < Kz / 16) {
+        umma_f16(d, mk(ah), mk(bh), idesc64, ks == 0 ? 0u : 1u);
+        umma_f16(d, mk(ah), mk(bl), idesc64, 1u);
+        umma_f16(d, mk(al), mk(bh), idesc64, 1u);
+        ah += 2u * (kDistLbo >> 4); al += 2u * (kDistLbo >> 4); bh += 2u * (kDistLbo >> 4); bl += 2u * (kDistLbo >> 4);  // two K chunks per 16-wide slice
+      }
     }
     umma_commit(&bar_mma[g_]);
   };
@@ -216,27 +262,27 @@ k_dist_gram_tc(const float* __restrict__ z, int64_t n_cells, int S, int L, float
   };
 
   if (!worker) {
-    // ================= issuer warp: bulk copies of z and all MMAs (one thread) =================
-    if (tid == kDistTcWorkers) {
+    // ================= issuer warps: one thread each; warp 16 -> warpgroup 0 + the bulk copies of z, warp 17 -> warpgroup 1
+    if ((tid & 31) == 0) {
+      const int g_ = (tid - kDistTcWorkers) >> 5;
       auto tma = [&](int64_t p) {
-        if (!use_tma) return;
+        if (!use_tma || g_ != 0) return;
         mbar_expect_tx(bar_z, zcell_bytes);
         bulk_g2s(stage, cell_src(p), zcell_bytes, bar_z);
       };
-      uint32_t ops_phase = 0, free_phase = 1;  // a fresh mbarrier passes a wait on parity 1; both warpgroups' barriers advance together
+      uint32_t ops_phase = 0, free_phase = 1;  // a fresh mbarrier passes a wait on parity 1
       tma(p0);
       mbar_wait(bar_ops, ops_phase); ops_phase ^= 1;    // operands of p0 written, staging consumed
       if (p0 + 1 < p1) tma(p0 + 1);
       for (int64_t p = p0; p < p1; ++p) {
         const int buf = (int)((p - p0) & 1);
+#pragma unroll 1
         for (int b = 0; b < 3; ++b) {
-#pragma unroll
-          for (int g_ = 0; g_ < 2; ++g_) {
-            mbar_wait(&bar_free[g_], free_phase);
-            tc_fence_after();
-            issue_block(g_, buf, b == 2 ? 1 : 0, b == 0 ? 0 : 1);
-          }
-          free_phase ^= 1;
+          mbar_wait(&bar_free[g_], free_phase); free_phase ^= 1;
+          tc_fence_after();
+          if (g_ == 0) DBG_STAMP(p - p0, 0 + 2 * b);
+          issue_block(g_, buf, b == 2 ? 1 : 0, b == 0 ? 0 : 1);
+          if (g_ == 0) DBG_STAMP(p - p0, 1 + 2 * b);
         }
         if (p + 1 < p1) {
           mbar_wait(bar_ops, ops_phase); ops_phase ^= 1;  // prep(p+1) done by every worker
@@ -260,15 +306,24 @@ k_dist_gram_tc(const float* __restrict__ z, int64_t n_cells, int S, int L, float
   int64_t cur_cell = -1;
   for (int64_t p = p0; p < p1; ++p) {
     const int buf = (int)((p - p0) & 1);
+    if (tid == 0) DBG_STAMP(p - p0, 22);
     const int64_t cell = gp.order ? (int64_t)gp.order[p] : p;
     const int code = gp.n_keys ? gp.comp_sorted[p] : 0;
+    if (tid == 0) DBG_STAMP(p - p0, 8);
     if (p + 1 < p1) {  // overlaps the MMAs of block (0,0), which the issuer warp has already queued
       stage_ready(p + 1);
+      if (tid == 0) DBG_STAMP(p - p0, 9);
       prep(buf ^ 1);
       fence_proxy_async();
       mbar_arrive(bar_ops);
     }
+
+    if (tid == 0) DBG_STAMP(p - p0, 10);
+#ifdef MRVI_DBG_DIST
+    const long long t_prep_done = clock64();
+#endif
     if (gp.n_keys && cur_cell >= 0 && code != cur_code) flush(cur_cell);
+    if (tid == 0) DBG_STAMP(p - p0, 23);
     cur_code = code; cur_cell = cell;
     const uint8_t* zh = smem + sm.z[buf];
     const uint8_t* zl = zh + zbytes;
@@ -276,44 +331,37 @@ k_dist_gram_tc(const float* __restrict__ z, int64_t n_cells, int S, int L, float
 #pragma unroll 1
     for (int b = 0; b < 3; ++b) {
       const int bi = b == 2 ? 1 : 0, bj = b == 0 ? 0 : 1;
+      if (tid == 0) DBG_STAMP(p - p0, 11 + 3 * b);
       mbar_wait(&bar_mma[wg], phase); phase ^= 1;
       tc_fence_after();
+      if (tid == 0) DBG_STAMP(p - p0, 12 + 3 * b);
       float g[32];
       tmem_ld32(t_work, g);
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(&bar_free[wg]);  // this thread has read its work columns: the issuer may queue the next block
+      if (tid == 0) DBG_STAMP(p - p0, 13 + 3 * b);
       const int i = bi * 128 + r, jbase = bj * 128 + colw;
       const float n_i = part[i];
       // warp-uniform cases: `full` = every row of the warp and the whole chunk lie inside the S x S matrix;
       // `diag_chunk` = the chunk holds the diagonal entries of this warp's rows (diagonal blocks only)
       const bool full = __all_sync(0xffffffffu, i < S) && jbase + 32 <= S;
       const bool diag_chunk = (b != 1) && ((colw >> 5) == warp_q);
-      const float2 ni2 = make_float2(n_i, n_i), m2 = make_float2(-2.0f, -2.0f), thr2 = make_float2(-1.0f / 4096.0f, -1.0f / 4096.0f);
-      if (full && !diag_chunk) {
-        // fast path: no bounds, no diagonal; cancellation-dominated entries are only DETECTED here (min of tt)
-        float tmin = 0.f;
+      if (full) {
+        // fast path: no bounds checks; cancellation-dominated entries are only DETECTED here
+        const float tmin = diag_chunk ? dist_chunk_fast<true>(g, part + jbase, n_i, tid & 31)
+                                      : dist_chunk_fast<false>(g, part + jbase, n_i, tid & 31);
+        if (__any_sync(0xffffffffu, tmin < 0.f)) {  // rare: near-duplicate samples -> exact direct-difference distance
+          uint32_t flagged = 0u;
+          if (tmin < 0.f) {
 #pragma unroll
-        for (int q4 = 0; q4 < 8; ++q4) {
-          const float4 nj = *reinterpret_cast<const float4*>(part + jbase + 4 * q4);
-          const float2 njp[2] = {make_float2(nj.x, nj.y), make_float2(nj.z, nj.w)};
-#pragma unroll
-          for (int e2 = 0; e2 < 2; ++e2) {
-            const int q = 4 * q4 + 2 * e2;
-            const float2 sn = __fadd2_rn(ni2, njp[e2]);
-            const float2 d2 = __ffma2_rn(make_float2(g[q], g[q + 1]), m2, sn);
-            const float2 tt = __ffma2_rn(sn, thr2, d2);  // < 0: cancellation dominated
-            tmin = fminf(tmin, fminf(tt.x, tt.y));
-            g[q] = sqrt_approx(fmaxf(d2.x, 0.f));
-            g[q + 1] = sqrt_approx(fmaxf(d2.y, 0.f));
+            for (int q = 0; q < 32; ++q)
+              if (jbase + q != i && g[q] * g[q] < (n_i + part[jbase + q]) * (1.0f / 4096.0f)) flagged |= 1u << q;
           }
-        }
-        if (tmin < 0.f) {  // rare: near-duplicate samples -> exact direct-difference distance
-#pragma unroll
-          for (int q = 0; q < 32; ++q)
-            if (g[q] * g[q] < (n_i + part[jbase + q]) * (1.0f / 4096.0f)) g[q] = sqrtf(exact_d2_256(zh, zl, i, jbase + q, L));
+          exact_fix_warp<kDistLbo>(g, flagged, zh, zl, i, jbase, L);
         }
       } else {
+        const float2 ni2 = make_float2(n_i, n_i), m2 = make_float2(-2.0f, -2.0f), thr2 = make_float2(-1.0f / 4096.0f, -1.0f / 4096.0f);
         uint32_t flagged = 0u;
 #pragma unroll
         for (int q4 = 0; q4 < 8; ++q4) {
@@ -333,11 +381,7 @@ k_dist_gram_tc(const float* __restrict__ z, int64_t n_cells, int S, int L, float
             g[q + 1] = in1 ? sqrt_approx(fmaxf(d2.y, 0.f)) : 0.f;
           }
         }
-        if (flagged) {
-#pragma unroll
-          for (int q = 0; q < 32; ++q)
-            if ((flagged >> q) & 1u) g[q] = sqrtf(exact_d2_256(zh, zl, i, jbase + q, L));
-        }
+        if (__any_sync(0xffffffffu, flagged != 0u)) exact_fix_warp<kDistLbo>(g, flagged, zh, zl, i, jbase, L);
       }
       if (cell_out != nullptr && i < S) {
         float* dst = cell_out + ((size_t)cell * S + i) * S + jbase;
@@ -357,21 +401,30 @@ k_dist_gram_tc(const float* __restrict__ z, int64_t n_cells, int S, int L, float
         }
       }
       if (gp.n_keys > 0) {
-        float acc[32];
-        tmem_ld32(t_acc0 + b * 128, acc);
-        tmem_ld_wait();
 #pragma unroll
-        for (int q = 0; q < 16; ++q) {
-          const float2 t = __fadd2_rn(make_float2(acc[2 * q], acc[2 * q + 1]), make_float2(g[2 * q], g[2 * q + 1]));
-          acc[2 * q] = t.x; acc[2 * q + 1] = t.y;
+        for (int hq = 0; hq < 2; ++hq) {  // two 16-column halves: bounds the live registers
+          float acc[16];
+          tmem_ld16(t_acc0 + b * 128 + hq * 16, acc);
+          tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float2 t = __fadd2_rn(make_float2(acc[2 * q], acc[2 * q + 1]), make_float2(g[hq * 16 + 2 * q], g[hq * 16 + 2 * q + 1]));
+            acc[2 * q] = t.x; acc[2 * q + 1] = t.y;
+          }
+          tmem_st16(t_acc0 + b * 128 + hq * 16, reinterpret_cast<uint32_t*>(acc));
         }
-        tmem_st32(t_acc0 + b * 128, reinterpret_cast<uint32_t*>(acc));
         tmem_st_wait();
       }
     }
     // the exact-recompute route and the norms read buffer buf: every worker is done with cell p before the prep
     // of cell p+2 overwrites it
+    if (tid == 0) DBG_STAMP(p - p0, 20);
+#ifdef MRVI_DBG_DIST
+    if (blockIdx.x == 0 && (tid & 31) == 0 && (p - p0) < 32) g_dbg_dist[1024 + (p - p0) * 16 + (tid >> 5)] = clock64();
+    if (blockIdx.x == 0 && (tid & 31) == 0 && (p - p0) < 24) g_dbg_dist[1536 + (p - p0) * 16 + (tid >> 5)] = t_prep_done;
+#endif
     workers_sync();
+    if (tid == 0) DBG_STAMP(p - p0, 21);
   }
   if (gp.n_keys && cur_cell >= 0) flush(cur_cell);
   tc_fence_before();

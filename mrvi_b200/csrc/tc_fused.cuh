@@ -131,11 +131,18 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
       : "r"(taddr));
 }
 
-// exact squared distance of tile rows a and b from the K-major (hi, lo) f16 operand buffers
-__device__ __noinline__ float exact_d2(const uint8_t* zh, const uint8_t* zl, int a, int b, int L) {
+// Exact direct-difference distances for the cancellation-dominated entries of a warp's rows, computed by the WHOLE
+// warp (a lane-serial version keeps 31 lanes, and everybody behind the next barrier, waiting for thousands of
+// cycles): every lane passes its operand row and the bit mask of its flagged entries among columns
+// [jbase, jbase + 32); for each flagged (lane, q) the 32 lanes split the K range, warp-reduce the squared
+// differences, and the owner lane replaces g[q].  Operands: K-major (hi, lo) f16 buffers, chunk stride LBO bytes.
+// Must be called by all 32 lanes.
+template <uint32_t LBO>
+__device__ __noinline__ float exact_dist_warp(const uint8_t* zh, const uint8_t* zl, int a, int b, int L) {
+  const int lane = threadIdx.x & 31;
   float e = 0.f;
-  for (int k = 0; k < L; ++k) {
-    const uint32_t ko = (uint32_t)(k >> 3) * 2048u + (uint32_t)(k & 7) * 2u;
+  for (int k = lane; k < L; k += 32) {
+    const uint32_t ko = (uint32_t)(k >> 3) * LBO + (uint32_t)(k & 7) * 2u;
     const float za = __half2float(*reinterpret_cast<const __half*>(zh + ko + a * 16)) +
                      __half2float(*reinterpret_cast<const __half*>(zl + ko + a * 16));
     const float zb = __half2float(*reinterpret_cast<const __half*>(zh + ko + b * 16)) +
@@ -143,7 +150,31 @@ __device__ __noinline__ float exact_d2(const uint8_t* zh, const uint8_t* zl, int
     const float df = zb - za;
     e = fmaf(df, df, e);
   }
-  return e;
+  return sqrtf(warp_sum(e));
+}
+// (inlined: g stays in registers; only the reduction above is an out-of-line call)
+template <uint32_t LBO>
+__device__ __forceinline__ void exact_fix_warp(float (&g)[32], uint32_t flagged, const uint8_t* zh, const uint8_t* zl, int row,
+                                               int jbase, int L) {
+  const int lane = threadIdx.x & 31;
+  uint32_t any = __ballot_sync(0xffffffffu, flagged != 0u);
+#pragma unroll 1
+  while (any) {
+    const int leader = __ffs(any) - 1;
+    any &= any - 1;
+    uint32_t fl = __shfl_sync(0xffffffffu, flagged, leader);
+    const int a = __shfl_sync(0xffffffffu, row, leader);
+#pragma unroll 1
+    while (fl) {
+      const int q = __ffs(fl) - 1;
+      fl &= fl - 1;
+      const float d = exact_dist_warp<LBO>(zh, zl, a, jbase + q, L);
+      const bool mine = lane == leader;
+#pragma unroll
+      for (int qq = 0; qq < 32; ++qq)
+        if (mine && qq == q) g[qq] = d;
+    }
+  }
 }
 
 // LayerNorm + gelu of the 128-column accumulator row, this thread's 64-column half, written back in
@@ -661,11 +692,8 @@ k_chain_fused_tc(const __grid_constant__ TcNet tc, CellBuf cb, int64_t n_cells, 
           g[q + 1] = in1 ? sqrt_approx(fmaxf(d2.y, 0.f)) : 0.f;
         }
       }
-      if (flagged) {  // rare: near-duplicate samples -> exact direct-difference distance
-#pragma unroll
-        for (int q = 0; q < 32; ++q)
-          if ((flagged >> q) & 1u) g[q] = sqrtf(exact_d2(zh, zl, r, c * 32 + q, L));
-      }
+      if (__any_sync(0xffffffffu, flagged != 0u))  // rare: near-duplicate samples -> exact direct-difference distance
+        exact_fix_warp<2048u>(g, flagged, zh, zl, r, c * 32, L);
       if (cell_out != nullptr && valid) {
         float* dst = cell_out + ((size_t)cell * S + s) * S;
         if ((S & 3) == 0) {  // c0 and S are multiples of 4: 16-byte stores
