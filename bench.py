@@ -330,7 +330,8 @@ def main():
                                                 "~992 MUFU ops (512 attention ex2, 320 tanh, 128 sqrt, 32 rcp) at the measured 16/clk/SM "
                                                 "= 62 clk; tensor work is ~12 clk/row (DESIGN.md section 4)"},
                     "note": "achieved = algorithmic FLOP/cell (SURVEY 8d: 2*S*(att+mlp0+mlp1) [+ 3*S^2*L fused]) x cells / kernel CUDA-event time"}
-        h2d = n_per * (G * 4 + 4 + (4 if n_groups else 0))
+        x_wire = h.last_h2d_bytes()  # bytes of X that actually crossed PCIe in the last step (count chunks are narrowed)
+        h2d = x_wire + n_per * (4 + (4 if n_groups else 0))
         d2h = (n_groups * S * S * 8 if n_groups else 0) + (n_per * S * S * 4 if keep_cell else 0)
         line = {"metric": "cells/sec", "value": value, "unit": "cells/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": dev_s / args.steps * 1e3, "higher_is_better": True,
@@ -340,7 +341,9 @@ def main():
                 "cell_S2_per_sec": value * S * S,
                 "e2e": {"value": e2e_value, "unit": "cells/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "steps": e2e_steps, "ms_per_step": e2e_wall / e2e_steps * 1e3,
-                        "api": "mrvi_run_host (C-ABI, pinned host buffers)"},
+                        "host_input_bytes_per_step": n_per * (G * 4 + 4 + (4 if n_groups else 0)),
+                        "api": "mrvi_run_host (C-ABI, pinned host float32 buffers; integer count chunks are narrowed "
+                               "losslessly to uint8/uint16 on the host, inside the timed region, before the copy)"},
                 "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks}
         if not args.no_cpu_baseline and world == 1:
             sample = args.cpu_sample_cells or max(2048, min(n_per, int(40000 * 32 / S * 2000 / G) // 256 * 256))

@@ -170,6 +170,18 @@ int mrvi_run_sampled_host(MrviHandle* h, int64_t n_cells, const float* X, int64_
                           int32_t normalize, float* cell_out, double* const* group_sums,
                           int64_t* const* group_counts, float* z_out, int64_t chunk_cells);
 
+/*
+ * mrvi_run_host narrows dense count chunks losslessly before the host->device copy: a chunk whose float32 values are
+ * all integers in [0, 255] ([0, 65535]) crosses PCIe as uint8 (uint16) and is widened back to the identical float32
+ * values on the GPU; any other chunk is copied as it is (env MRVI_B200_NO_HOST_PACK=1 disables the narrowing).
+ * mrvi_last_h2d_bytes: bytes of X the most recent mrvi_run_host call actually copied host->device.
+ * mrvi_narrow_counts: the host-side narrowing itself (no GPU needed; exposed for tests): writes dense
+ * [n_rows][n_cols] uint8 / uint16 to `out` (capacity 2 * n_rows * n_cols bytes) and returns 1 / 2, or 0 when the
+ * rows are not narrowable.
+ */
+int64_t mrvi_last_h2d_bytes(MrviHandle* h);
+int mrvi_narrow_counts(const float* X, int64_t ldx, int64_t n_rows, int32_t n_cols, void* out, int32_t n_threads);
+
 /* Timing taps: device milliseconds spent in each stage of the most recent mrvi_run_* call
  * (CUDA events on the launching stream; valid after that stream is synchronised).
  * out_ms[0]=encoder (x->u), [1]=q(z|u,s) chain, [2]=distances+reductions, [3]=whole call. */

@@ -33,6 +33,8 @@ EXPORTED_SYMBOLS = (
     "mrvi_run_sampled_host",
     "mrvi_distances_device",
     "mrvi_last_stage_ms",
+    "mrvi_last_h2d_bytes",
+    "mrvi_narrow_counts",
 )
 
 
@@ -88,6 +90,10 @@ def load_library():
     lib.mrvi_distances_device.restype = C.c_int
     lib.mrvi_distances_device.argtypes = [vp, i64, vp, i32, C.POINTER(vp), C.POINTER(i32), i32, vp,
                                           C.POINTER(vp), vp]
+    lib.mrvi_last_h2d_bytes.restype = i64
+    lib.mrvi_last_h2d_bytes.argtypes = [vp]
+    lib.mrvi_narrow_counts.restype = C.c_int
+    lib.mrvi_narrow_counts.argtypes = [vp, i64, i64, i32, vp, i32]
     lib.mrvi_last_stage_ms.restype = C.c_int
     lib.mrvi_last_stage_ms.argtypes = [vp, C.POINTER(C.c_float)]
     if lib.mrvi_abi_version() != ABI_VERSION:
@@ -113,6 +119,22 @@ def _i32_array(vals: Sequence[int]):
     for i, v in enumerate(vals):
         arr[i] = int(v)
     return arr
+
+
+def narrow_counts(X: np.ndarray, n_threads: int = 4):
+    """The host-side lossless narrowing ``mrvi_run_host`` applies to dense count chunks (no GPU needed).
+    Returns ``(mode, array)``: mode 1 -> uint8, 2 -> uint16, 0 -> not narrowable (array is None)."""
+    X = np.ascontiguousarray(X, dtype=np.float32)
+    n, G = X.shape
+    out = np.empty(n * G * 2, dtype=np.uint8)
+    mode = load_library().mrvi_narrow_counts(X.ctypes.data, G, n, G, out.ctypes.data, int(n_threads))
+    if mode < 0:
+        _check(mode)
+    if mode == 1:
+        return 1, out[: n * G].reshape(n, G)
+    if mode == 2:
+        return 2, out.view(np.uint16)[: n * G].reshape(n, G)
+    return 0, None
 
 
 def kernel_launch_count() -> int:
@@ -283,6 +305,10 @@ class Handle:
         if want_z:
             out["z"] = z
         return out
+
+    def last_h2d_bytes(self) -> int:
+        """Bytes of X the last ``run_host`` copied host->device (count chunks are narrowed to uint8 / uint16)."""
+        return int(load_library().mrvi_last_h2d_bytes(self._h))
 
     def last_stage_ms(self):
         buf = (C.c_float * 4)()

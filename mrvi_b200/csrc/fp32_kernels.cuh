@@ -682,6 +682,26 @@ __global__ void k_csr_densify(const int64_t* __restrict__ indptr, int64_t nz0, c
   }
 }
 
+// widen a narrowed count chunk (uint8 / uint16, see host_pack.cpp) back to the identical float32 values
+template <typename T>
+__global__ void k_unpack_counts(const T* __restrict__ in, float* __restrict__ X, int64_t n) {
+  const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 16;
+  if (i0 + 16 <= n && (reinterpret_cast<uintptr_t>(in) & 15) == 0) {
+    T v[16];
+    if (sizeof(T) == 1) {
+      *reinterpret_cast<uint4*>(v) = __ldg(reinterpret_cast<const uint4*>(in + i0));
+    } else {
+      reinterpret_cast<uint4*>(v)[0] = __ldg(reinterpret_cast<const uint4*>(in + i0));
+      reinterpret_cast<uint4*>(v)[1] = __ldg(reinterpret_cast<const uint4*>(in + i0) + 1);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      *reinterpret_cast<float4*>(X + i0 + 4 * q) = make_float4((float)v[4 * q], (float)v[4 * q + 1], (float)v[4 * q + 2], (float)v[4 * q + 3]);
+  } else {
+    for (int64_t i = i0; i < min(n, i0 + 16); ++i) X[i] = (float)in[i];
+  }
+}
+
 // composite group code of each cell (mixed radix over (code_k + 1)), for the per-chunk sort
 __global__ void k_composite_codes(GroupPlan gp, const int32_t* n_groups_dev, int64_t n, int32_t* comp,
                                   int32_t* idx) {

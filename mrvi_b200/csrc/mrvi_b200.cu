@@ -3,16 +3,19 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include <atomic>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
+#include <thread>
 #include <string>
 #include <vector>
 
 #include "common.cuh"
+#include "host_pack.h"
 #include "fp32_kernels.cuh"
 #include "tc_kernels.cuh"
 #include "tc_encoder.cuh"
@@ -72,6 +75,11 @@ struct HostStage {  // device-side staging of mrvi_run_host, cached across calls
   int n_keys = 0;
   bool has_cell = false, has_z = false, has_u = false;
   float* X[2] = {nullptr, nullptr};
+  uint8_t* dpack[2] = {nullptr, nullptr};     // narrowed counts on the device (host_pack.cpp)
+  uint8_t* hpack[2] = {nullptr, nullptr};     // pinned host staging of the narrowed chunk
+  size_t pack_bytes = 0;
+  std::unique_ptr<PackPool> pool;
+  double pack_rate_gbps = 0.0;   // measured host narrowing rate (float32 bytes consumed per second), smoothed
   int64_t* csr_ptr[2] = {nullptr, nullptr};   // CSR staging (mrvi_run_host_csr)
   int32_t* csr_idx[2] = {nullptr, nullptr};
   float* csr_val[2] = {nullptr, nullptr};
@@ -89,6 +97,8 @@ struct HostStage {  // device-side staging of mrvi_run_host, cached across calls
   void free_buffers() {
     for (void* p : owned) cudaFree(p);
     owned.clear();
+    for (int i = 0; i < 2; ++i) { if (hpack[i]) cudaFreeHost(hpack[i]); hpack[i] = nullptr; dpack[i] = nullptr; }
+    pack_bytes = 0;
   }
   ~HostStage() {
     free_buffers();
@@ -117,6 +127,7 @@ struct MrviHandle {
   TcNet tc{};
   EncTc enc_tc{};
   EncTail enc_tail{};
+  int64_t last_h2d_bytes = 0;  // bytes of X the last mrvi_run_host call actually copied host->device
   size_t dist_tc_smem = 0;  // k_dist_gram_tc (128 < S <= 256), 0 = unavailable
   float* h1buf = nullptr;  // [chunk][128] Dense_0 output of the tensor-core encoder GEMM
   // workspace for one chunk of cells
@@ -855,13 +866,23 @@ static int run_host_impl(MrviHandle* h, int64_t n_cells, const float* X, int64_t
       CUDA_TRY(cudaEventCreateWithFlags(&hs.ev_d2h[i], cudaEventDisableTiming));
     }
   }
+  // lossless narrowing of count chunks before the copy (host_pack.cpp): dense input, big enough to matter
+  static const bool pack_disabled = getenv("MRVI_B200_NO_HOST_PACK") != nullptr;
+  static const double pack_min_gbps = getenv("MRVI_B200_PACK_MIN_GBPS") ? atof(getenv("MRVI_B200_PACK_MIN_GBPS")) : 45.0;
+  const bool use_pack = !csr && !pack_disabled && n_cells * (int64_t)G >= (1ll << 22);
+  if (use_pack && !hs.pool) {
+    int nt = (int)std::thread::hardware_concurrency();
+    if (const char* e = getenv("MRVI_B200_PACK_THREADS")) nt = atoi(e);
+    hs.pool.reset(new PackPool(std::max(1, std::min(nt, 32))));
+  }
+  if (use_pack && chunk_cells <= 0) ch = std::min<int64_t>(ch, 8192);  // finer pipeline: narrowing of chunk c+1 overlaps the copy of c
   bool sums_ok = true;
   for (int k = 0; k < n_keys; ++k) sums_ok &= hs.sums_elems[k] >= (size_t)n_groups[k] * S * S;
   int64_t max_nnz = 0;
   if (csr)
     for (int64_t lo = 0; lo < n_cells; lo += ch) max_nnz = std::max(max_nnz, indptr[std::min(n_cells, lo + ch)] - indptr[lo]);
   if (hs.chunk < ch || hs.n_keys < n_keys || (cell_out && !hs.has_cell) || (z_out && !hs.has_z) || (u_out && !hs.has_u) || !sums_ok ||
-      (csr && hs.csr_nnz_cap < max_nnz)) {
+      (csr && hs.csr_nnz_cap < max_nnz) || (use_pack && hs.pack_bytes < (size_t)ch * G * 2)) {
     CUDA_TRY(cudaDeviceSynchronize());
     hs.free_buffers();
     auto A = [&](void** p, size_t bytes) -> cudaError_t {
@@ -871,6 +892,11 @@ static int run_host_impl(MrviHandle* h, int64_t n_cells, const float* X, int64_t
     };
     for (int b = 0; b < 2; ++b) {
       CUDA_TRY(A((void**)&hs.X[b], ch * G * sizeof(float)));
+      if (use_pack) {
+        CUDA_TRY(A((void**)&hs.dpack[b], (size_t)ch * G * 2));
+        CUDA_TRY(cudaHostAlloc((void**)&hs.hpack[b], (size_t)ch * G * 2, cudaHostAllocDefault));
+        hs.pack_bytes = (size_t)ch * G * 2;
+      }
       hs.csr_ptr[b] = nullptr; hs.csr_idx[b] = nullptr; hs.csr_val[b] = nullptr;
       if (csr) {
         CUDA_TRY(A((void**)&hs.csr_ptr[b], (ch + 1) * sizeof(int64_t)));
@@ -896,6 +922,8 @@ static int run_host_impl(MrviHandle* h, int64_t n_cells, const float* X, int64_t
   for (int k = 0; k < n_keys; ++k)
     CUDA_TRY(cudaMemsetAsync(hs.sums[k], 0, (size_t)n_groups[k] * S * S * sizeof(double), hs.s_comp));
   h->ev_used = 0;
+  h->last_h2d_bytes = 0;
+  int pack_mode[2] = {0, 0};
   CUDA_TRY(cudaEventRecord(h->ev_call[0], hs.s_comp));
   int64_t c = 0;
   for (int64_t lo = 0; lo < n_cells; lo += ch, ++c) {
@@ -906,13 +934,34 @@ static int run_host_impl(MrviHandle* h, int64_t n_cells, const float* X, int64_t
     if (csr) {
       const int64_t nz0 = indptr[lo], nnz = indptr[lo + m] - nz0;
       CUDA_TRY(cudaMemcpyAsync(hs.csr_ptr[b], indptr + lo, (m + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, hs.s_h2d));
+      h->last_h2d_bytes += (m + 1) * 8 + nnz * 8;
       if (nnz > 0) {
         CUDA_TRY(cudaMemcpyAsync(hs.csr_idx[b], indices + nz0, nnz * sizeof(int32_t), cudaMemcpyHostToDevice, hs.s_h2d));
         CUDA_TRY(cudaMemcpyAsync(hs.csr_val[b], data + nz0, nnz * sizeof(float), cudaMemcpyHostToDevice, hs.s_h2d));
       }
     } else {
-      CUDA_TRY(cudaMemcpy2DAsync(hs.X[b], (size_t)G * sizeof(float), X + lo * ldx, (size_t)ldx * sizeof(float),
-                                 (size_t)G * sizeof(float), (size_t)m, cudaMemcpyHostToDevice, hs.s_h2d));
+      int narrow = 0;
+      // The narrowing pays only if the host reads X faster than PCIe would carry it raw (~47 GB/s measured): keep it
+      // while the measured rate stays above the threshold.  (Mixing narrowed and raw chunks to keep both the host
+      // threads and the copy engine busy was measured SLOWER: DMA reads and the packer share the host memory bus.)
+      const bool want_pack = use_pack && (hs.pack_rate_gbps == 0.0 || hs.pack_rate_gbps >= pack_min_gbps);
+      if (want_pack) {
+        if (c >= 2) CUDA_TRY(cudaEventSynchronize(hs.ev_h2d[b]));  // the copy of chunk c-2 has left the pinned staging buffer
+        const auto t0 = std::chrono::steady_clock::now();
+        narrow = narrow_counts(*hs.pool, X + lo * ldx, ldx, m, G, hs.hpack[b]);
+        const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        const double gbps = (double)m * G * 4 / std::max(sec, 1e-9) * 1e-9;
+        if (m * (int64_t)G >= (1ll << 22)) hs.pack_rate_gbps = hs.pack_rate_gbps == 0.0 ? gbps : 0.7 * hs.pack_rate_gbps + 0.3 * gbps;
+      }
+      pack_mode[b] = narrow;
+      if (narrow) {
+        CUDA_TRY(cudaMemcpyAsync(hs.dpack[b], hs.hpack[b], (size_t)m * G * narrow, cudaMemcpyHostToDevice, hs.s_h2d));
+        h->last_h2d_bytes += (int64_t)m * G * narrow;
+      } else {
+        CUDA_TRY(cudaMemcpy2DAsync(hs.X[b], (size_t)G * sizeof(float), X + lo * ldx, (size_t)ldx * sizeof(float),
+                                   (size_t)G * sizeof(float), (size_t)m, cudaMemcpyHostToDevice, hs.s_h2d));
+        h->last_h2d_bytes += (int64_t)m * G * 4;
+      }
     }
     CUDA_TRY(cudaMemcpyAsync(hs.sid[b], sample_idx + lo, m * sizeof(int32_t), cudaMemcpyHostToDevice, hs.s_h2d));
     for (int k = 0; k < n_keys; ++k)
@@ -921,6 +970,13 @@ static int run_host_impl(MrviHandle* h, int64_t n_cells, const float* X, int64_t
     // compute (wait for inputs, and for the D2H of chunk c-2 to release output buffers b)
     CUDA_TRY(cudaStreamWaitEvent(hs.s_comp, hs.ev_h2d[b], 0));
     if (c >= 2) CUDA_TRY(cudaStreamWaitEvent(hs.s_comp, hs.ev_d2h[b], 0));
+    if (!csr && pack_mode[b]) {  // widen the narrowed counts back to float32
+      const int64_t ne = m * (int64_t)G;
+      const unsigned blocks = (unsigned)((ne + 16 * 256 - 1) / (16 * 256));
+      if (pack_mode[b] == 1) k_unpack_counts<uint8_t><<<blocks, 256, 0, hs.s_comp>>>(hs.dpack[b], hs.X[b], ne);
+      else k_unpack_counts<uint16_t><<<blocks, 256, 0, hs.s_comp>>>(reinterpret_cast<const uint16_t*>(hs.dpack[b]), hs.X[b], ne);
+      LAUNCH_CHECK();
+    }
     if (csr) {  // expand the chunk's non-zeros to dense rows on the GPU
       CUDA_TRY(cudaMemsetAsync(hs.X[b], 0, (size_t)m * G * sizeof(float), hs.s_comp));
       k_csr_densify<<<(unsigned)((m + 7) / 8), 256, 0, hs.s_comp>>>(hs.csr_ptr[b], indptr[lo], hs.csr_idx[b], hs.csr_val[b], m, G, hs.X[b]);
@@ -979,6 +1035,14 @@ int mrvi_dbg_dist_read(long long* out, int n) {  // debug builds only (tools/dbg
   return (int)cudaMemcpyFromSymbol(out, mrvi::g_dbg_dist, sizeof(long long) * n);
 }
 #endif
+
+int64_t mrvi_last_h2d_bytes(MrviHandle* h) { return h ? h->last_h2d_bytes : 0; }
+
+int mrvi_narrow_counts(const float* X, int64_t ldx, int64_t n_rows, int32_t n_cols, void* out, int32_t n_threads) {
+  if (!X || !out || n_rows < 0 || n_cols <= 0 || ldx < n_cols) return fail(MRVI_ERR_INVALID_ARG, "mrvi_narrow_counts: bad argument");
+  PackPool pool(std::max(1, (int)n_threads));
+  return narrow_counts(pool, X, ldx, n_rows, n_cols, out);
+}
 
 int mrvi_last_stage_ms(MrviHandle* h, float out_ms[4]) {
   if (!h || !out_ms) return fail(MRVI_ERR_INVALID_ARG, "null argument");

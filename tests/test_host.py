@@ -137,3 +137,28 @@ def test_product_never_imports_oracle():
         if fn.endswith(".py"):
             src = open(os.path.join(pkg, fn)).read()
             assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), fn
+
+
+def test_host_narrowing_of_count_chunks_is_lossless(built_library):
+    """`mrvi_run_host` sends integer count chunks as uint8 / uint16 (host_pack.cpp): exact round trip, and every
+    non-narrowable input is refused (-> sent as float32)."""
+    from mrvi_b200 import _capi
+
+    rng = np.random.default_rng(0)
+    for G in (7, 32, 100, 257):
+        X = rng.integers(0, 256, size=(37, G)).astype(np.float32)
+        mode, out = _capi.narrow_counts(X, n_threads=3)
+        assert mode == 1 and out.dtype == np.uint8 and np.array_equal(out.astype(np.float32), X)
+        X[5, G // 2] = 256.0
+        mode, out = _capi.narrow_counts(X)
+        assert mode == 2 and out.dtype == np.uint16 and np.array_equal(out.astype(np.float32), X)
+        X[6, 0] = 65535.0
+        assert _capi.narrow_counts(X)[0] == 2
+        for bad in (65536.0, -1.0, 0.5, np.nan, np.inf, 3e9, -0.25, 1e-30):
+            Y = X.copy()
+            Y[3, G - 1] = bad
+            assert _capi.narrow_counts(Y)[0] == 0, bad
+            Y = X.copy()
+            Y[0, 0] = bad
+            assert _capi.narrow_counts(Y, n_threads=1)[0] == 0, bad
+    assert _capi.narrow_counts(np.zeros((0, 5), np.float32))[0] == 1
