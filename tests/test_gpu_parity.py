@@ -98,6 +98,36 @@ def test_chunking_and_ragged(built_library):
     h.close()
 
 
+@pytest.mark.parametrize("precision", ["fp32", "tc"])
+def test_host_narrowing_is_bit_transparent(built_library, precision):
+    """Count chunks cross PCIe as uint8 / uint16 (host_pack.cpp) and are widened back on the GPU: the result must be
+    BIT-identical to the float32 route, which a single non-integer value per chunk forces (only the cells that own
+    the changed values may differ)."""
+    dims = mrvi_b200.MrviDims(n_input=1200, n_sample=8)
+    params, h = _model(dims, seed=3, precision=precision)
+    n = 4000                                   # 4.8 M values: above the narrowing threshold
+    X, sid = _inputs(n, 1200, 8, seed=4)
+    a = h.run_host(X, sid, keep_cell=True, chunk_cells=1024)
+    assert h.last_h2d_bytes() == n * 1200      # uint8
+    X16 = X.copy()
+    X16[::7, 5] = 40000.0                      # -> uint16 chunks
+    b = h.run_host(X16, sid, keep_cell=True, chunk_cells=1024)
+    assert h.last_h2d_bytes() == n * 1200 * 2
+    Xf = X.copy()
+    poison = np.arange(0, n, 1024)             # first cell of every chunk: every chunk goes raw
+    Xf[poison, 0] += 0.5
+    c = h.run_host(Xf, sid, keep_cell=True, chunk_cells=1024)
+    assert h.last_h2d_bytes() == n * 1200 * 4
+    keep = np.ones(n, bool)
+    keep[poison] = False
+    assert np.array_equal(a["cell"][keep], c["cell"][keep])
+    Xf16 = X16.copy()
+    Xf16[poison, 0] += 0.5
+    d = h.run_host(Xf16, sid, keep_cell=True, chunk_cells=1024)
+    assert np.array_equal(b["cell"][keep], d["cell"][keep])
+    h.close()
+
+
 def test_drop_in_api_matches_reference_layout(built_library):
     """The reference's own grouped-distance test (`tests/test_model.py:221-241`): shapes, symmetry, both
     outputs in one Dataset -- plus values against the oracle and value_counts() group order."""
