@@ -319,7 +319,7 @@ def main():
         peak_tf = pk["bf16_tflops_sustained"]
         rows = n_per * S
         clk_per_row = chain_ms * 1e-3 * 148 * 1.965e9 / rows if chain_ms > 0 else None
-        roofline = {"bound": "tensor", "kernel": "k_qz_fp32" if precision == "fp32" else ("k_chain_fused_tc" if fused else "k_chain_tc"),
+        roofline = {"bound": "tensor", "kernel": "k_qz_fp32" if precision == "fp32" else ("k_chain_fused_tc" if fused else "k_chain_fused_tc (chain only; distances in k_dist_gram_tc)"),
                     "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                     "frac": (achieved / peak_tf) if achieved else None, "traffic": None,
                     "peak_source": f"MEASURED_PEAKS.json bf16 sustained ({pk['source']})",

@@ -44,6 +44,7 @@ CASES = [
     ("S15_iso", dict(n_input=60, n_sample=15, n_latent=10, n_latent_u=10), 40, 2),
     ("S32", dict(n_input=200, n_sample=32), 50, 4),
     ("S128", dict(n_input=64, n_sample=128), 12, 2),
+    ("S130", dict(n_input=48, n_sample=130, n_latent=12, n_latent_u=6), 9, 2),   # large-S route: chain + k_dist_gram_tc, per-row z_base
 ]
 
 
