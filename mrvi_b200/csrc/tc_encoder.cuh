@@ -14,6 +14,8 @@
 // cost 4-8e-4 normwise on the distances).  Epilogues are thread-per-row (TMEM lane =
 // cell), chunked by 32 columns, fp32.
 #pragma once
+#include <cuda.h>
+
 #include "tc_kernels.cuh"
 
 namespace mrvi {
@@ -148,19 +150,43 @@ __device__ __forceinline__ void enc_ep(uint32_t t_d, uint32_t t_res, int half, i
 constexpr int kEncPStages = 4;
 constexpr int kEncPThreads = 640;
 constexpr size_t kEncPSmem = (size_t)kEncPStages * kEncStageBytes + kEncLayerBytes + 4096 + 1024;
+// TMAX variant (16-byte aligned rows): X is streamed by the copy engine, not by the producers' registers.
+//   raw X ring   kEncRX stages x [128 rows x 128 B]   ONE 2-D tensor copy (cp.async.bulk.tensor, 128 x 32 box of the
+//                                                     [n, G] matrix, out-of-range rows / columns zero-filled) per K block,
+//                                                     issued 4 K blocks ahead: the bytes in flight no longer depend on
+//                                                     how fast the converters run.  (128 per-row bulk copies instead were
+//                                                     measured at ~90 clk per copy per SM: 4x slower than the LDG path.)
+//   W0 ring      kEncRW stages x 16 KiB (hi | lo)
+//   A ring       kEncRA stages x (hi | lo) converted operand
+// The producers become converters: raw stage (shared-memory latency instead of 1.5 us of HBM latency) -> log1p ->
+// (hi, lo) split -> A stage.
+constexpr int kEncRX = 4, kEncRW = 3, kEncRA = 2;
+constexpr int kEncRawBytes = 128 * 128;
+constexpr size_t kEncTSmem = (size_t)kEncRX * kEncRawBytes + (size_t)kEncRW * kEncBBytes + (size_t)kEncRA * 2 * kEncAHalf +
+                             kEncLayerBytes + 4096 + 1024;
 
+template <bool TMAX>
 __global__ void __launch_bounds__(kEncPThreads, 1)
 k_encoder_tc(const float* __restrict__ X, int64_t ldx, const int32_t* __restrict__ sample_idx, int64_t n_cells, int G,
-             EncTc enc, const __grid_constant__ EncTail tail, CellBuf cb, int x_vec_ok) {
+             EncTc enc, const __grid_constant__ EncTail tail, CellBuf cb, int x_vec_ok, const __grid_constant__ CUtensorMap xmap) {
   // no-swizzle UMMA operands and bulk copies need 16-byte alignment only; keeping the plain array (no integer
   // re-alignment) lets the compiler see the shared address space (LDS/STS instead of generic LD/ST)
   extern __shared__ __align__(1024) uint8_t smem_tc[];
   uint8_t* const smem = smem_tc;
-  uint8_t* wbuf = smem + (size_t)kEncPStages * kEncStageBytes;              // tail layer weights (hi | lo)
+  // TMAX layout: [raw X ring | W0 ring | A ring | wbuf | barriers]
+  uint8_t* const rawx = smem;
+  uint8_t* const w0ring = smem + (size_t)kEncRX * kEncRawBytes;
+  uint8_t* const aring = w0ring + (size_t)kEncRW * kEncBBytes;
+  uint8_t* wbuf = TMAX ? aring + (size_t)kEncRA * 2 * kEncAHalf
+                       : smem + (size_t)kEncPStages * kEncStageBytes;       // tail layer weights (hi | lo)
   uint64_t* bars = reinterpret_cast<uint64_t*>(wbuf + kEncLayerBytes);
-  uint64_t* full = bars;                       // [stages] producers (256) + W0 expect_tx (1)
-  uint64_t* empty = full + kEncPStages;        // [stages] tcgen05.commit
-  uint64_t* acc_full = empty + kEncPStages;    // [2] phase-1 accumulator of a tile complete
+  uint64_t* full = bars;                       // [stages] producers (256) + W0 expect_tx (1)   (TMAX: a_full[kEncRA], 256)
+  uint64_t* empty = full + kEncPStages;        // [stages] tcgen05.commit                       (TMAX: a_empty[kEncRA])
+  uint64_t* x_full = empty + kEncPStages;      // TMAX [kEncRX] raw rows landed (1 + tx)
+  uint64_t* x_empty = x_full + kEncRX;         // TMAX [kEncRX] converters have the raw values in registers (256)
+  uint64_t* w_full = x_empty + kEncRX;         // TMAX [kEncRW] W0 block landed (1 + tx)
+  uint64_t* w_empty = w_full + kEncRW;         // TMAX [kEncRW] tcgen05.commit
+  uint64_t* acc_full = w_empty + kEncRW;       // [2] phase-1 accumulator of a tile complete
   uint64_t* acc_free = acc_full + 2;           // [2] accumulator region may be overwritten
   uint64_t* bar_a = acc_free + 2;              // tail: next layer's activation is in TMEM (256 arrivals)
   uint64_t* bar_d = bar_a + 1;                 // tail: layer MMAs complete
@@ -174,7 +200,9 @@ k_encoder_tc(const float* __restrict__ X, int64_t ldx, const int32_t* __restrict
   const int64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
   if (tid == 0) {
-    for (int s = 0; s < kEncPStages; ++s) { mbar_init(full + s, 257); mbar_init(empty + s, 1); }
+    for (int s = 0; s < kEncPStages; ++s) { mbar_init(full + s, TMAX ? 256 : 257); mbar_init(empty + s, 1); }
+    for (int s = 0; s < kEncRX; ++s) { mbar_init(x_full + s, 1); mbar_init(x_empty + s, 256); }
+    for (int s = 0; s < kEncRW; ++s) { mbar_init(w_full + s, 1); mbar_init(w_empty + s, 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(acc_full + b, 1); mbar_init(acc_free + b, 1); }
     mbar_init(bar_a, 256);
     mbar_init(bar_d, 1);
@@ -187,7 +215,48 @@ k_encoder_tc(const float* __restrict__ X, int64_t ldx, const int32_t* __restrict
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < 8) {
+  if (TMAX && warp < 8) {
+    // ------------------------------------------------------------ converters: raw X stage -> (hi, lo) A stage
+    const int rsub = lane >> 2, chunk = lane & 3;
+    const int64_t total = my_tiles * nkb;
+    for (int64_t g = 0; g < total; ++g) {
+      const int sx = (int)(g % kEncRX), sa = (int)(g % kEncRA);
+      mbar_wait(x_full + sx, (uint32_t)((g / kEncRX) & 1));
+      float4 v[4];
+#pragma unroll
+      for (int p = 0; p < 2; ++p) {
+        const int row = warp * 16 + p * 8 + rsub;
+        const float4* src = reinterpret_cast<const float4*>(rawx + (size_t)sx * kEncRawBytes + row * 128 + chunk * 32);
+        v[2 * p] = src[0];
+        v[2 * p + 1] = src[1];
+      }
+      // convert first: the arrival on x_empty below must not be performed before the shared-memory loads above have
+      // returned their data (the copy engine refills the stage as soon as the 256 arrivals are in), and only a use
+      // of the values orders that
+      uint32_t h[2][4], l[2][4];
+#pragma unroll
+      for (int p = 0; p < 2; ++p) {
+        const float4 a = v[2 * p], b = v[2 * p + 1];
+        split2(log1p_fast(a.x), log1p_fast(a.y), h[p][0], l[p][0]);
+        split2(log1p_fast(a.z), log1p_fast(a.w), h[p][1], l[p][1]);
+        split2(log1p_fast(b.x), log1p_fast(b.y), h[p][2], l[p][2]);
+        split2(log1p_fast(b.z), log1p_fast(b.w), h[p][3], l[p][3]);
+      }
+      asm volatile("" ::"r"(h[0][0]), "r"(h[1][0]), "r"(l[0][3]), "r"(l[1][3]), "r"(h[0][2]), "r"(h[1][2]) : "memory");
+      fence_proxy_async();  // generic-proxy reads of the raw stage before the copy engine (async proxy) refills it
+      mbar_arrive(x_empty + sx);
+      if (g >= kEncRA) mbar_wait(empty + sa, (uint32_t)((g / kEncRA - 1) & 1));
+      uint8_t* stage = aring + (size_t)sa * 2 * kEncAHalf;
+#pragma unroll
+      for (int p = 0; p < 2; ++p) {
+        const int row = warp * 16 + p * 8 + rsub;
+        *reinterpret_cast<uint4*>(stage + chunk * kEncALbo + row * 16) = make_uint4(h[p][0], h[p][1], h[p][2], h[p][3]);
+        *reinterpret_cast<uint4*>(stage + kEncAHalf + chunk * kEncALbo + row * 16) = make_uint4(l[p][0], l[p][1], l[p][2], l[p][3]);
+      }
+      fence_proxy_async();
+      mbar_arrive(full + sa);
+    }
+  } else if (warp < 8) {
     // ------------------------------------------------------------ producers: flat loop over (tile, K block)
     const int rsub = lane >> 2, chunk = lane & 3;
     const int64_t total = my_tiles * nkb;
@@ -358,11 +427,14 @@ k_encoder_tc(const float* __restrict__ X, int64_t ldx, const int32_t* __restrict
         const uint32_t t_acc = tmem_base + (uint32_t)(ti & 1) * 128;
         if (ti >= 2) { mbar_wait(acc_free + (ti & 1), (uint32_t)(((ti >> 1) - 1) & 1)); tc_fence_after(); }
         for (int kb = 0; kb < nkb; ++kb, ++g) {
-          const int s = (int)(g % kEncPStages);
-          mbar_wait(full + s, (uint32_t)((g / kEncPStages) & 1));
+          const int s = (int)(g % (TMAX ? kEncRA : kEncPStages));
+          const int sw = (int)(g % kEncRW);
+          mbar_wait(full + s, (uint32_t)((g / (TMAX ? kEncRA : kEncPStages)) & 1));
+          if (TMAX) mbar_wait(w_full + sw, (uint32_t)((g / kEncRW) & 1));
           tc_fence_after();
-          const uint32_t a_h = smem_u32(smem + s * kEncStageBytes), a_l = a_h + kEncAHalf;
-          const uint32_t b_h = a_h + 2 * kEncAHalf, b_l = b_h + 4 * 2048;
+          const uint32_t a_h = TMAX ? smem_u32(aring + (size_t)s * 2 * kEncAHalf) : smem_u32(smem + s * kEncStageBytes);
+          const uint32_t a_l = a_h + kEncAHalf;
+          const uint32_t b_h = TMAX ? smem_u32(w0ring + (size_t)sw * kEncBBytes) : a_h + 2 * kEncAHalf, b_l = b_h + 4 * 2048;
 #pragma unroll
           for (int ks = 0; ks < 2; ++ks) {
             const uint64_t ah = umma_desc(a_h + ks * 2 * kEncALbo, kEncALbo, 128);
@@ -374,6 +446,7 @@ k_encoder_tc(const float* __restrict__ X, int64_t ldx, const int32_t* __restrict
             umma_f16(t_acc, ah, bl, idesc, 1u);
           }
           umma_commit(empty + s);
+          if (TMAX) umma_commit(w_empty + sw);
         }
         umma_commit(acc_full + (ti & 1));
       }
@@ -408,7 +481,33 @@ k_encoder_tc(const float* __restrict__ X, int64_t ldx, const int32_t* __restrict
     }
   } else if (warp == 18) {
     // ------------------------------------------------------------ W0 loader (TMA bulk copies)
-    if (lane == 0) {
+    if (TMAX) {
+      const int64_t total = my_tiles * nkb;
+      if (lane == 0) {
+        // raw X tiles: one tensor copy per K block
+        for (int64_t g = 0; g < total; ++g) {
+          const int64_t ti = g / nkb;
+          const int kb = (int)(g - ti * nkb);
+          const int64_t cell0 = ((int64_t)blockIdx.x + ti * gridDim.x) * 128;
+          const int sx = (int)(g % kEncRX);
+          if (g >= kEncRX) mbar_wait(x_empty + sx, (uint32_t)((g / kEncRX - 1) & 1));
+          mbar_expect_tx(x_full + sx, kEncRawBytes);
+          asm volatile(
+              "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                  smem_u32(rawx + (size_t)sx * kEncRawBytes)),
+              "l"(reinterpret_cast<uint64_t>(&xmap)), "r"(kb * kEncBK), "r"((int)cell0), "r"(smem_u32(x_full + sx))
+              : "memory");
+        }
+      } else if (lane == 16) {
+        for (int64_t g = 0; g < total; ++g) {
+          const int sw = (int)(g % kEncRW);
+          const int kb = (int)(g % nkb);
+          if (g >= kEncRW) mbar_wait(w_empty + sw, (uint32_t)((g / kEncRW - 1) & 1));
+          mbar_expect_tx(w_full + sw, kEncBBytes);
+          bulk_g2s(w0ring + (size_t)sw * kEncBBytes, enc.w0img + (size_t)kb * kEncBBytes, kEncBBytes, w_full + sw);
+        }
+      }
+    } else if (lane == 0) {
       const int64_t total = my_tiles * nkb;
       for (int64_t g = 0; g < total; ++g) {
         const int s = (int)(g % kEncPStages);
@@ -541,13 +640,35 @@ inline int enc_tail_build(EncTail& t, const NetW& net, const tc_detail::PMap& pm
   if ((err = tc_upload(arena, wq.data(), wq.size() * sizeof(float), (const void**)&t.wq))) return err;
   t.Lq = net.Lq; t.L = net.L; t.S = net.S;
   { int dev = 0, sms = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); t.sm_count = sms; }
-  if (cudaFuncSetAttribute(k_encoder_tc, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                           (int)kEncPSmem) != cudaSuccess) {
+  if (cudaFuncSetAttribute(k_encoder_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEncPSmem) != cudaSuccess ||
+      cudaFuncSetAttribute(k_encoder_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEncTSmem) != cudaSuccess) {
     g_tc_error = "cudaFuncSetAttribute(k_encoder_tc) failed";
     return MRVI_ERR_CUDA;
   }
   t.ready = true;
   return 0;
+}
+
+// 2-D tensor map of X [n rows][G columns], row stride ldx floats, box = 32 columns x 128 rows (driver entry point
+// fetched through the runtime: no link-time dependency on libcuda)
+inline bool enc_make_xmap(const float* X, int64_t n, int G, int64_t ldx, CUtensorMap* out) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return reinterpret_cast<EncodeFn>(p);
+  }();
+  if (!fn) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)G, (cuuint64_t)n};
+  const cuuint64_t strides[1] = {(cuuint64_t)ldx * sizeof(float)};
+  const cuuint32_t box[2] = {(cuuint32_t)kEncBK, 128u};
+  const cuuint32_t estr[2] = {1u, 1u};
+  return fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(X), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 inline void enc_full_tc_launch(const EncTc& enc, const EncTail& tail, const float* X, int64_t ldx, const int32_t* sid, int64_t n,
@@ -556,7 +677,14 @@ inline void enc_full_tc_launch(const EncTc& enc, const EncTail& tail, const floa
   const int grid = (int)std::min<int64_t>(n_tiles, tail.sm_count);
   if (grid == 0) return;
   const int vec_ok = ((ldx % 4) == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
-  k_encoder_tc<<<grid, kEncPThreads, kEncPSmem, st>>>(X, ldx, sid, n, G, enc, tail, cb, vec_ok);
+  // rows that are 16-byte aligned with a 16-byte multiple of columns stream through the copy engine
+  static const bool no_tmax = getenv("MRVI_B200_ENCODER_LDG") != nullptr;
+  CUtensorMap xmap;
+  memset(&xmap, 0, sizeof(xmap));
+  if (vec_ok && n < (1ll << 31) && !no_tmax && enc_make_xmap(X, n, G, ldx, &xmap))
+    k_encoder_tc<true><<<grid, kEncPThreads, kEncTSmem, st>>>(X, ldx, sid, n, G, enc, tail, cb, vec_ok, xmap);
+  else
+    k_encoder_tc<false><<<grid, kEncPThreads, kEncPSmem, st>>>(X, ldx, sid, n, G, enc, tail, cb, vec_ok, xmap);
 }
 
 }  // namespace mrvi
