@@ -1030,6 +1030,9 @@ int mrvi_run_sampled_host(MrviHandle* h, int64_t n_cells, const float* X, int64_
                                group_codes, n_groups, norm, normalize, cell_out, group_sums, group_counts, z_out, chunk_cells);
 }
 
+#ifdef MRVI_DBG_ENC
+int mrvi_dbg_enc_read(long long* out, int n) { return (int)cudaMemcpyFromSymbol(out, mrvi::g_dbg_enc, sizeof(long long) * n); }
+#endif
 #ifdef MRVI_DBG_DIST
 int mrvi_dbg_dist_read(long long* out, int n) {  // debug builds only (tools/dbg)
   return (int)cudaMemcpyFromSymbol(out, mrvi::g_dbg_dist, sizeof(long long) * n);

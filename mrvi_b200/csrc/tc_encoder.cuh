@@ -161,6 +161,12 @@ constexpr size_t kEncPSmem = (size_t)kEncPStages * kEncStageBytes + kEncLayerByt
 // The producers become converters: raw stage (shared-memory latency instead of 1.5 us of HBM latency) -> log1p ->
 // (hi, lo) split -> A stage.
 constexpr int kEncRX = 4, kEncRW = 3, kEncRA = 2;
+#ifdef MRVI_DBG_ENC
+__device__ long long g_dbg_enc[64 * 16];  // clock64 timeline of CTA 0, per K block g < 64 (tools/dbg)
+#define ENC_STAMP(gi, slot) do { if (blockIdx.x == 0 && (gi) >= 128 && (gi) < 192) g_dbg_enc[((gi) - 128) * 16 + (slot)] = clock64(); } while (0)
+#else
+#define ENC_STAMP(gi, slot) do { } while (0)
+#endif
 constexpr int kEncRawBytes = 128 * 128;
 constexpr size_t kEncTSmem = (size_t)kEncRX * kEncRawBytes + (size_t)kEncRW * kEncBBytes + (size_t)kEncRA * 2 * kEncAHalf +
                              kEncLayerBytes + 4096 + 1024;
@@ -221,7 +227,9 @@ k_encoder_tc(const float* __restrict__ X, int64_t ldx, const int32_t* __restrict
     const int64_t total = my_tiles * nkb;
     for (int64_t g = 0; g < total; ++g) {
       const int sx = (int)(g % kEncRX), sa = (int)(g % kEncRA);
+      if (tid == 0) ENC_STAMP(g, 0);
       mbar_wait(x_full + sx, (uint32_t)((g / kEncRX) & 1));
+      if (tid == 0) ENC_STAMP(g, 1);
       float4 v[4];
 #pragma unroll
       for (int p = 0; p < 2; ++p) {
@@ -230,22 +238,18 @@ k_encoder_tc(const float* __restrict__ X, int64_t ldx, const int32_t* __restrict
         v[2 * p] = src[0];
         v[2 * p + 1] = src[1];
       }
-      // convert first: the arrival on x_empty below must not be performed before the shared-memory loads above have
-      // returned their data (the copy engine refills the stage as soon as the 256 arrivals are in), and only a use
-      // of the values orders that
       uint32_t h[2][4], l[2][4];
 #pragma unroll
       for (int p = 0; p < 2; ++p) {
         const float4 a = v[2 * p], b = v[2 * p + 1];
-        split2(log1p_fast(a.x), log1p_fast(a.y), h[p][0], l[p][0]);
-        split2(log1p_fast(a.z), log1p_fast(a.w), h[p][1], l[p][1]);
-        split2(log1p_fast(b.x), log1p_fast(b.y), h[p][2], l[p][2]);
-        split2(log1p_fast(b.z), log1p_fast(b.w), h[p][3], l[p][3]);
+        split2v(log1p_fast2(make_float2(a.x, a.y)), h[p][0], l[p][0]);
+        split2v(log1p_fast2(make_float2(a.z, a.w)), h[p][1], l[p][1]);
+        split2v(log1p_fast2(make_float2(b.x, b.y)), h[p][2], l[p][2]);
+        split2v(log1p_fast2(make_float2(b.z, b.w)), h[p][3], l[p][3]);
       }
-      asm volatile("" ::"r"(h[0][0]), "r"(h[1][0]), "r"(l[0][3]), "r"(l[1][3]), "r"(h[0][2]), "r"(h[1][2]) : "memory");
-      fence_proxy_async();  // generic-proxy reads of the raw stage before the copy engine (async proxy) refills it
-      mbar_arrive(x_empty + sx);
+      if (tid == 0) ENC_STAMP(g, 2);
       if (g >= kEncRA) mbar_wait(empty + sa, (uint32_t)((g / kEncRA - 1) & 1));
+      if (tid == 0) ENC_STAMP(g, 4);
       uint8_t* stage = aring + (size_t)sa * 2 * kEncAHalf;
 #pragma unroll
       for (int p = 0; p < 2; ++p) {
@@ -253,8 +257,13 @@ k_encoder_tc(const float* __restrict__ X, int64_t ldx, const int32_t* __restrict
         *reinterpret_cast<uint4*>(stage + chunk * kEncALbo + row * 16) = make_uint4(h[p][0], h[p][1], h[p][2], h[p][3]);
         *reinterpret_cast<uint4*>(stage + kEncAHalf + chunk * kEncALbo + row * 16) = make_uint4(l[p][0], l[p][1], l[p][2], l[p][3]);
       }
+      // ONE proxy fence serves both directions: the stores above become visible to the MMAs (async proxy), and the
+      // shared-memory loads of the raw stage (their values were consumed by the stores) are ordered before the copy
+      // engine refills it.  Without it the refill raced the reads: a few rows per launch came out wrong.
       fence_proxy_async();
       mbar_arrive(full + sa);
+      mbar_arrive(x_empty + sx);
+      if (tid == 0) ENC_STAMP(g, 5);
     }
   } else if (warp < 8) {
     // ------------------------------------------------------------ producers: flat loop over (tile, K block)
@@ -430,8 +439,10 @@ k_encoder_tc(const float* __restrict__ X, int64_t ldx, const int32_t* __restrict
           const int s = (int)(g % (TMAX ? kEncRA : kEncPStages));
           const int sw = (int)(g % kEncRW);
           mbar_wait(full + s, (uint32_t)((g / (TMAX ? kEncRA : kEncPStages)) & 1));
+          ENC_STAMP(g, 6);
           if (TMAX) mbar_wait(w_full + sw, (uint32_t)((g / kEncRW) & 1));
           tc_fence_after();
+          ENC_STAMP(g, 7);
           const uint32_t a_h = TMAX ? smem_u32(aring + (size_t)s * 2 * kEncAHalf) : smem_u32(smem + s * kEncStageBytes);
           const uint32_t a_l = a_h + kEncAHalf;
           const uint32_t b_h = TMAX ? smem_u32(w0ring + (size_t)sw * kEncBBytes) : a_h + 2 * kEncAHalf, b_l = b_h + 4 * 2048;
@@ -447,6 +458,7 @@ k_encoder_tc(const float* __restrict__ X, int64_t ldx, const int32_t* __restrict
           }
           umma_commit(empty + s);
           if (TMAX) umma_commit(w_empty + sw);
+          ENC_STAMP(g, 8);
         }
         umma_commit(acc_full + (ti & 1));
       }
@@ -490,7 +502,9 @@ k_encoder_tc(const float* __restrict__ X, int64_t ldx, const int32_t* __restrict
           const int kb = (int)(g - ti * nkb);
           const int64_t cell0 = ((int64_t)blockIdx.x + ti * gridDim.x) * 128;
           const int sx = (int)(g % kEncRX);
+          ENC_STAMP(g, 9);
           if (g >= kEncRX) mbar_wait(x_empty + sx, (uint32_t)((g / kEncRX - 1) & 1));
+          ENC_STAMP(g, 10);
           mbar_expect_tx(x_full + sx, kEncRawBytes);
           asm volatile(
               "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(

@@ -113,14 +113,6 @@ __device__ __forceinline__ float2 gelu_fast2(float2 x) {
   const float2 hx = __fmul2_rn(x, make_float2(0.5f, 0.5f));
   return __ffma2_rn(hx, t, hx);
 }
-// (hi, lo) f16 split of a pair (see split2): the two remainders come from one FADD2
-__device__ __forceinline__ void split2v(float2 a, uint32_t& hi, uint32_t& lo) {
-  const float2 ah = make_float2(__uint_as_float(__float_as_uint(a.x) & 0xFFFFE000u), __uint_as_float(__float_as_uint(a.y) & 0xFFFFE000u));
-  const float2 r = __fadd2_rn(a, make_float2(-ah.x, -ah.y));
-  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(ah.y), "f"(ah.x));
-  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(r.y), "f"(r.x));
-}
-
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   uint32_t* r = reinterpret_cast<uint32_t*>(v);
   asm volatile(

@@ -780,6 +780,22 @@ __device__ __forceinline__ float log1p_fast(float x) {
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(1.0f + x));
   return y * 0.6931471805599453f;
 }
+// (hi, lo) f16 split of a pair (see split2): the two remainders come from one FADD2
+__device__ __forceinline__ void split2v(float2 a, uint32_t& hi, uint32_t& lo) {
+  const float2 ah = make_float2(__uint_as_float(__float_as_uint(a.x) & 0xFFFFE000u), __uint_as_float(__float_as_uint(a.y) & 0xFFFFE000u));
+  const float2 r = __fadd2_rn(a, make_float2(-ah.x, -ah.y));
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(ah.y), "f"(ah.x));
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(r.y), "f"(r.x));
+}
+
+// log1p of a pair through MUFU.LG2, packed add / multiply
+__device__ __forceinline__ float2 log1p_fast2(float2 x) {
+  const float2 t = __fadd2_rn(x, make_float2(1.0f, 1.0f));
+  float a, b;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(a) : "f"(t.x));
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(b) : "f"(t.y));
+  return __fmul2_rn(make_float2(a, b), make_float2(0.6931471805599453f, 0.6931471805599453f));
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
