@@ -308,11 +308,12 @@ static int build_net(MrviHandle* h, const ParamTable& pt) {
 
 static int setup_workspace(MrviHandle* h) {
   const NetW& n = h->net;
-  // chunk: z buffer <= 2 GiB (of 180 GB), <= 65536 cells, multiple of 128 cells.  Long chunks matter for the
-  // grouped reductions: every CTA flushes its run accumulators at least once per launch
+  // chunk: z buffer <= 2 GiB (of 180 GB), <= 262144 cells, multiple of 128 cells.  Long chunks matter for the
+  // grouped reductions (every CTA flushes its run accumulators at least once per launch) and for the persistent
+  // kernels' tails
   int64_t per_cell = (int64_t)n.S * n.L * sizeof(float);
   int64_t ch = (2048ll << 20) / per_cell;
-  if (ch > 65536) ch = 65536;
+  if (ch > 262144) ch = 262144;
   ch = ch / 128 * 128;
   if (ch < 128) ch = 128;
   h->chunk_cells = ch;
