@@ -113,6 +113,7 @@ __attribute__((target("avx2"))) uint32_t narrow_rows_u8_avx2(const float* X, int
   for (int64_t r = r0; r < r1; ++r) {
     const float* x = X + r * ldx;
     uint8_t* o = out + r * G;
+    const bool stream16 = (reinterpret_cast<uintptr_t>(o) & 15) == 0;
     int k = 0;
     for (; k + 32 <= G; k += 32) {
       const __m256 a0 = _mm256_loadu_ps(x + k), a1 = _mm256_loadu_ps(x + k + 8), a2 = _mm256_loadu_ps(x + k + 16),
@@ -126,7 +127,14 @@ __attribute__((target("avx2"))) uint32_t narrow_rows_u8_avx2(const float* X, int
       vor = _mm256_or_si256(vor, _mm256_or_si256(_mm256_or_si256(i0, i1), _mm256_or_si256(i2, i3)));
       const __m256i p01 = _mm256_packus_epi32(i0, i1), p23 = _mm256_packus_epi32(i2, i3);   // 16-bit, lane interleaved
       const __m256i p = _mm256_permutevar8x32_epi32(_mm256_packus_epi16(p01, p23), fix);      // 8-bit, in order
-      _mm256_storeu_si256(reinterpret_cast<__m256i*>(o + k), p);
+      // the narrowed chunk is only read back by the DMA engine: non-temporal stores skip the read-for-ownership of
+      // the staging buffer (a fifth of the packer's memory traffic)
+      if (stream16) {
+        _mm_stream_si128(reinterpret_cast<__m128i*>(o + k), _mm256_castsi256_si128(p));
+        _mm_stream_si128(reinterpret_cast<__m128i*>(o + k + 16), _mm256_extracti128_si256(p, 1));
+      } else {
+        _mm256_storeu_si256(reinterpret_cast<__m256i*>(o + k), p);
+      }
     }
     if (k < G) {
       for (; k < G; ++k) {
@@ -138,6 +146,7 @@ __attribute__((target("avx2"))) uint32_t narrow_rows_u8_avx2(const float* X, int
       }
     }
   }
+  _mm_sfence();
   alignas(32) uint32_t ors[8];
   _mm256_store_si256(reinterpret_cast<__m256i*>(ors), vor);
   uint32_t o = 0;

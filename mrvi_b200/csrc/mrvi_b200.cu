@@ -873,6 +873,7 @@ static int run_host_impl(MrviHandle* h, int64_t n_cells, const float* X, int64_t
   const bool use_pack = !csr && !pack_disabled && n_cells * (int64_t)G >= (1ll << 22);
   if (use_pack && !hs.pool) {
     int nt = (int)std::thread::hardware_concurrency();
+    if (const char* e = getenv("LOCAL_WORLD_SIZE")) nt /= std::max(1, atoi(e));  // one process per GPU shares the host cores
     if (const char* e = getenv("MRVI_B200_PACK_THREADS")) nt = atoi(e);
     hs.pool.reset(new PackPool(std::max(1, std::min(nt, 32))));
   }
