@@ -346,3 +346,74 @@ def test_sparse_csr_input_equals_dense(built_library, precision):
     assert np.array_equal(np.asarray(out["cell"].values), a["cell"])
     model.close()
     h.close()
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tc"])
+def test_device_entry_points_match_host_path(built_library, precision):
+    """`mrvi_run_device` (device-resident buffers, caller's stream) and `mrvi_distances_device` (stage 3 alone)
+    against `mrvi_run_host` / the oracle."""
+    import torch
+
+    dims = mrvi_b200.MrviDims(n_input=96, n_sample=12)
+    params, h = _model(dims, seed=5, precision=precision)
+    n = 700
+    X, sid = _inputs(n, 96, 12, seed=6)
+    codes = np.random.default_rng(0).integers(-1, 4, size=n).astype(np.int32)
+    ref = h.run_host(X, sid, [codes], [4], keep_cell=True, want_z=True, want_u=True)
+    dev = torch.device("cuda:0")
+    st = torch.cuda.Stream(device=dev)
+    with torch.cuda.stream(st):
+        Xd = torch.from_numpy(np.pad(X, ((0, 0), (0, 4)))).to(dev)        # ldx = 100 > n_input
+        sd, cd = torch.from_numpy(sid).to(dev), torch.from_numpy(codes).to(dev)
+        cell = torch.empty((n, 12, 12), dtype=torch.float32, device=dev)
+        sums = torch.zeros((4, 12, 12), dtype=torch.float64, device=dev)
+        z = torch.empty((n, 12, dims.n_latent), dtype=torch.float32, device=dev)
+        u = torch.empty((n, dims.n_latent_q), dtype=torch.float32, device=dev)
+        h.run_device(n, Xd.data_ptr(), 100, sd.data_ptr(), [cd.data_ptr()], [4], cell_out_ptr=cell.data_ptr(),
+                     group_sum_ptrs=[sums.data_ptr()], z_out_ptr=z.data_ptr(), u_out_ptr=u.data_ptr(), stream=st.cuda_stream)
+        # sums are ADDED into: a second call doubles them
+        h.run_device(n, Xd.data_ptr(), 100, sd.data_ptr(), [cd.data_ptr()], [4], group_sum_ptrs=[sums.data_ptr()],
+                     stream=st.cuda_stream)
+    st.synchronize()
+    assert np.array_equal(u.cpu().numpy(), ref["u"]) and np.array_equal(z.cpu().numpy(), ref["z"])
+    assert np.array_equal(cell.cpu().numpy(), ref["cell"])
+    assert np.allclose(sums.cpu().numpy(), 2 * ref["group_sums"][0], rtol=1e-6, atol=1e-9)
+    # stage 3 alone on given representations, every norm
+    zt = torch.from_numpy(ref["z"]).to(dev)
+    for norm in ("l2", "l1", "linf"):
+        out = torch.empty((n, 12, 12), dtype=torch.float32, device=dev)
+        gs = torch.zeros((4, 12, 12), dtype=torch.float64, device=dev)
+        h.distances_device(n, zt.data_ptr(), [cd.data_ptr()], [4], norm=norm, cell_out_ptr=out.data_ptr(), group_sum_ptrs=[gs.data_ptr()])
+        torch.cuda.synchronize()
+        dref = orc.pairwise_distances(ref["z"].astype(np.float64), norm)
+        assert _relerr(out.cpu().numpy(), dref) < 1e-6
+        gref = np.stack([dref[codes == g].sum(0) for g in range(4)])
+        assert _relerr(gs.cpu().numpy(), gref) < 1e-6
+    h.close()
+
+
+def test_distances_device_large_S_tensor_core(built_library):
+    """`mrvi_distances_device` in tensor-core mode with 128 < S <= 256 runs `k_dist_gram_tc` on caller-provided z."""
+    import torch
+
+    S, L, n = 160, 24, 300
+    dims = mrvi_b200.MrviDims(n_input=32, n_sample=S, n_latent=L)
+    params, h = _model(dims, seed=1, precision="tc")
+    rng = np.random.default_rng(3)
+    z = (rng.standard_normal((n, 1, L)) + 0.2 * rng.standard_normal((n, S, L))).astype(np.float32)  # common offset + spread
+    z[:, 7] = z[:, 3]                                                                                 # duplicate sample
+    codes = rng.integers(0, 6, size=n).astype(np.int32)
+    dev = torch.device("cuda:0")
+    zt, cd = torch.from_numpy(z).to(dev), torch.from_numpy(codes).to(dev)
+    out = torch.empty((n, S, S), dtype=torch.float32, device=dev)
+    gs = torch.zeros((6, S, S), dtype=torch.float64, device=dev)
+    h.distances_device(n, zt.data_ptr(), [cd.data_ptr()], [6], cell_out_ptr=out.data_ptr(), group_sum_ptrs=[gs.data_ptr()])
+    torch.cuda.synchronize()
+    dref = orc.pairwise_distances(z.astype(np.float64))
+    got = out.cpu().numpy()
+    scale = dref.max(axis=(1, 2), keepdims=True)
+    assert (np.abs(got - dref) / scale).max() < 1e-4
+    assert np.all(got[:, 3, 7] == 0) and np.all(np.diagonal(got, axis1=1, axis2=2) == 0)
+    gref = np.stack([dref[codes == g].sum(0) for g in range(6)])
+    assert _relerr(gs.cpu().numpy(), gref) < 1e-4
+    h.close()
