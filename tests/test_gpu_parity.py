@@ -417,3 +417,31 @@ def test_distances_device_large_S_tensor_core(built_library):
     gref = np.stack([dref[codes == g].sum(0) for g in range(6)])
     assert _relerr(gs.cpu().numpy(), gref) < 1e-4
     h.close()
+
+
+def test_tc_kernels_are_run_to_run_deterministic(built_library):
+    """Racecheck substitute (compute-sanitizer is not available on the pool): the warp-specialised kernels must give
+    bit-identical u, z and per-cell distances for identical input, across runs and host chunkings.  (This is the
+    check that caught the missing `fence.proxy.async` between the converters' shared-memory loads and the copy
+    engine's refill of a raw stage in `k_encoder_tc`: a few hundred of 100k cells were wrong per launch.)"""
+    n, G = 30000, 1200                      # several 128-cell tiles per CTA: the encoder's rings wrap many times
+    dims = mrvi_b200.MrviDims(n_input=G, n_sample=8)
+    params, h = _model(dims, seed=3, precision="tc")
+    X, sid = _inputs(n, G, 8, seed=4)
+    ref = h.run_host(X, sid, keep_cell=True, want_u=True, want_z=True)
+    for it in range(6):
+        r = h.run_host(X, sid, keep_cell=True, want_u=True, want_z=True, chunk_cells=[0, 4096, 777][it % 3])
+        assert np.array_equal(r["u"], ref["u"]), f"encoder output differs between runs (iteration {it})"
+        assert np.array_equal(r["z"], ref["z"]) and np.array_equal(r["cell"], ref["cell"])
+    h.close()
+    for S, L in ((128, 30), (256, 50)):
+        dims = mrvi_b200.MrviDims(n_input=64, n_sample=S, n_latent=L)
+        params, h = _model(dims, seed=5, precision="tc")
+        X, sid = _inputs(600, 64, S, seed=6)
+        codes = np.random.default_rng(2).integers(0, 5, size=600).astype(np.int32)
+        ref = h.run_host(X, sid, [codes], [5], keep_cell=True)
+        for it in range(4):
+            r = h.run_host(X, sid, [codes], [5], keep_cell=True, chunk_cells=[0, 250][it % 2])
+            assert np.array_equal(r["cell"], ref["cell"])
+            assert np.allclose(r["group_sums"][0], ref["group_sums"][0], rtol=1e-5, atol=1e-5 * ref["cell"].max())
+        h.close()
