@@ -348,6 +348,14 @@ static int setup_workspace(MrviHandle* h) {
   if (h->enc_smem > 227 * 1024 || h->qz_smem > 227 * 1024)
     return fail(MRVI_ERR_UNSUPPORTED, "hyper-parameters need %zu / %zu bytes of shared memory (> 227 KiB)",
                 h->enc_smem, h->qz_smem);
+  if (n.S * n.S <= 1024) {  // k_dist_small keeps a warp's S x L tile in shared memory: above 48 KiB it needs the opt-in
+    const size_t dsm = (size_t)(kThreads / 32) * n.S * (n.L | 1) * sizeof(float);
+    if (dsm > 48 * 1024) {
+      CUDA_TRY(cudaFuncSetAttribute(k_dist_small<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
+      CUDA_TRY(cudaFuncSetAttribute(k_dist_small<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
+      CUDA_TRY(cudaFuncSetAttribute(k_dist_small<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
+    }
+  }
   CUDA_TRY(cudaFuncSetAttribute(k_encoder_fp32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->enc_smem));
   CUDA_TRY(cudaFuncSetAttribute(k_qz_fp32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->qz_smem));
   return 0;

@@ -106,6 +106,8 @@ def tc_chain_residual(flat, u, fmt_act="f16", fmt_w="f16"):
     A (activation) / B (weight) operands of every GEMM (None = fp32; the kernel's hi/lo split of the
     activations is equivalent to fmt_act=None).  u: (B, Lq) float (the encoder output)."""
     f = fold_weights(flat)
+    if not isinstance(fmt_w, dict):  # per-operand formats: {"B1": ..., "B2t": ..., ...} (design studies)
+        fmt_w = {k: fmt_w for k in ("B1", "B2t", "B2a", "B3", "B4t", "B4a", "B5")}
     p32 = {k: np.asarray(v, dtype=np.float32) for k, v in flat.items()}
     Lq, E, nh = f["Lq"], f["E"], f["nh"]
     B = u.shape[0]
@@ -123,14 +125,14 @@ def tc_chain_residual(flat, u, fmt_act="f16", fmt_w="f16"):
     ones = np.ones((B, S, 1), np.float32)
     m = m * np.float32(1.4426950408889634)
     A1 = _round(np.concatenate([m.reshape(B, S, nh * E), ones], -1), fmt_act)
-    h1 = A1 @ _round(f["B1"], fmt_w)
+    h1 = A1 @ _round(f["B1"], fmt_w["B1"])
     t1 = _ln_gelu(h1, *f["ln"]["ln1"])
-    y2 = _round(t1, fmt_act) @ _round(f["B2t"], fmt_w) + A1 @ _round(f["B2a"], fmt_w)
+    y2 = _round(t1, fmt_act) @ _round(f["B2t"], fmt_w["B2t"]) + A1 @ _round(f["B2a"], fmt_w["B2a"])
     t2 = _ln_gelu(y2, *f["ln"]["ln2"])
     A3 = _round(np.concatenate([t2, np.broadcast_to(u_ln[:, None, :], (B, S, Lq)), ones], -1), fmt_act)
-    h3 = A3 @ _round(f["B3"], fmt_w)
+    h3 = A3 @ _round(f["B3"], fmt_w["B3"])
     t3 = _ln_gelu(h3, *f["ln"]["ln3"])
-    y4 = _round(t3, fmt_act) @ _round(f["B4t"], fmt_w) + A3 @ _round(f["B4a"], fmt_w)
+    y4 = _round(t3, fmt_act) @ _round(f["B4t"], fmt_w["B4t"]) + A3 @ _round(f["B4a"], fmt_w["B4a"])
     t4 = _ln_gelu(y4, *f["ln"]["ln4"])
     A5 = _round(np.concatenate([t4, ones], -1), fmt_act)
-    return A5 @ _round(f["B5"], fmt_w)
+    return A5 @ _round(f["B5"], fmt_w["B5"])

@@ -43,6 +43,7 @@ CASES = [
     ("H64_skip", dict(n_input=50, n_sample=7, encoder_n_hidden=64), 100),
     ("qz_layers2", dict(n_input=50, n_sample=9, qz_n_layers=2), 100),
     ("odd_G", dict(n_input=101, n_sample=3), 65),
+    ("S31_L64_bigtile", dict(n_input=64, n_sample=31, n_latent=64, n_latent_u=5), 69),   # k_dist_small above 48 KiB of smem (found by tools/fuzz_parity.py)
 ]
 
 

@@ -1,0 +1,61 @@
+"""Randomised parity sweep: random hyper-parameters / sizes / group codes, both precision modes, against the float64
+oracle.  Not part of the test suite (runtime); run on a GPU box:  python tools/fuzz_parity.py [n_configs] [seed]"""
+import os, sys
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import mrvi_b200
+from mrvi_b200 import _capi
+from oracle import mrvi_oracle as orc
+
+n_cfg = int(sys.argv[1]) if len(sys.argv) > 1 else 30
+rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 0)
+worst = {"fp32": 0.0, "tc": 0.0}
+fails = 0
+for c in range(n_cfg):
+    S = int(rng.choice([2, 3, 4, 5, 7, 8, 13, 16, 31, 32, 33, 48, 64, 65, 100, 127, 128, 129, 160, 255, 256, 300]))
+    # (LayerNorm over fewer than ~5 latent dimensions is ill-conditioned -- with 2 it is a sign function -- and makes
+    #  float32 vs float64 parity meaningless; the reference's smallest tested n_latent_u is 5)
+    L = int(rng.choice([5, 10, 16, 30, 31, 32, 33, 50, 64]))
+    iso = rng.random() < 0.25
+    Lu = None if iso else int(rng.choice([5, 8, 10, 16]))
+    if Lu == L:
+        Lu = None
+    G = int(rng.choice([8, 31, 32, 33, 100, 101, 256, 1000]))
+    use_map = bool(rng.random() < 0.8)
+    qzl = int(rng.choice([1, 1, 1, 2]))
+    encl = int(rng.choice([1, 2, 2, 3]))
+    n = int(rng.integers(1, max(2, 40000 // (S * S) + 40)))
+    dims = mrvi_b200.MrviDims(n_input=G, n_sample=S, n_latent=L, n_latent_u=Lu, use_map=use_map, qz_n_layers=qzl, encoder_n_layers=encl)
+    flat = mrvi_b200.init_params(dims, seed=int(rng.integers(1 << 30)))
+    X = mrvi_b200.synthetic_counts(n, G, seed=int(rng.integers(1 << 30)))
+    sid = rng.integers(0, S, n).astype(np.int32)
+    ng = int(rng.integers(1, 6))
+    codes = rng.integers(-1, ng, n).astype(np.int32)
+    zref = orc.counterfactual_z(flat, X, sid, dtype=np.float64)
+    dref = orc.pairwise_distances(zref)
+    scale = np.maximum(dref.max(axis=(1, 2), keepdims=True), 1e-30)
+    gref = np.stack([dref[codes == g].sum(0) for g in range(ng)])
+    for prec, tol in (("fp32", 1e-5), ("tc", 1e-3)):
+        try:
+            h = _capi.Handle(dims, flat, device=0, precision=_capi.PRECISION_FP32 if prec == "fp32" else _capi.PRECISION_TC)
+            r = h.run_host(X, sid, [codes], [ng], keep_cell=True, want_z=True, chunk_cells=int(rng.choice([0, 1, 7, 64])))
+            g_only = h.run_host(X, sid, [codes], [ng], keep_cell=False)
+            h.close()
+        except _capi.MrviError as e:
+            print(f"cfg {c} {prec}: S={S} L={L} Lu={Lu} G={G} n={n}: {e}")
+            if e.status != -5:
+                fails += 1
+            continue
+        err = float((np.abs(r["cell"] - dref) / scale).max())
+        errz = float(np.abs(r["z"] - zref).max() / np.abs(zref).max())
+        gs = max(np.abs(gref).max(), 1e-30)
+        errg = float(np.abs(r["group_sums"][0] - gref).max() / gs)
+        errg2 = float(np.abs(g_only["group_sums"][0] - gref).max() / gs)
+        cnt_ok = np.array_equal(r["group_counts"][0], np.bincount(codes[codes >= 0], minlength=ng))
+        worst[prec] = max(worst[prec], err, errg, errg2)
+        ok = err < tol and errz < tol and errg < tol and errg2 < tol and cnt_ok and np.all(np.diagonal(r["cell"], axis1=1, axis2=2) == 0)
+        if not ok:
+            fails += 1
+        print(f"cfg {c:2d} {prec:4s} S={S:3d} L={L:2d} Lu={Lu} G={G:4d} n={n:4d} use_map={int(use_map)} qz={qzl} enc={encl} ng={ng}: "
+              f"cell {err:.1e} z {errz:.1e} group {errg:.1e}/{errg2:.1e} {'ok' if ok else 'FAIL'}", flush=True)
+print("worst normwise error:", worst, "failures:", fails)
