@@ -132,6 +132,7 @@ k_dist_gram_tc(const float* __restrict__ z, int64_t n_cells, int S, int L, float
   const uint32_t t_acc0 = tmem_base + 128 + lane_off + colw;  // + 128 * block
   const uint32_t idesc64 = umma_idesc_f16(64);
   const uint32_t zbytes = (uint32_t)(Kz >> 3) * kDistLbo;     // one of (zh, zl)
+  const int nblk = S > 128 ? 3 : 1;                           // S <= 128: the single block (0,0) (stage 3 alone on given z)
   uint32_t phase = 0;
 
   const int64_t p0 = (int64_t)blockIdx.x * cells_per_cta;
@@ -146,7 +147,7 @@ k_dist_gram_tc(const float* __restrict__ z, int64_t n_cells, int S, int L, float
     uint32_t zz[32];
 #pragma unroll
     for (int q = 0; q < 32; ++q) zz[q] = 0u;
-    for (int b = 0; b < 3; ++b) tmem_st32(t_acc0 + b * 128, zz);
+    for (int b = 0; b < nblk; ++b) tmem_st32(t_acc0 + b * 128, zz);
     tmem_st_wait();
   }
 
@@ -179,7 +180,7 @@ k_dist_gram_tc(const float* __restrict__ z, int64_t n_cells, int S, int L, float
     }
     const bool even = (L & 1) == 0;
 #pragma unroll 2
-    for (int row = rr; row < 256; row += rows_per_pass) {
+    for (int row = rr; row < (nblk == 3 ? 256 : 128); row += rows_per_pass) {
       const bool vrow = row < S;
       const float* zr = stage + (vrow ? row : 0) * L + c * 8;
       uint32_t hw[4], lw[4];
@@ -231,7 +232,7 @@ k_dist_gram_tc(const float* __restrict__ z, int64_t n_cells, int S, int L, float
   // ---- flush this thread's accumulator columns of the three blocks into the float64 group sums
   auto flush = [&](int64_t rep_cell) {
 #pragma unroll 1
-    for (int b = 0; b < 3; ++b) {
+    for (int b = 0; b < nblk; ++b) {
       const int bi = b == 2 ? 1 : 0, bj = b == 0 ? 0 : 1;
       float a[32];
       tmem_ld32(t_acc0 + b * 128, a);
@@ -277,7 +278,7 @@ k_dist_gram_tc(const float* __restrict__ z, int64_t n_cells, int S, int L, float
       for (int64_t p = p0; p < p1; ++p) {
         const int buf = (int)((p - p0) & 1);
 #pragma unroll 1
-        for (int b = 0; b < 3; ++b) {
+        for (int b = 0; b < nblk; ++b) {
           mbar_wait(&bar_free[g_], free_phase); free_phase ^= 1;
           tc_fence_after();
           if (g_ == 0) DBG_STAMP(p - p0, 0 + 2 * b);
@@ -329,7 +330,7 @@ k_dist_gram_tc(const float* __restrict__ z, int64_t n_cells, int S, int L, float
     const uint8_t* zl = zh + zbytes;
     const float* part = reinterpret_cast<const float*>(smem + sm.part[buf]);
 #pragma unroll 1
-    for (int b = 0; b < 3; ++b) {
+    for (int b = 0; b < nblk; ++b) {
       const int bi = b == 2 ? 1 : 0, bj = b == 0 ? 0 : 1;
       if (tid == 0) DBG_STAMP(p - p0, 11 + 3 * b);
       mbar_wait(&bar_mma[wg], phase); phase ^= 1;
@@ -432,7 +433,9 @@ k_dist_gram_tc(const float* __restrict__ z, int64_t n_cells, int S, int L, float
   if (tid < 32) tmem_dealloc(tmem_base, 512);
 }
 
-inline bool dist_tc_supported(int S, int L, int norm) { return norm == MRVI_NORM_L2 && S > 128 && S <= 256 && L <= 64; }
+// 128 < S <= 256: the large-S route of the path.  32 < S <= 128: only reached through mrvi_distances_device (stage 3
+// alone on caller-provided z; the path itself runs the fused kernel there), one cell per iteration in block (0,0).
+inline bool dist_tc_supported(int S, int L, int norm) { return norm == MRVI_NORM_L2 && S > 32 && S <= 256 && L <= 64; }
 
 inline int dist_tc_prepare(int L, int S, size_t* smem_bytes) {
   const size_t bytes = dist_tc_smem(L, S).total;

@@ -393,11 +393,12 @@ def test_device_entry_points_match_host_path(built_library, precision):
     h.close()
 
 
-def test_distances_device_large_S_tensor_core(built_library):
-    """`mrvi_distances_device` in tensor-core mode with 128 < S <= 256 runs `k_dist_gram_tc` on caller-provided z."""
+@pytest.mark.parametrize("S,L,n", [(160, 24, 300), (128, 30, 400), (100, 50, 333), (33, 10, 500)])
+def test_distances_device_large_S_tensor_core(built_library, S, L, n):
+    """`mrvi_distances_device` in tensor-core mode with 32 < S <= 256 runs `k_dist_gram_tc` on caller-provided z
+    (three symmetric blocks above 128 samples, one block below)."""
     import torch
 
-    S, L, n = 160, 24, 300
     dims = mrvi_b200.MrviDims(n_input=32, n_sample=S, n_latent=L)
     params, h = _model(dims, seed=1, precision="tc")
     rng = np.random.default_rng(3)
