@@ -171,6 +171,19 @@ int mrvi_run_sampled_host(MrviHandle* h, int64_t n_cells, const float* X, int64_
                           int64_t* const* group_counts, float* z_out, int64_t chunk_cells);
 
 /*
+ * mrvi_run_host for a dense count matrix that is ALREADY stored as small unsigned integers (raw counts kept as
+ * uint8 / uint16 in adata.X or a layer): X [n_cells, ldx] elements of x_dtype, ldx >= n_input in ELEMENTS.  The
+ * matrix crosses PCIe as it is (1 or 2 bytes per value, no host pass) and is widened to float32 on the GPU, i.e. the
+ * result is identical to mrvi_run_host on X.astype(float32) -- what scvi's loader would hand the reference
+ * (src/mrvi/_model.py:317-319, 377-384).  Other arguments as mrvi_run_host.
+ */
+typedef enum MrviXDtype { MRVI_X_UINT8 = 1, MRVI_X_UINT16 = 2 } MrviXDtype;
+int mrvi_run_host_counts(MrviHandle* h, int64_t n_cells, const void* X, int32_t x_dtype, int64_t ldx,
+                         const int32_t* sample_idx, int32_t n_keys, const int32_t* const* group_codes,
+                         const int32_t* n_groups, int32_t norm, float* cell_out, double* const* group_sums,
+                         int64_t* const* group_counts, float* z_out, float* u_out, int64_t chunk_cells);
+
+/*
  * mrvi_run_host narrows dense count chunks losslessly before the host->device copy: a chunk whose float32 values are
  * all integers in [0, 255] ([0, 65535]) crosses PCIe as uint8 (uint16) and is widened back to the identical float32
  * values on the GPU; any other chunk is copied as it is (env MRVI_B200_NO_HOST_PACK=1 disables the narrowing).

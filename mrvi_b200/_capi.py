@@ -30,6 +30,7 @@ EXPORTED_SYMBOLS = (
     "mrvi_run_device",
     "mrvi_run_host",
     "mrvi_run_host_csr",
+    "mrvi_run_host_counts",
     "mrvi_run_sampled_host",
     "mrvi_distances_device",
     "mrvi_last_stage_ms",
@@ -84,6 +85,9 @@ def load_library():
     lib.mrvi_run_host_csr.restype = C.c_int
     lib.mrvi_run_host_csr.argtypes = [vp, i64, vp, vp, vp, vp, i32, C.POINTER(vp), C.POINTER(i32), i32, vp,
                                       C.POINTER(vp), C.POINTER(vp), vp, vp, i64]
+    lib.mrvi_run_host_counts.restype = C.c_int
+    lib.mrvi_run_host_counts.argtypes = [vp, i64, vp, i32, i64, vp, i32, C.POINTER(vp), C.POINTER(i32), i32, vp,
+                                         C.POINTER(vp), C.POINTER(vp), vp, vp, i64]
     lib.mrvi_run_sampled_host.restype = C.c_int
     lib.mrvi_run_sampled_host.argtypes = [vp, i64, vp, i64, vp, i32, C.c_uint64, i64, vp, vp, i32, C.POINTER(vp),
                                           C.POINTER(i32), i32, i32, vp, C.POINTER(vp), C.POINTER(vp), vp, i64]
@@ -210,12 +214,16 @@ class Handle:
                 X.sum_duplicates()
             csr = (np.ascontiguousarray(X.indptr, dtype=np.int64), np.ascontiguousarray(X.indices, dtype=np.int32),
                    np.ascontiguousarray(X.data, dtype=np.float32))
+        elif X.dtype in (np.uint8, np.uint16) and X.ndim == 2:
+            # raw counts stored as small unsigned integers: cross PCIe as they are, widened on the GPU
+            if X.strides[1] != X.itemsize or X.strides[0] % X.itemsize != 0:
+                X = np.ascontiguousarray(X)
         elif X.dtype != np.float32 or X.ndim != 2 or X.strides[1] != 4 or X.strides[0] % 4 != 0:
             X = np.ascontiguousarray(X, dtype=np.float32)
         n = X.shape[0]
         if X.shape[1] != d.n_input:
             raise ValueError(f"X has {X.shape[1]} genes, model expects {d.n_input}")
-        ldx = d.n_input if (csr is not None or n <= 1) else X.strides[0] // 4
+        ldx = d.n_input if (csr is not None or n <= 1) else X.strides[0] // X.itemsize
         sid = np.ascontiguousarray(sample_idx, dtype=np.int32).reshape(-1)
         if sid.shape[0] != n:
             raise ValueError("sample_idx length does not match X")
@@ -240,6 +248,8 @@ class Handle:
                 z.ctypes.data if want_z else None, u.ctypes.data if want_u else None, int(chunk_cells))
         if csr is not None:
             _check(load_library().mrvi_run_host_csr(self._h, n, csr[0].ctypes.data, csr[1].ctypes.data, csr[2].ctypes.data, *tail))
+        elif X.dtype in (np.uint8, np.uint16):
+            _check(load_library().mrvi_run_host_counts(self._h, n, X.ctypes.data, 1 if X.dtype == np.uint8 else 2, ldx, *tail))
         else:
             _check(load_library().mrvi_run_host(self._h, n, X.ctypes.data, ldx, *tail))
         out["group_sums"] = sums

@@ -162,6 +162,8 @@ class MrVI:
         X = adata.X
         if hasattr(X, "tocsr") and not isinstance(X, np.ndarray):
             Xh = X.tocsr() if whole else X.tocsr()[idx]  # stays sparse: densified on the GPU (mrvi_run_host_csr)
+        elif isinstance(X, np.ndarray) and X.dtype in (np.uint8, np.uint16):
+            Xh = X if whole else X[idx]     # raw counts kept as small integers: sent as they are (mrvi_run_host_counts)
         elif whole and isinstance(X, np.ndarray) and X.dtype == np.float32 and X.flags.c_contiguous:
             Xh = X
         elif whole:

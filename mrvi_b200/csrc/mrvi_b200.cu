@@ -77,8 +77,9 @@ struct HostStage {  // device-side staging of mrvi_run_host, cached across calls
   float* X[2] = {nullptr, nullptr};
   uint8_t* dpack[2] = {nullptr, nullptr};     // narrowed counts on the device (host_pack.cpp)
   uint8_t* hpack[2] = {nullptr, nullptr};     // pinned host staging of the narrowed chunk
-  size_t pack_bytes = 0;
+  size_t pack_bytes = 0, dpack_bytes = 0;
   std::unique_ptr<PackPool> pool;
+  bool pack_unavailable = false; // pinned staging could not be allocated
   double pack_rate_gbps = 0.0;   // measured host narrowing rate (float32 bytes consumed per second), smoothed
   int64_t* csr_ptr[2] = {nullptr, nullptr};   // CSR staging (mrvi_run_host_csr)
   int32_t* csr_idx[2] = {nullptr, nullptr};
@@ -99,6 +100,7 @@ struct HostStage {  // device-side staging of mrvi_run_host, cached across calls
     owned.clear();
     for (int i = 0; i < 2; ++i) { if (hpack[i]) cudaFreeHost(hpack[i]); hpack[i] = nullptr; dpack[i] = nullptr; }
     pack_bytes = 0;
+    dpack_bytes = 0;
   }
   ~HostStage() {
     free_buffers();
@@ -834,7 +836,8 @@ int mrvi_distances_device(MrviHandle* h, int64_t n_cells, const float* z, int32_
   return 0;
 }
 
-static int run_host_impl(MrviHandle* h, int64_t n_cells, const float* X, int64_t ldx, const int64_t* indptr,
+// x_elem: bytes per element of a dense X: 4 = float32, 1 / 2 = uint8 / uint16 counts (mrvi_run_host_counts)
+static int run_host_impl(MrviHandle* h, int64_t n_cells, const float* X, int x_elem, int64_t ldx, const int64_t* indptr,
                          const int32_t* indices, const float* data, const int32_t* sample_idx,
                          int32_t n_keys, const int32_t* const* group_codes, const int32_t* n_groups, int32_t norm,
                          float* cell_out, double* const* group_sums, int64_t* const* group_counts, float* z_out,
@@ -878,7 +881,8 @@ static int run_host_impl(MrviHandle* h, int64_t n_cells, const float* X, int64_t
   // lossless narrowing of count chunks before the copy (host_pack.cpp): dense input, big enough to matter
   static const bool pack_disabled = getenv("MRVI_B200_NO_HOST_PACK") != nullptr;
   static const double pack_min_gbps = getenv("MRVI_B200_PACK_MIN_GBPS") ? atof(getenv("MRVI_B200_PACK_MIN_GBPS")) : 45.0;
-  const bool use_pack = !csr && !pack_disabled && n_cells * (int64_t)G >= (1ll << 22);
+  const bool narrow_in = !csr && x_elem < 4;  // the caller's matrix is already uint8 / uint16: copied as it is, widened on the GPU
+  const bool use_pack = !csr && !narrow_in && !pack_disabled && n_cells * (int64_t)G >= (1ll << 22);
   if (use_pack && !hs.pool) {
     int nt = (int)std::thread::hardware_concurrency();
     if (const char* e = getenv("LOCAL_WORLD_SIZE")) nt /= std::max(1, atoi(e));  // one process per GPU shares the host cores
@@ -892,7 +896,8 @@ static int run_host_impl(MrviHandle* h, int64_t n_cells, const float* X, int64_t
   if (csr)
     for (int64_t lo = 0; lo < n_cells; lo += ch) max_nnz = std::max(max_nnz, indptr[std::min(n_cells, lo + ch)] - indptr[lo]);
   if (hs.chunk < ch || hs.n_keys < n_keys || (cell_out && !hs.has_cell) || (z_out && !hs.has_z) || (u_out && !hs.has_u) || !sums_ok ||
-      (csr && hs.csr_nnz_cap < max_nnz) || (use_pack && hs.pack_bytes < (size_t)ch * G * 2)) {
+      (csr && hs.csr_nnz_cap < max_nnz) || (use_pack && !hs.pack_unavailable && hs.pack_bytes < (size_t)ch * G * 2) ||
+      (narrow_in && hs.dpack_bytes < (size_t)ch * G * 2)) {
     CUDA_TRY(cudaDeviceSynchronize());
     hs.free_buffers();
     auto A = [&](void** p, size_t bytes) -> cudaError_t {
@@ -902,10 +907,18 @@ static int run_host_impl(MrviHandle* h, int64_t n_cells, const float* X, int64_t
     };
     for (int b = 0; b < 2; ++b) {
       CUDA_TRY(A((void**)&hs.X[b], ch * G * sizeof(float)));
-      if (use_pack) {
+      if ((use_pack && !hs.pack_unavailable) || narrow_in) {
         CUDA_TRY(A((void**)&hs.dpack[b], (size_t)ch * G * 2));
-        CUDA_TRY(cudaHostAlloc((void**)&hs.hpack[b], (size_t)ch * G * 2, cudaHostAllocDefault));
-        hs.pack_bytes = (size_t)ch * G * 2;
+        hs.dpack_bytes = (size_t)ch * G * 2;
+      }
+      if (use_pack && !hs.pack_unavailable) {
+        if (cudaHostAlloc((void**)&hs.hpack[b], (size_t)ch * G * 2, cudaHostAllocDefault) != cudaSuccess) {
+          cudaGetLastError();          // no pinned memory to spare: the narrowing is an optimisation, not a requirement
+          hs.hpack[b] = nullptr;
+          hs.pack_unavailable = true;
+        } else {
+          hs.pack_bytes = (size_t)ch * G * 2;
+        }
       }
       hs.csr_ptr[b] = nullptr; hs.csr_idx[b] = nullptr; hs.csr_val[b] = nullptr;
       if (csr) {
@@ -949,12 +962,22 @@ static int run_host_impl(MrviHandle* h, int64_t n_cells, const float* X, int64_t
         CUDA_TRY(cudaMemcpyAsync(hs.csr_idx[b], indices + nz0, nnz * sizeof(int32_t), cudaMemcpyHostToDevice, hs.s_h2d));
         CUDA_TRY(cudaMemcpyAsync(hs.csr_val[b], data + nz0, nnz * sizeof(float), cudaMemcpyHostToDevice, hs.s_h2d));
       }
+    } else if (narrow_in) {
+      const uint8_t* Xb = reinterpret_cast<const uint8_t*>(X);
+      if (ldx == G)  // contiguous rows: one linear copy (a pitched copy of 2 KB rows is descriptor-bound)
+        CUDA_TRY(cudaMemcpyAsync(hs.dpack[b], Xb + (size_t)lo * G * x_elem, (size_t)m * G * x_elem, cudaMemcpyHostToDevice, hs.s_h2d));
+      else
+        CUDA_TRY(cudaMemcpy2DAsync(hs.dpack[b], (size_t)G * x_elem, Xb + (size_t)lo * ldx * x_elem, (size_t)ldx * x_elem,
+                                   (size_t)G * x_elem, (size_t)m, cudaMemcpyHostToDevice, hs.s_h2d));
+      pack_mode[b] = x_elem;
+      h->last_h2d_bytes += (int64_t)m * G * x_elem;
     } else {
       int narrow = 0;
       // The narrowing pays only if the host reads X faster than PCIe would carry it raw (~47 GB/s measured): keep it
       // while the measured rate stays above the threshold.  (Mixing narrowed and raw chunks to keep both the host
       // threads and the copy engine busy was measured SLOWER: DMA reads and the packer share the host memory bus.)
-      const bool want_pack = use_pack && (hs.pack_rate_gbps == 0.0 || hs.pack_rate_gbps >= pack_min_gbps);
+      const bool want_pack = use_pack && !hs.pack_unavailable && hs.hpack[b] != nullptr &&
+                             (hs.pack_rate_gbps == 0.0 || hs.pack_rate_gbps >= pack_min_gbps);
       if (want_pack) {
         if (c >= 2) CUDA_TRY(cudaEventSynchronize(hs.ev_h2d[b]));  // the copy of chunk c-2 has left the pinned staging buffer
         const auto t0 = std::chrono::steady_clock::now();
@@ -968,8 +991,11 @@ static int run_host_impl(MrviHandle* h, int64_t n_cells, const float* X, int64_t
         CUDA_TRY(cudaMemcpyAsync(hs.dpack[b], hs.hpack[b], (size_t)m * G * narrow, cudaMemcpyHostToDevice, hs.s_h2d));
         h->last_h2d_bytes += (int64_t)m * G * narrow;
       } else {
-        CUDA_TRY(cudaMemcpy2DAsync(hs.X[b], (size_t)G * sizeof(float), X + lo * ldx, (size_t)ldx * sizeof(float),
-                                   (size_t)G * sizeof(float), (size_t)m, cudaMemcpyHostToDevice, hs.s_h2d));
+        if (ldx == G)
+          CUDA_TRY(cudaMemcpyAsync(hs.X[b], X + lo * ldx, (size_t)m * G * sizeof(float), cudaMemcpyHostToDevice, hs.s_h2d));
+        else
+          CUDA_TRY(cudaMemcpy2DAsync(hs.X[b], (size_t)G * sizeof(float), X + lo * ldx, (size_t)ldx * sizeof(float),
+                                     (size_t)G * sizeof(float), (size_t)m, cudaMemcpyHostToDevice, hs.s_h2d));
         h->last_h2d_bytes += (int64_t)m * G * 4;
       }
     }
@@ -1018,8 +1044,17 @@ int mrvi_run_host(MrviHandle* h, int64_t n_cells, const float* X, int64_t ldx, c
                   int32_t n_keys, const int32_t* const* group_codes, const int32_t* n_groups, int32_t norm,
                   float* cell_out, double* const* group_sums, int64_t* const* group_counts, float* z_out,
                   float* u_out, int64_t chunk_cells) {
-  return run_host_impl(h, n_cells, X, ldx, nullptr, nullptr, nullptr, sample_idx, n_keys, group_codes, n_groups, norm, cell_out,
+  return run_host_impl(h, n_cells, X, 4, ldx, nullptr, nullptr, nullptr, sample_idx, n_keys, group_codes, n_groups, norm, cell_out,
                        group_sums, group_counts, z_out, u_out, chunk_cells);
+}
+
+int mrvi_run_host_counts(MrviHandle* h, int64_t n_cells, const void* X, int32_t x_dtype, int64_t ldx, const int32_t* sample_idx,
+                         int32_t n_keys, const int32_t* const* group_codes, const int32_t* n_groups, int32_t norm,
+                         float* cell_out, double* const* group_sums, int64_t* const* group_counts, float* z_out,
+                         float* u_out, int64_t chunk_cells) {
+  if (x_dtype != MRVI_X_UINT8 && x_dtype != MRVI_X_UINT16) return fail(MRVI_ERR_INVALID_ARG, "x_dtype must be MRVI_X_UINT8 or MRVI_X_UINT16");
+  return run_host_impl(h, n_cells, reinterpret_cast<const float*>(X), x_dtype == MRVI_X_UINT8 ? 1 : 2, ldx, nullptr, nullptr, nullptr,
+                       sample_idx, n_keys, group_codes, n_groups, norm, cell_out, group_sums, group_counts, z_out, u_out, chunk_cells);
 }
 
 int mrvi_run_host_csr(MrviHandle* h, int64_t n_cells, const int64_t* indptr, const int32_t* indices, const float* data,
@@ -1027,7 +1062,7 @@ int mrvi_run_host_csr(MrviHandle* h, int64_t n_cells, const int64_t* indptr, con
                       int32_t norm, float* cell_out, double* const* group_sums, int64_t* const* group_counts, float* z_out,
                       float* u_out, int64_t chunk_cells) {
   if (!indptr) return fail(MRVI_ERR_INVALID_ARG, "indptr is null");
-  return run_host_impl(h, n_cells, nullptr, h ? h->dims.n_input : 0, indptr, indices, data, sample_idx, n_keys, group_codes, n_groups,
+  return run_host_impl(h, n_cells, nullptr, 4, h ? h->dims.n_input : 0, indptr, indices, data, sample_idx, n_keys, group_codes, n_groups,
                        norm, cell_out, group_sums, group_counts, z_out, u_out, chunk_cells);
 }
 

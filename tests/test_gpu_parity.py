@@ -129,6 +129,37 @@ def test_host_narrowing_is_bit_transparent(built_library, precision):
     h.close()
 
 
+@pytest.mark.parametrize("dtype", [np.uint8, np.uint16])
+def test_integer_count_matrix_input(built_library, dtype):
+    """`mrvi_run_host_counts`: adata.X stored as uint8 / uint16 counts gives bit-identical results to its float32 copy
+    (what scvi's loader would hand the reference), with 1 / 2 bytes per value on the wire; strided rows; model API."""
+    dims = mrvi_b200.MrviDims(n_input=300, n_sample=6)
+    params, h = _model(dims, seed=2, precision="tc")
+    X, sid = _inputs(900, 300, 6, seed=3)
+    Xi = X.astype(dtype)
+    if dtype == np.uint16:
+        Xi[::5, 7] = 50000
+    codes = [(np.arange(900) % 3).astype(np.int32)]
+    a = h.run_host(Xi.astype(np.float32), sid, codes, [3], keep_cell=True, want_u=True)
+    b = h.run_host(Xi, sid, codes, [3], keep_cell=True, want_u=True, chunk_cells=256)
+    assert h.last_h2d_bytes() == 900 * 300 * Xi.itemsize
+    assert np.array_equal(a["cell"], b["cell"]) and np.array_equal(a["u"], b["u"])
+    wide = np.zeros((900, 320), dtype=dtype)
+    wide[:, :300] = Xi
+    c = h.run_host(wide[:, :300], sid, codes, [3], keep_cell=True)   # ldx = 320 elements
+    assert np.array_equal(a["cell"], c["cell"])
+    h.close()
+    ad = mrvi_b200.synthetic_iid(n_obs=200, n_vars=300, n_sample=6, seed=1)
+    m32 = mrvi_b200.MrVI(ad, params, sample_key="sample_str", precision="tc")
+    d32 = np.asarray(m32.get_local_sample_distances(keep_cell=True)["cell"].values)
+    m32.close()
+    ad.X = ad.X.astype(dtype)
+    mi = mrvi_b200.MrVI(ad, params, sample_key="sample_str", precision="tc")
+    di = np.asarray(mi.get_local_sample_distances(keep_cell=True)["cell"].values)
+    assert np.array_equal(d32, di)
+    mi.close()
+
+
 def test_drop_in_api_matches_reference_layout(built_library):
     """The reference's own grouped-distance test (`tests/test_model.py:221-241`): shapes, symmetry, both
     outputs in one Dataset -- plus values against the oracle and value_counts() group order."""
