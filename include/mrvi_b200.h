@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define MRVI_B200_ABI_VERSION 2
+#define MRVI_B200_ABI_VERSION 3
 
 typedef struct MrviHandle MrviHandle;
 

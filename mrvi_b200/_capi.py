@@ -12,7 +12,7 @@ import numpy as np
 
 from ._params import MrviDims
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 PRECISION_FP32 = 0
 PRECISION_TC = 1
 NORMS = {"l2": 0, "l1": 1, "linf": 2}
