@@ -43,6 +43,8 @@ struct DistTcSmem {
   uint32_t z[2];      // per buffer: zh | zl, each 256 rows x Kz f16, K-major, LBO = kDistLbo
   uint32_t part[2];   // per buffer: [256] fp32 squared norms of the (hi + lo) operand rows
   uint32_t stage;     // raw fp32 z of the next cell ([S][L], landed by one bulk copy)
+  uint32_t tr;        // store transposition tiles: 16 warps x [32 rows x 16 columns] fp32 (0 bytes when it does not fit)
+  uint32_t tr_bytes;
   uint32_t ctrl;
   uint32_t total;
   int Kz;
@@ -58,6 +60,9 @@ __host__ __device__ inline DistTcSmem dist_tc_smem(int L, int S = 256) {
   m.part[0] = o; o += 2048;
   m.part[1] = o; o += 2048;
   m.stage = o; o += (((uint32_t)S * (uint32_t)L * 4u) + 127u) & ~127u;
+  m.tr = o;
+  m.tr_bytes = (o + 16u * 2048u + 64u <= 227u * 1024u) ? 16u * 2048u : 0u;
+  o += m.tr_bytes;
   m.ctrl = o; o += 64;
   m.total = o;
   return m;
@@ -384,7 +389,29 @@ k_dist_gram_tc(const float* __restrict__ z, int64_t n_cells, int S, int L, float
         }
         if (__any_sync(0xffffffffu, flagged != 0u)) exact_fix_warp<kDistLbo>(g, flagged, zh, zl, i, jbase, L);
       }
-      if (cell_out != nullptr && i < S) {
+      if (cell_out != nullptr && (S & 3) == 0 && sm.tr_bytes != 0) {
+        // rows through a per-warp shared-memory tile so that every store instruction writes full 32-byte sectors:
+        // a thread-per-row float4 store touches 32 rows = 32 half-used sectors.  Two 16-column sub-steps; 16-byte
+        // units are XOR-swizzled with the row so that neither side has bank conflicts.
+        const int lane = tid & 31;
+        float4* T = reinterpret_cast<float4*>(smem + sm.tr + (tid >> 5) * 2048);
+        const int row0 = bi * 128 + warp_q * 32;   // first row of this warp
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            T[lane * 4 + (q ^ ((lane >> 1) & 3))] = make_float4(g[h2 * 16 + 4 * q], g[h2 * 16 + 4 * q + 1], g[h2 * 16 + 4 * q + 2], g[h2 * 16 + 4 * q + 3]);
+          __syncwarp();
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const int rl = it * 8 + (lane >> 2), unit = lane & 3;
+            const int ii = row0 + rl, jj = jbase + h2 * 16 + unit * 4;
+            const float4 v = T[rl * 4 + (unit ^ ((rl >> 1) & 3))];
+            if (ii < S && jj < S) *reinterpret_cast<float4*>(cell_out + ((size_t)cell * S + ii) * S + jj) = v;
+          }
+          __syncwarp();
+        }
+      } else if (cell_out != nullptr && i < S) {
         float* dst = cell_out + ((size_t)cell * S + i) * S + jbase;
         if ((S & 3) == 0) {
 #pragma unroll
@@ -395,6 +422,8 @@ k_dist_gram_tc(const float* __restrict__ z, int64_t n_cells, int S, int L, float
 #pragma unroll
           for (int q = 0; q < 32; ++q) if (jbase + q < S) dst[q] = g[q];
         }
+      }
+      if (cell_out != nullptr && i < S) {
         if (b == 1) {  // block (1,0) = transpose of (0,1): lanes hold consecutive i -> coalesced 128-byte rows
           float* dt = cell_out + (size_t)cell * S * S + i;
 #pragma unroll
