@@ -99,9 +99,12 @@ __device__ __forceinline__ float dist_chunk_fast(float (&g)[32], const float* nr
   return tmin;
 }
 
+// KEEP: per-cell output requested (compiled out of the groupby-only instantiation: its store path costs registers)
+template <bool KEEP>
 __global__ void __launch_bounds__(kDistTcThreads, 1)
-k_dist_gram_tc(const float* __restrict__ z, int64_t n_cells, int S, int L, float* __restrict__ cell_out, GroupPlan gp,
+k_dist_gram_tc(const float* __restrict__ z, int64_t n_cells, int S, int L, float* __restrict__ cell_out_arg, GroupPlan gp,
                int64_t cells_per_cta) {
+  float* const cell_out = KEEP ? cell_out_arg : nullptr;
   extern __shared__ __align__(1024) uint8_t smem_tc[];
   uint8_t* const smem = smem_tc;
   const DistTcSmem sm = dist_tc_smem(L, S);
@@ -469,7 +472,8 @@ inline bool dist_tc_supported(int S, int L, int norm) { return norm == MRVI_NORM
 inline int dist_tc_prepare(int L, int S, size_t* smem_bytes) {
   const size_t bytes = dist_tc_smem(L, S).total;
   if (bytes > 227 * 1024) { *smem_bytes = 0; return 0; }
-  if (cudaFuncSetAttribute(k_dist_gram_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) {
+  if (cudaFuncSetAttribute(k_dist_gram_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess ||
+      cudaFuncSetAttribute(k_dist_gram_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) {
     g_tc_error = "cudaFuncSetAttribute(k_dist_gram_tc) failed";
     return MRVI_ERR_CUDA;
   }
@@ -482,7 +486,10 @@ inline void dist_tc_launch(const float* z, int64_t n, int S, int L, float* cell_
   if (n == 0) return;
   const int grid = (int)std::min<int64_t>(n, sm_count);
   const int64_t cpc = (n + grid - 1) / grid;
-  k_dist_gram_tc<<<(int)((n + cpc - 1) / cpc), kDistTcThreads, smem_bytes, st>>>(z, n, S, L, cell_out, gp, cpc);
+  if (cell_out)
+    k_dist_gram_tc<true><<<(int)((n + cpc - 1) / cpc), kDistTcThreads, smem_bytes, st>>>(z, n, S, L, cell_out, gp, cpc);
+  else
+    k_dist_gram_tc<false><<<(int)((n + cpc - 1) / cpc), kDistTcThreads, smem_bytes, st>>>(z, n, S, L, nullptr, gp, cpc);
 }
 
 }  // namespace mrvi
