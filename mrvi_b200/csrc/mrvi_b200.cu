@@ -80,6 +80,7 @@ struct HostStage {  // device-side staging of mrvi_run_host, cached across calls
   size_t pack_bytes = 0, dpack_bytes = 0;
   std::unique_ptr<PackPool> pool;
   bool pack_unavailable = false; // pinned staging could not be allocated
+  int pack_skipped = 0;          // chunks sent raw since the rate fell below the threshold
   double pack_rate_gbps = 0.0;   // measured host narrowing rate (float32 bytes consumed per second), smoothed
   int64_t* csr_ptr[2] = {nullptr, nullptr};   // CSR staging (mrvi_run_host_csr)
   int32_t* csr_idx[2] = {nullptr, nullptr};
@@ -976,6 +977,10 @@ static int run_host_impl(MrviHandle* h, int64_t n_cells, const float* X, int x_e
       // The narrowing pays only if the host reads X faster than PCIe would carry it raw (~47 GB/s measured): keep it
       // while the measured rate stays above the threshold.  (Mixing narrowed and raw chunks to keep both the host
       // threads and the copy engine busy was measured SLOWER: DMA reads and the packer share the host memory bus.)
+      if (use_pack && hs.pack_rate_gbps != 0.0 && hs.pack_rate_gbps < pack_min_gbps && ++hs.pack_skipped >= 64) {
+        hs.pack_rate_gbps = 0.0;  // the host may have been busy when the rate was measured: probe again now and then
+        hs.pack_skipped = 0;
+      }
       const bool want_pack = use_pack && !hs.pack_unavailable && hs.hpack[b] != nullptr &&
                              (hs.pack_rate_gbps == 0.0 || hs.pack_rate_gbps >= pack_min_gbps);
       if (want_pack) {
