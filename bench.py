@@ -338,9 +338,9 @@ def main():
                     "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                     "frac": (achieved / peak_tf) if achieved else None,
                     # DRAM bytes of the dominant kernel per launch, from the ncu --set full capture of this workload's
-                    # step (profiles/r1_final_tc_fused_c2_ncu_raw.csv: dram__bytes_read 7.702 MB + dram__bytes_write
-                    # 2 KB for a 65536-cell launch = 117.6 B per cell: the per-cell chain inputs; z and D stay on chip)
-                    "traffic": (117.6 * n_per) if (fused and args.workload == "c2" and not keep_cell) else None,
+                    # step (profiles/r1_final_tc_fused_c2_ncu_raw.csv: dram__bytes_read 11.56 MB + dram__bytes_write 0 for
+                    # the 100k-cell launch = 115.6 B per cell: the per-cell chain inputs; z and D stay on chip)
+                    "traffic": (115.6 * n_per) if (fused and args.workload == "c2" and not keep_cell) else None,
                     "peak_source": f"MEASURED_PEAKS.json bf16 sustained ({pk['source']})",
                     "stage_ms_last_step": stage,
                     "algorithmic_flop_per_cell": (fl["chain"] + (fl["dist"] if fused else 0)),
