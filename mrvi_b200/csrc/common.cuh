@@ -14,6 +14,10 @@ constexpr int kMaxKeys = 8;          // groupby keys per call
 constexpr int kMaxE = 32;            // n_latent_sample (outerprod_dim) supported by the kernels
 constexpr int kMaxHeadDim = 8;
 constexpr int kMaxHeads = 8;
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a process-wide, per-device property of a kernel, not of a handle:
+// it is always raised to the device limit, never to a handle-specific size (a second handle with smaller dims
+// must not lower it under the first one's launches)
+constexpr int kMaxSmemOptin = 227 * 1024;
 
 // Row-major packed weight: [Kpad][ld] with Kpad = roundup(K,4), ld = roundup(N,4); zero padding.
 struct DenseW {
@@ -87,6 +91,7 @@ struct GroupPlan {
   double* sums[kMaxKeys];          // [n_groups][S][S]
   const int32_t* order;            // [n] cell index of sorted position i (null when n_keys == 0)
   const int32_t* comp_sorted;      // [n] composite code at sorted position i
+  const int32_t* n_groups;         // [n_keys] device copy of the group counts: codes outside [0, n_groups[k]) never reach the sums
 };
 
 __device__ __forceinline__ float gelu_tanh_f(float v) {

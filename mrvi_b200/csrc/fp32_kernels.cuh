@@ -485,7 +485,7 @@ __device__ __forceinline__ float dist_final(float acc) { return NORM == 0 ? sqrt
 __device__ __forceinline__ void flush_entry(const GroupPlan& gp, int64_t cell, int S, int a, int b, float v) {
   for (int k = 0; k < gp.n_keys; ++k) {
     const int g = gp.codes[k][cell];
-    if (g >= 0) atomicAdd(gp.sums[k] + ((size_t)g * S + a) * S + b, (double)v);
+    if (g >= 0 && g < gp.n_groups[k]) atomicAdd(gp.sums[k] + ((size_t)g * S + a) * S + b, (double)v);
   }
 }
 

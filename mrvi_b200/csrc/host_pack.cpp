@@ -8,7 +8,10 @@
 // runs on a small persistent thread pool and overlaps the copy / kernels of the previous chunk.
 #include "host_pack.h"
 
+#if (defined(__x86_64__) || defined(_M_X64)) && !defined(MRVI_PACK_NO_AVX2)
+#define MRVI_PACK_AVX2 1
 #include <immintrin.h>
+#endif
 
 #include <algorithm>
 #include <condition_variable>
@@ -104,6 +107,7 @@ uint32_t narrow_rows_scalar(const float* X, int64_t ldx, int64_t r0, int64_t r1,
   return (bad ? 1u : 0u) | ((big & limit) ? 2u : 0u);
 }
 
+#ifdef MRVI_PACK_AVX2
 __attribute__((target("avx2"))) uint32_t narrow_rows_u8_avx2(const float* X, int64_t ldx, int64_t r0, int64_t r1, int G,
                                                              uint8_t* out) {
   __m256i vor = _mm256_setzero_si256();
@@ -161,6 +165,12 @@ bool have_avx2() {
   static const bool v = __builtin_cpu_supports("avx2");
   return v;
 }
+#else   // aarch64 hosts (Grace): the scalar path, which the compiler vectorises for the target
+bool have_avx2() { return false; }
+uint32_t narrow_rows_u8_avx2(const float* X, int64_t ldx, int64_t r0, int64_t r1, int G, uint8_t* out) {
+  return narrow_rows_scalar<uint8_t>(X, ldx, r0, r1, G, out);
+}
+#endif
 
 }  // namespace
 

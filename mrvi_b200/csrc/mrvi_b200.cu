@@ -102,6 +102,14 @@ struct HostStage {  // device-side staging of mrvi_run_host, cached across calls
     for (int i = 0; i < 2; ++i) { if (hpack[i]) cudaFreeHost(hpack[i]); hpack[i] = nullptr; dpack[i] = nullptr; }
     pack_bytes = 0;
     dpack_bytes = 0;
+    // nothing below may survive a failed re-allocation: a later call must see "no buffers", never stale pointers
+    chunk = 0; n_keys = 0; has_cell = has_z = has_u = false; csr_nnz_cap = 0;
+    for (int i = 0; i < 2; ++i) {
+      X[i] = nullptr; sid[i] = nullptr; cell[i] = nullptr; z[i] = nullptr; u[i] = nullptr;
+      csr_ptr[i] = nullptr; csr_idx[i] = nullptr; csr_val[i] = nullptr;
+      for (int k = 0; k < kMaxKeys; ++k) codes[i][k] = nullptr;
+    }
+    for (int k = 0; k < kMaxKeys; ++k) { sums[k] = nullptr; sums_elems[k] = 0; }
   }
   ~HostStage() {
     free_buffers();
@@ -351,16 +359,14 @@ static int setup_workspace(MrviHandle* h) {
   if (h->enc_smem > 227 * 1024 || h->qz_smem > 227 * 1024)
     return fail(MRVI_ERR_UNSUPPORTED, "hyper-parameters need %zu / %zu bytes of shared memory (> 227 KiB)",
                 h->enc_smem, h->qz_smem);
-  if (n.S * n.S <= 1024) {  // k_dist_small keeps a warp's S x L tile in shared memory: above 48 KiB it needs the opt-in
-    const size_t dsm = (size_t)(kThreads / 32) * n.S * (n.L | 1) * sizeof(float);
-    if (dsm > 48 * 1024) {
-      CUDA_TRY(cudaFuncSetAttribute(k_dist_small<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
-      CUDA_TRY(cudaFuncSetAttribute(k_dist_small<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
-      CUDA_TRY(cudaFuncSetAttribute(k_dist_small<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm));
-    }
-  }
-  CUDA_TRY(cudaFuncSetAttribute(k_encoder_fp32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->enc_smem));
-  CUDA_TRY(cudaFuncSetAttribute(k_qz_fp32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->qz_smem));
+  // k_dist_small keeps a warp's S x L tile in shared memory: above 48 KiB it needs the opt-in (see kMaxSmemOptin)
+  if ((size_t)(kThreads / 32) * n.S * (n.L | 1) * sizeof(float) > (size_t)kMaxSmemOptin && n.S * n.S <= 1024)
+    return fail(MRVI_ERR_UNSUPPORTED, "n_sample x n_latent tile needs more than 227 KiB of shared memory");
+  CUDA_TRY(cudaFuncSetAttribute(k_dist_small<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemOptin));
+  CUDA_TRY(cudaFuncSetAttribute(k_dist_small<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemOptin));
+  CUDA_TRY(cudaFuncSetAttribute(k_dist_small<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemOptin));
+  CUDA_TRY(cudaFuncSetAttribute(k_encoder_fp32, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemOptin));
+  CUDA_TRY(cudaFuncSetAttribute(k_qz_fp32, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemOptin));
   return 0;
 }
 
@@ -456,6 +462,7 @@ static int plan_groups(MrviHandle* h, int64_t n, int n_keys, const int32_t* cons
   g_launches.fetch_add(2, std::memory_order_relaxed);  // cub: histogram + onesweep (at least)
   gp->order = h->order;
   gp->comp_sorted = h->comp_sorted;
+  gp->n_groups = h->n_groups_dev;
   return 0;
 }
 
@@ -480,6 +487,15 @@ static int validate_run(MrviHandle* h, int64_t n, const void* X, int64_t ldx, co
     if (!codes || !codes[k] || !n_groups || !sums || !sums[k]) return fail(MRVI_ERR_INVALID_ARG, "group key %d: null pointer", k);
     if (n_groups[k] <= 0) return fail(MRVI_ERR_INVALID_ARG, "group key %d: n_groups must be > 0", k);
   }
+  return 0;
+}
+
+// host buffers only: every sample code must index the per-sample tables (the kernels clamp, the ABI rejects)
+static int validate_sample_idx(const MrviHandle* h, const int32_t* sid, int64_t n) {
+  const int S = h->dims.n_sample;
+  for (int64_t i = 0; i < n; ++i)
+    if (sid[i] < 0 || sid[i] >= S)
+      return fail(MRVI_ERR_INVALID_ARG, "sample_idx[%lld] = %d outside [0, %d)", (long long)i, sid[i], S);
   return 0;
 }
 
@@ -563,6 +579,7 @@ static int run_sampled_host_impl(MrviHandle* h, int64_t n_cells, const float* X,
   int err;
   if ((err = validate_run(h, n_cells, X, ldx, sample_idx, n_keys, group_codes, n_groups, norm, group_sums))) return err;
   if (mc <= 0 || mc > 4096) return fail(MRVI_ERR_INVALID_ARG, "mc_samples must be in [1, 4096]");
+  if ((err = validate_sample_idx(h, sample_idx, n_cells))) return err;
   if (normalize && norm != MRVI_NORM_L2) return fail(MRVI_ERR_INVALID_ARG, "Norm must be 'l2' when using normalized distances");
   if (!h->dims.use_map) return fail(MRVI_ERR_UNSUPPORTED, "sampled paths with use_map=False (sampled eps) are not implemented");
   if (h->net.enc_scale.w == nullptr)
@@ -849,6 +866,7 @@ static int run_host_impl(MrviHandle* h, int64_t n_cells, const float* X, int x_e
                           group_codes, n_groups, norm, group_sums))) return err;
   if (csr && n_cells > 0 && (!indices || !data) && indptr[n_cells] > indptr[0])
     return fail(MRVI_ERR_INVALID_ARG, "CSR indices / data is null");
+  if ((err = validate_sample_idx(h, sample_idx, n_cells))) return err;
   CUDA_TRY(cudaSetDevice(h->device));
   const NetW& net = h->net;
   const int S = net.S, L = net.L, G = net.G, Lq = net.Lq;

@@ -250,7 +250,7 @@ k_dist_gram_tc(const float* __restrict__ z, int64_t n_cells, int S, int L, float
 #pragma unroll 1
         for (int k = 0; k < gp.n_keys; ++k) {
           const int g = gp.codes[k][rep_cell];
-          if (g < 0) continue;
+          if (g < 0 || g >= gp.n_groups[k]) continue;
           double* base = gp.sums[k] + (size_t)g * S * S;
 #pragma unroll
           for (int q = 0; q < 32; ++q) {
@@ -472,8 +472,8 @@ inline bool dist_tc_supported(int S, int L, int norm) { return norm == MRVI_NORM
 inline int dist_tc_prepare(int L, int S, size_t* smem_bytes) {
   const size_t bytes = dist_tc_smem(L, S).total;
   if (bytes > 227 * 1024) { *smem_bytes = 0; return 0; }
-  if (cudaFuncSetAttribute(k_dist_gram_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess ||
-      cudaFuncSetAttribute(k_dist_gram_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) {
+  if (cudaFuncSetAttribute(k_dist_gram_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemOptin) != cudaSuccess ||
+      cudaFuncSetAttribute(k_dist_gram_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemOptin) != cudaSuccess) {
     g_tc_error = "cudaFuncSetAttribute(k_dist_gram_tc) failed";
     return MRVI_ERR_CUDA;
   }

@@ -654,8 +654,8 @@ inline int enc_tail_build(EncTail& t, const NetW& net, const tc_detail::PMap& pm
   if ((err = tc_upload(arena, wq.data(), wq.size() * sizeof(float), (const void**)&t.wq))) return err;
   t.Lq = net.Lq; t.L = net.L; t.S = net.S;
   { int dev = 0, sms = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); t.sm_count = sms; }
-  if (cudaFuncSetAttribute(k_encoder_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEncPSmem) != cudaSuccess ||
-      cudaFuncSetAttribute(k_encoder_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kEncTSmem) != cudaSuccess) {
+  if (cudaFuncSetAttribute(k_encoder_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemOptin) != cudaSuccess ||
+      cudaFuncSetAttribute(k_encoder_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemOptin) != cudaSuccess) {
     g_tc_error = "cudaFuncSetAttribute(k_encoder_tc) failed";
     return MRVI_ERR_CUDA;
   }

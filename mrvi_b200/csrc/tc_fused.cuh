@@ -29,11 +29,10 @@ namespace mrvi {
 constexpr int kFusedThreads = 512;
 
 struct FusedSmemMap {
-  uint32_t w;            // weight image
-  uint32_t wg[2];        // per-warpgroup scratch: [a1h a1l a3h a3l] overlaid later by [zf | zh zl]
-  uint32_t off_a1l, off_a3h, off_a3l;   // offsets inside the scratch (a1h at 0)
-  uint32_t off_zf, off_zh, off_zl;      // overlay offsets
-  uint32_t mean[2];      // [32 cells][Kz] fp32
+  uint32_t w;            // weight image (hi | lo)
+  uint32_t wg[2];        // per-warpgroup scratch: [a1h a1l a3h a3l] overlaid later by [zf] (z output only), then [zh zl | T | cref]
+  uint32_t off_a1l, off_a3h, off_a3l;   // offsets inside the scratch (a1h at 0); a1l holds the 4 feature chunks only
+  uint32_t off_zf, off_zh, off_zl, off_T, off_cref;  // overlay offsets
   uint32_t nrm[2];       // [128] fp32
   uint32_t xch[2];       // [2 halves][128] float2: partial row statistics
   uint32_t lnv;          // TcLn copy (640 floats)
@@ -48,23 +47,26 @@ __host__ __device__ inline FusedSmemMap fused_smem_map(uint32_t wimg_bytes, int 
   uint32_t o = 0;
   auto up = [](uint32_t b) { return (b + 1023u) & ~1023u; };
   m.w = o; o += up(wimg_bytes);
-  const uint32_t a1 = up(128 * K1 * 2), a3 = up(128 * K3 * 2);
-  m.off_a1l = a1; m.off_a3h = 2 * a1; m.off_a3l = 2 * a1 + a3;
-  const uint32_t abytes = 2 * a1 + 2 * a3;
+  const uint32_t a1 = up(128 * K1 * 2), a1l = 128 * 32 * 2, a3 = up(128 * K3 * 2);
+  m.off_a1l = a1; m.off_a3h = a1 + a1l; m.off_a3l = a1 + a1l + a3;
+  const uint32_t abytes = a1 + a1l + 2 * a3;
   m.Kz = L <= 32 ? 32 : 64;
   m.zf_ld = m.Kz + 1;
+  // A1 / A3 are dead after GEMM5.  The fp32 z tile (only when z is an output) is copied out before the Gram operands
+  // overwrite it; behind the operands: the keep_cell staging tiles T (8 warps x 2 KB) and the per-cell reference rows
+  // cref [32 cells][Kz] fp32 (sample 0 of each cell, subtracted before the Gram).
   const uint32_t zf = up(128 * m.zf_ld * 4), zk = up(128 * m.Kz * 2);
-  m.off_zf = 0; m.off_zh = zf; m.off_zl = zf + zk;
-  const uint32_t scratch = abytes > zf + 2 * zk ? abytes : zf + 2 * zk;
+  m.off_zf = 0; m.off_zh = 0; m.off_zl = zk; m.off_T = 2 * zk; m.off_cref = 2 * zk + 16384;
+  uint32_t scratch = abytes;
+  if (scratch < zf) scratch = zf;
+  if (scratch < m.off_cref + 32u * m.Kz * 4u) scratch = m.off_cref + 32u * m.Kz * 4u;
   m.wg[0] = o; o += scratch;
   m.wg[1] = o; o += scratch;
-  m.mean[0] = o; o += up(32 * m.Kz * 4);
-  m.mean[1] = o; o += up(32 * m.Kz * 4);
   m.nrm[0] = o; o += 512;
   m.nrm[1] = o; o += 512;
   m.xch[0] = o; o += 2048;
   m.xch[1] = o; o += 2048;
-  m.lnv = o; o += up(sizeof(TcLn));
+  m.lnv = o; o += (uint32_t)((sizeof(TcLn) + 127) & ~size_t(127));
   m.ctrl = o; o += 128;
   m.total = o;
   return m;
@@ -258,15 +260,16 @@ __device__ __forceinline__ void ep32(uint32_t t_lane32, int half, int r, int wg,
   }
 }
 
-// [128 x 128] (A in TMEM, chunked [hi16|lo16] layout) x [128 x N]
-__device__ __forceinline__ void issue_gemm_ts2(uint32_t d_tmem, uint32_t a_tmem, uint32_t b, int N, uint32_t idesc) {
-  const uint32_t b_lbo = (uint32_t)N * 16;
+// [128 x 128] (A in TMEM, chunked [hi16|lo16] layout) x [128 x N], weights (hi, lo): Ah.Wh + Al.Wh + Ah.Wl
+__device__ __forceinline__ void issue_gemm_ts2(uint32_t d_tmem, uint32_t a_tmem, uint32_t s_w, const TcOp& b, uint32_t idesc) {
 #pragma unroll
   for (int ks = 0; ks < 8; ++ks) {
-    const uint64_t bd = umma_desc(b + ks * 2 * b_lbo, b_lbo, 128);
+    const uint64_t bd = umma_desc(s_w + b.h + ks * 2 * b.lbo, b.lbo, 128);
+    const uint64_t bl = umma_desc(s_w + b.l + ks * 2 * b.lbo, b.lbo, 128);
     const uint32_t a = a_tmem + (ks >> 1) * 32 + (ks & 1) * 8;
     umma_f16_ts(d_tmem, a, bd, idesc, ks == 0 ? 0u : 1u);
     umma_f16_ts(d_tmem, a + 16, bd, idesc, 1u);
+    umma_f16_ts(d_tmem, a, bl, idesc, 1u);
   }
 }
 
@@ -283,7 +286,7 @@ __device__ __forceinline__ void flush_acc(uint32_t t_acc_lane, int half, const G
 #pragma unroll 1
       for (int k = 0; k < gp.n_keys; ++k) {
         const int g = gp.codes[k][rep_cell];
-        if (g < 0) continue;
+        if (g < 0 || g >= gp.n_groups[k]) continue;
         double* base = gp.sums[k] + ((size_t)g * S + (r - c0)) * S;
 #pragma unroll
         for (int q = 0; q < 32; ++q) {
@@ -348,7 +351,7 @@ k_chain_fused_tc(const __grid_constant__ TcNet tc, CellBuf cb, int64_t n_cells, 
   float* zf = reinterpret_cast<float*>(scratch + sm.off_zf);
   uint8_t* zh = scratch + sm.off_zh;
   uint8_t* zl = scratch + sm.off_zl;
-  float* mean_s = reinterpret_cast<float*>(smem + sm.mean[wg]);
+  float* cref_s = reinterpret_cast<float*>(scratch + sm.off_cref);
   float* nrm_s = reinterpret_cast<float*>(smem + sm.nrm[wg]);
   float2* xch = reinterpret_cast<float2*>(smem + sm.xch[wg]);
   uint64_t* bar_mma = &ctrl->bar_mma[wg];
@@ -434,19 +437,17 @@ k_chain_fused_tc(const __grid_constant__ TcNet tc, CellBuf cb, int64_t n_cells, 
         *reinterpret_cast<uint32_t*>(row_a1l + off) = lw;
       }
       if (half == 0) {  // constant-one column (k = 32) and zero padding of A1
-        for (int c = 4; c < tc.K1 / 8; ++c) {
+        for (int c = 4; c < tc.K1 / 8; ++c)   // (the lo copy of A1 holds the feature chunks only: issue_gemm K_lo = 32)
           *reinterpret_cast<uint4*>(row_a1h + c * 2048) = make_uint4(c == 4 ? 0x00003C00u : 0u, 0u, 0u, 0u);
-          *reinterpret_cast<uint4*>(row_a1l + c * 2048) = make_uint4(0u, 0u, 0u, 0u);
-        }
-      } else {          // A3 static part: columns 32.. = u_ln[0..Lq), then 1.0, then zeros
+      } else {          // A3 static part: column 32 = 1.0, columns 33.. = u_ln[0..Lq), then zeros
         const float* ul = cb.u_ln + fi * Lq;
         for (int c = 4; c < tc.K3 / 8; ++c) {
           uint32_t hw[4], lw[4];
 #pragma unroll
           for (int j2 = 0; j2 < 4; ++j2) {
-            const int k0 = (c - 4) * 8 + 2 * j2, k1 = k0 + 1;
-            const float a = k0 < Lq ? __ldg(ul + k0) : (k0 == Lq ? 1.0f : 0.f);
-            const float b = k1 < Lq ? __ldg(ul + k1) : (k1 == Lq ? 1.0f : 0.f);
+            const int k0 = (c - 4) * 8 + 2 * j2 - 1, k1 = k0 + 1;   // index into u_ln; -1 = the constant column
+            const float a = k0 < 0 ? 1.0f : (k0 < Lq ? __ldg(ul + k0) : 0.f);
+            const float b = k1 < Lq ? __ldg(ul + k1) : 0.f;
             split2(a, b, hw[j2], lw[j2]);
           }
           *reinterpret_cast<uint4*>(row_a3h + c * 2048) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
@@ -460,7 +461,7 @@ k_chain_fused_tc(const __grid_constant__ TcNet tc, CellBuf cb, int64_t n_cells, 
     // ================= GEMM1 / epilogue 1 =================
     if (issuer) {
       tc_fence_after();
-      issue_gemm(t_r0, s_a1h, s_a1l, s_w + tc.off_b1, tc.K1, 128, idesc128, true);
+      issue_gemm(t_r0, s_a1h, s_a1l, s_w, tc.b1, tc.K1, 32, idesc128, true);
       umma_commit(bar_mma);
     }
     mbar_wait(bar_mma, phase); phase ^= 1;
@@ -471,8 +472,8 @@ k_chain_fused_tc(const __grid_constant__ TcNet tc, CellBuf cb, int64_t n_cells, 
     // ================= GEMM2 / epilogue 2 =================
     if (issuer) {
       tc_fence_after();
-      issue_gemm_ts2(t_d2, t_r0, s_w + tc.off_b2t, 32, idesc32);
-      issue_gemm(t_d2, s_a1h, s_a1l, s_w + tc.off_b2a, tc.K1, 32, idesc32, false);
+      issue_gemm_ts2(t_d2, t_r0, s_w, tc.b2t, idesc32);
+      issue_gemm(t_d2, s_a1h, s_a1l, s_w, tc.b2a, tc.K1, 32, idesc32, false);
       umma_commit(bar_mma);
     }
     mbar_wait(bar_mma, phase); phase ^= 1;
@@ -484,7 +485,7 @@ k_chain_fused_tc(const __grid_constant__ TcNet tc, CellBuf cb, int64_t n_cells, 
     // ================= GEMM3 / epilogue 3 =================
     if (issuer) {
       tc_fence_after();
-      issue_gemm(t_r0, s_a3h, s_a3l, s_w + tc.off_b3, tc.K3, 128, idesc128, true);
+      issue_gemm(t_r0, s_a3h, s_a3l, s_w, tc.b3, tc.K3, tc.K3, idesc128, true);
       umma_commit(bar_mma);
     }
     mbar_wait(bar_mma, phase); phase ^= 1;
@@ -495,8 +496,8 @@ k_chain_fused_tc(const __grid_constant__ TcNet tc, CellBuf cb, int64_t n_cells, 
     // ================= GEMM4 / epilogue 4 =================
     if (issuer) {
       tc_fence_after();
-      issue_gemm_ts2(t_d2, t_r0, s_w + tc.off_b4t, 32, idesc32);
-      issue_gemm(t_d2, s_a3h, s_a3l, s_w + tc.off_b4a, tc.K3, 32, idesc32, false);
+      issue_gemm_ts2(t_d2, t_r0, s_w, tc.b4t, idesc32);
+      issue_gemm(t_d2, s_a3h, s_a3l, s_w, tc.b4a, tc.K3, tc.K3, idesc32, false);
       umma_commit(bar_mma);
     }
     mbar_wait(bar_mma, phase); phase ^= 1;
@@ -509,38 +510,38 @@ k_chain_fused_tc(const __grid_constant__ TcNet tc, CellBuf cb, int64_t n_cells, 
     // ================= GEMM5 / residual rows =================
     if (issuer) {
       tc_fence_after();
-      issue_gemm(t_r0, s_a1h, s_a1l, s_w + tc.off_b5, tc.K5, tc.N5, idescN5, true);
+      issue_gemm(t_r0, s_a1h, s_a1l, s_w, tc.b5, tc.K5, 32, idescN5, true);
       umma_commit(bar_mma);
     }
     mbar_wait(bar_mma, phase); phase ^= 1;
     tc_fence_after();
-    {
-      // this thread's half of the N5 output columns
-      const int ncol = tc.N5 >> 1, col0 = half * ncol;
-      float v[32];
-      if (ncol == 16) tmem_ld16(t_lane + col0, v); else tmem_ld32(t_lane + col0, v);
-      tmem_ld_wait();
-      if (cb.per_row && valid) {
-        const float* zb = cb.zbase + fi * L;
+    // this thread's half of the N5 output columns stays in registers until the Gram operands are built
+    const int ncol = tc.N5 >> 1, col0 = half * ncol;
+    float v[32];
+    if (ncol == 16) tmem_ld16(t_lane + col0, v); else tmem_ld32(t_lane + col0, v);
+    tmem_ld_wait();
 #pragma unroll
-        for (int l = 0; l < 32; ++l)
-          if (l < ncol && col0 + l < L) v[l] += __ldg(zb + col0 + l);
-      }
-      // A1/A3 are dead (GEMM5 done): overlay the fp32 residual tile on them
+    for (int l = 0; l < 32; ++l) v[l] = (l < ncol && col0 + l < L && valid) ? v[l] : 0.f;
+    if (cb.per_row && valid) {
+      const float* zb = cb.zbase + fi * L;
 #pragma unroll
       for (int l = 0; l < 32; ++l)
-        if (l < ncol && col0 + l < Kz) zf[r * zld + col0 + l] = (col0 + l < L && valid) ? v[l] : 0.f;
-      if (z_out != nullptr && half == 0) {  // row -> (output row, z_base row) for the coalesced copy below
-        long long* rowinfo = reinterpret_cast<long long*>(xch);  // xch is free between the epilogues and the centring
-        rowinfo[r] = valid ? (long long)(cell * S + sr) : -1ll;
-        rowinfo[128 + r] = (long long)fi;
-      }
+        if (l < ncol && col0 + l < L) v[l] += __ldg(zb + col0 + l);
     }
     tc_fence_before();
-    wg_sync(wg);
     if (z_out != nullptr) {
-      // z = z_base + residual, written with fully coalesced 4-byte stores: consecutive threads walk the tile
-      // row-major (a thread-per-row store would touch 32 different rows, i.e. 32 sectors, per instruction)
+      // A1/A3 are dead (GEMM5 done): stage the fp32 residual tile on them, then write z = z_base + residual with
+      // fully coalesced 4-byte stores: consecutive threads walk the tile row-major (a thread-per-row store would
+      // touch 32 different rows, i.e. 32 sectors, per instruction)
+#pragma unroll
+      for (int l = 0; l < 32; ++l)
+        if (l < ncol && col0 + l < Kz) zf[r * zld + col0 + l] = v[l];
+      long long* rowinfo_w = reinterpret_cast<long long*>(xch);  // xch is free between the epilogues and the Gram
+      if (half == 0) {  // row -> (output row, z_base row)
+        rowinfo_w[r] = valid ? (long long)(cell * S + sr) : -1ll;
+        rowinfo_w[128 + r] = (long long)fi;
+      }
+      wg_sync(wg);
       const long long* rowinfo = reinterpret_cast<const long long*>(xch);
       const bool add_zb = !cb.per_row;
       int r2 = wt / L, l2 = wt - r2 * L;
@@ -555,64 +556,45 @@ k_chain_fused_tc(const __grid_constant__ TcNet tc, CellBuf cb, int64_t n_cells, 
         r2 += dr; l2 += dl;
         if (l2 >= L) { l2 -= L; ++r2; }
       }
-      wg_sync(wg);  // rowinfo (xch) and zf are reused right away
     }
-    if (!need_dist) continue;
+    if (!need_dist) {
+      wg_sync(wg);  // D5 consumed, zf / rowinfo free before the next tile
+      continue;
+    }
 
-    // ================= centre per cell, norms, (hi, lo) Gram operands =================
-    {
-      // per-cell column means of the residual tile, all 256 threads: nseg threads share one (cell, column)
-      const int O = cells_per_tile * Kz;                 // outputs
-      if (O >= 256) {                                    // small S: one thread per output, few rows each
-        for (int idx = wt; idx < O; idx += 256) {
-          const int cl = idx / Kz, l = idx - cl * Kz;
-          float sum = 0.f;
-          for (int q = 0; q < S; ++q) sum += zf[(cl * S + q) * zld + l];
-          mean_s[idx] = sum / (float)S;
-        }
-        wg_sync(wg);
-      } else {
-        const int nseg = 256 / O;                        // 2, 4 or 8 row segments per output
-        const int o = wt % O, seg = wt / O;
-        const int cl = o / Kz, l = o - cl * Kz;
-        const int per = (S + nseg - 1) / nseg;
-        float sum = 0.f;
-        if (seg < nseg) {
-          const int q1 = min(S, (seg + 1) * per);
-          for (int q = seg * per; q < q1; ++q) sum += zf[(cl * S + q) * zld + l];
-        }
-        float* part = reinterpret_cast<float*>(xch);     // [nseg][O] <= 256 floats (xch is free here)
-        if (seg < nseg) part[seg * O + o] = sum;
-        wg_sync(wg);
-        if (wt < O) {
-          float t = 0.f;
-          for (int k = 0; k < nseg; ++k) t += part[k * O + wt];
-          mean_s[wt] = t / (float)S;
-        }
-        wg_sync(wg);
-      }
+    // ================= reference row per cell, norms, (hi, lo) Gram operands =================
+    // Distances are invariant under a per-cell shift: every row is re-centred on the cell's sample 0 (keeps the
+    // norms, and with them the cancellation in n_i + n_j - 2 g, small; the same choice as k_dist_gram_tc).
+    if (row_in_tile && s == 0) {
+#pragma unroll
+      for (int l = 0; l < 32; ++l)
+        if (l < ncol) cref_s[lc * Kz + col0 + l] = v[l];
     }
+    wg_sync(wg);  // reference rows visible; with z output: every thread is done with zf / rowinfo
     {
-      const float* mrow = mean_s + (row_in_tile ? lc : 0) * Kz;
+      const float* crow = cref_s + (row_in_tile ? lc : 0) * Kz + col0;
       float nrm_p = 0.f;
       const int nch = Kz >> 4;  // K chunks per half
-#pragma unroll 1
-      for (int cc = 0; cc < nch; ++cc) {
-        const int c = half * nch + cc;
-        uint32_t hw[4], lw[4];
 #pragma unroll
-        for (int j2 = 0; j2 < 4; ++j2) {
-          const int k0 = c * 8 + 2 * j2;
-          const float a = zf[r * zld + k0] - mrow[k0];
-          const float b = zf[r * zld + k0 + 1] - mrow[k0 + 1];
-          split2(a, b, hw[j2], lw[j2]);
-          // norms from the values the tensor core sees (hi + lo), so that n_i + n_j - 2 g cancels consistently
-          const float ar = h2f_lo(hw[j2]) + h2f_lo(lw[j2]), br = h2f_hi(hw[j2]) + h2f_hi(lw[j2]);
-          nrm_p = fmaf(ar, ar, nrm_p);
-          nrm_p = fmaf(br, br, nrm_p);
+      for (int cc = 0; cc < 4; ++cc) {
+        if (cc < nch) {
+          const int c = half * nch + cc;
+          uint32_t hw[4], lw[4];
+#pragma unroll
+          for (int j2 = 0; j2 < 4; ++j2) {
+            const int k0 = cc * 8 + 2 * j2;
+            const float2 cr = *reinterpret_cast<const float2*>(crow + k0);
+            const float a = v[k0] - cr.x;
+            const float b = v[k0 + 1] - cr.y;
+            split2(a, b, hw[j2], lw[j2]);
+            // norms from the values the tensor core sees (hi + lo), so that n_i + n_j - 2 g cancels consistently
+            const float ar = h2f_lo(hw[j2]) + h2f_lo(lw[j2]), br = h2f_hi(hw[j2]) + h2f_hi(lw[j2]);
+            nrm_p = fmaf(ar, ar, nrm_p);
+            nrm_p = fmaf(br, br, nrm_p);
+          }
+          *reinterpret_cast<uint4*>(zh + c * 2048 + r * 16) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+          *reinterpret_cast<uint4*>(zl + c * 2048 + r * 16) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
         }
-        *reinterpret_cast<uint4*>(zh + c * 2048 + r * 16) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-        *reinterpret_cast<uint4*>(zl + c * 2048 + r * 16) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
       }
       xch[half * 128 + r].x = nrm_p;
     }
@@ -693,7 +675,7 @@ k_chain_fused_tc(const __grid_constant__ TcNet tc, CellBuf cb, int64_t n_cells, 
         // 16-byte units XOR-swizzled with the row: no bank conflicts on either side.  The rows of a warp may belong
         // to different cells: the destination row and the cell's first column travel by shuffle.
         const int lane = tid & 31;
-        float4* T = reinterpret_cast<float4*>(zf) + (wt >> 5) * 128;
+        float4* T = reinterpret_cast<float4*>(scratch + sm.off_T) + (wt >> 5) * 128;
         const int my_row = valid ? (int)(cell * S + s) : -1;   // < 2^31: cells are indices inside one device chunk
 #pragma unroll
         for (int h2 = 0; h2 < 2; ++h2) {
@@ -733,7 +715,7 @@ k_chain_fused_tc(const __grid_constant__ TcNet tc, CellBuf cb, int64_t n_cells, 
       } else if (gp.n_keys > 0 && valid) {  // mixed tile: straight to the float64 sums
         for (int k = 0; k < gp.n_keys; ++k) {
           const int gk = gp.codes[k][cell];
-          if (gk < 0) continue;
+          if (gk < 0 || gk >= gp.n_groups[k]) continue;
           double* base = gp.sums[k] + ((size_t)gk * S + s) * S;
 #pragma unroll
           for (int q = 0; q < 32; ++q) {
@@ -769,7 +751,7 @@ inline bool tc_fused_supported(const TcNet& tc, int S, int norm) { return tc.rea
 inline int tc_fused_prepare(TcNet& tc, int L) {
   const size_t bytes = fused_smem_map(tc.wimg_bytes, tc.K1, tc.K3, L).total + 1024;
   if (bytes > 227 * 1024) return 0;  // fused path unavailable for this shape; the unfused kernels are used
-  if (cudaFuncSetAttribute(k_chain_fused_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) {
+  if (cudaFuncSetAttribute(k_chain_fused_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemOptin) != cudaSuccess) {
     g_tc_error = "cudaFuncSetAttribute(k_chain_fused_tc) failed";
     return MRVI_ERR_CUDA;
   }

@@ -11,17 +11,18 @@
 //   epi1   T = gelu(LN(D1))                              (fp32, thread-local row statistics)
 //   GEMM2  D2[128x32]  = T x B2t + A1 x B2a              (Dense_2; the skip Dense_1 folded: (a Ws) Wout)
 //   epi2   t2 = gelu(LN(D2))
-//   GEMM3  D3[128x128] = A3[t2 | u_ln | 1]    x B3      (MLP_0 Dense_0(out) and MLP_1 Dense_0 fused)
+//   GEMM3  D3[128x128] = A3[t2 | 1 | u_ln]    x B3      (MLP_0 Dense_0(out) and MLP_1 Dense_0 fused)
 //   epi3   T = gelu(LN(D3))
 //   GEMM4  D4[128x32]  = T x B4t + A3 x B4a
 //   epi4   t4 = gelu(LN(D4))
 //   GEMM5  D5[128xN5]  = A5[t4 | 1]           x B5      (MLP_1 final Dense, first L outputs)
 //
-// Every A operand is written as an (hi, lo) pair of f16 values (hi = 11 leading bits, lo = the
-// remainder) and multiplied against the same f16 weights twice, which keeps the activation
-// rounding at 2^-21; weights are rounded to f16 once (systematic 3e-4 normwise effect on the
-// distances, measured in oracle/tc_emulation.py).  All folding of weights is done in float64 on the
-// host at create time (tc_build).
+// Every operand is an (hi, lo) pair of f16 values (hi = 11 leading bits, lo = the remainder) and every
+// product is the 3-term split  Ah.Wh + Al.Wh + Ah.Wl  (fp32 accumulate), i.e. ~21 significant bits on
+// both sides.  Round 1 rounded the weights to f16 once: a systematic 3-5e-4 normwise effect on the
+// distances with a tail above the 1e-3 bar (6 of 120 random configurations); with the lo weight image
+// the emulation (oracle/tc_emulation.py) and the measured error drop to the 1e-5 level.  All folding of
+// weights is done in float64 on the host at create time (tc_build).
 //
 // Operands use the canonical no-swizzle K-major UMMA layout: 16-byte chunk kc of row r of an
 // [R x K] operand lives at  base + kc * (R * 16) + r * 16  (LBO = R*16 bytes between K chunks,
@@ -51,13 +52,22 @@ struct TcLn {
   float g4[32], b4[32];    // MLP_1 ResnetBlock LayerNorm_1
 };
 
+// One B operand of the chain inside the weight image: byte offsets of its hi / lo f16 copies and the byte stride
+// between 16-byte K chunks (canonical K-major layout).  The 32-wide operands are stored CONCATENATED along N,
+// [W_hi | W_lo] (64 rows per K chunk, lbo = 1024, lo = hi + 512): one N = 64 MMA then forms A.W_hi and A.W_lo side by
+// side (tcgen05.mma costs ~42 clk per instruction for N <= 64, tools/mma_microbench.cu), while N = 32 descriptors on
+// `h` / `l` still address the two copies separately.
+struct TcOp {
+  uint32_t h = 0, l = 0, lbo = 0;
+};
+
 struct TcNet {
   const float* kvtok = nullptr;   // [S][16] per-sample kv tokens (fp32)
   const float* kvl = nullptr;     // [S][16] kv * log2(e)
   const float* kvref = nullptr;   // [S][2]  (max_j kv, min_j kv) * log2(e)
   const uint8_t* wimg = nullptr;  // packed f16 operand image (device), copied verbatim to smem
   uint32_t wimg_bytes = 0;
-  uint32_t off_b1 = 0, off_b2t = 0, off_b2a = 0, off_b3 = 0, off_b4t = 0, off_b4a = 0, off_b5 = 0;
+  TcOp b1, b2t, b2a, b3, b4t, b4a, b5;  // operands inside the image
   int K1 = 48, K3 = 48, K5 = 48, N5 = 32;
   float alpha[2] = {0, 0}, beta[2] = {0, 0};  // t[h,i] = alpha[h] * q_tok[i] + beta[h]
   TcLn ln;
@@ -294,25 +304,31 @@ __device__ __forceinline__ void ln_gelu_store_tmem(float (&v)[128], const float*
   tmem_st_wait();
 }
 
-// [128 x 128] (A in TMEM: hi at a_tmem, lo at a_tmem + 64 columns) x [128 x N]
-__device__ __forceinline__ void issue_gemm_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t b, int N, uint32_t idesc) {
-  const uint32_t b_lbo = (uint32_t)N * 16;
+// [128 x 128] (A in TMEM: hi at a_tmem, lo at a_tmem + 64 columns) x [128 x N], weights (hi, lo): Ah.Wh + Al.Wh + Ah.Wl
+__device__ __forceinline__ void issue_gemm_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t s_w, const TcOp& b, uint32_t idesc) {
 #pragma unroll
   for (int ks = 0; ks < 8; ++ks) {
-    const uint64_t bd = umma_desc(b + ks * 2 * b_lbo, b_lbo, 128);
+    const uint64_t bd = umma_desc(s_w + b.h + ks * 2 * b.lbo, b.lbo, 128);
+    const uint64_t bl = umma_desc(s_w + b.l + ks * 2 * b.lbo, b.lbo, 128);
     umma_f16_ts(d_tmem, a_tmem + ks * 8, bd, idesc, ks == 0 ? 0u : 1u);
     umma_f16_ts(d_tmem, a_tmem + 64 + ks * 8, bd, idesc, 1u);
+    umma_f16_ts(d_tmem, a_tmem + ks * 8, bl, idesc, 1u);
   }
 }
 
-// issue the MMAs of one [128 x K] x [K x N] product for both the hi and lo copy of A
-__device__ __forceinline__ void issue_gemm(uint32_t d_tmem, uint32_t a_h, uint32_t a_l, uint32_t b, int K, int N,
+// issue the MMAs of one [128 x K] x [K x N] product: (hi, lo) activations against (hi, lo) weights, 3 terms per K slice.
+// K_lo: K extent of the lo copy of A (A1 / A5 = [features | 1 | 0...]: the lo halves of the constant column and of the
+// padding are zero, so their last K slice is skipped and not even stored).
+__device__ __forceinline__ void issue_gemm(uint32_t d_tmem, uint32_t a_h, uint32_t a_l, uint32_t s_w, const TcOp& b, int K, int K_lo,
                                            uint32_t idesc, bool first_clears) {
-  const uint32_t a_lbo = 128 * 16, b_lbo = (uint32_t)N * 16;
+  const uint32_t a_lbo = 128 * 16;
   for (int ks = 0; ks < K / 16; ++ks) {
-    const uint64_t bd = umma_desc(b + ks * 2 * b_lbo, b_lbo, 128);
-    umma_f16(d_tmem, umma_desc(a_h + ks * 2 * a_lbo, a_lbo, 128), bd, idesc, (first_clears && ks == 0) ? 0u : 1u);
-    umma_f16(d_tmem, umma_desc(a_l + ks * 2 * a_lbo, a_lbo, 128), bd, idesc, 1u);
+    const uint64_t bd = umma_desc(s_w + b.h + ks * 2 * b.lbo, b.lbo, 128);
+    const uint64_t bl = umma_desc(s_w + b.l + ks * 2 * b.lbo, b.lbo, 128);
+    const uint64_t ah = umma_desc(a_h + ks * 2 * a_lbo, a_lbo, 128);
+    umma_f16(d_tmem, ah, bd, idesc, (first_clears && ks == 0) ? 0u : 1u);
+    if (ks * 16 < K_lo) umma_f16(d_tmem, umma_desc(a_l + ks * 2 * a_lbo, a_lbo, 128), bd, idesc, 1u);
+    umma_f16(d_tmem, ah, bl, idesc, 1u);
   }
 }
 
@@ -428,15 +444,15 @@ k_chain_tc(const __grid_constant__ TcNet tc, CellBuf cb, int64_t n_cells, int S,
         *reinterpret_cast<uint4*>(row_a1h + c * 2048) = make_uint4(c == 4 ? one_h : 0u, 0u, 0u, 0u);
         *reinterpret_cast<uint4*>(row_a1l + c * 2048) = make_uint4(0u, 0u, 0u, 0u);
       }
-      // A3 static part: columns 32.. = u_ln[0..Lq), then 1.0, then zeros
+      // A3 static part: column 32 = 1.0, columns 33.. = u_ln[0..Lq), then zeros
       const float* ul = cb.u_ln + cc * Lq;
       for (int c = 4; c < tc.K3 / 8; ++c) {
         uint32_t hw[4], lw[4];
 #pragma unroll
         for (int j2 = 0; j2 < 4; ++j2) {
-          const int k0 = (c - 4) * 8 + 2 * j2, k1 = k0 + 1;
-          const float a = k0 < Lq ? __ldg(ul + k0) : (k0 == Lq ? 1.0f : 0.f);
-          const float b = k1 < Lq ? __ldg(ul + k1) : (k1 == Lq ? 1.0f : 0.f);
+          const int k0 = (c - 4) * 8 + 2 * j2 - 1, k1 = k0 + 1;   // index into u_ln; -1 = the constant column
+          const float a = k0 < 0 ? 1.0f : (k0 < Lq ? __ldg(ul + k0) : 0.f);
+          const float b = k1 < Lq ? __ldg(ul + k1) : 0.f;
           split2(a, b, hw[j2], lw[j2]);
         }
         *reinterpret_cast<uint4*>(row_a3h + c * 2048) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
@@ -449,7 +465,7 @@ k_chain_tc(const __grid_constant__ TcNet tc, CellBuf cb, int64_t n_cells, int S,
     // ---- GEMM1
     if (tid == 0) {
       tc_fence_after();
-      issue_gemm(tmem_base, s_a1h, s_a1l, s_w + tc.off_b1, tc.K1, 128, idesc128, true);
+      issue_gemm(tmem_base, s_a1h, s_a1l, s_w, tc.b1, tc.K1, tc.K1, idesc128, true);
       umma_commit(bar_mma);
     }
     mbar_wait(bar_mma, phase); phase ^= 1;
@@ -466,8 +482,8 @@ k_chain_tc(const __grid_constant__ TcNet tc, CellBuf cb, int64_t n_cells, int S,
     // ---- GEMM2: D2 = T x B2t + A1 x B2a
     if (tid == 0) {
       tc_fence_after();
-      issue_gemm_ts(tmem_base + 128, tmem_base, s_w + tc.off_b2t, 32, idesc32);
-      issue_gemm(tmem_base + 128, s_a1h, s_a1l, s_w + tc.off_b2a, tc.K1, 32, idesc32, false);
+      issue_gemm_ts(tmem_base + 128, tmem_base, s_w, tc.b2t, idesc32);
+      issue_gemm(tmem_base + 128, s_a1h, s_a1l, s_w, tc.b2a, tc.K1, tc.K1, idesc32, false);
       umma_commit(bar_mma);
     }
     mbar_wait(bar_mma, phase); phase ^= 1;
@@ -485,7 +501,7 @@ k_chain_tc(const __grid_constant__ TcNet tc, CellBuf cb, int64_t n_cells, int S,
     // ---- GEMM3
     if (tid == 0) {
       tc_fence_after();
-      issue_gemm(tmem_base, s_a3h, s_a3l, s_w + tc.off_b3, tc.K3, 128, idesc128, true);
+      issue_gemm(tmem_base, s_a3h, s_a3l, s_w, tc.b3, tc.K3, tc.K3, idesc128, true);
       umma_commit(bar_mma);
     }
     mbar_wait(bar_mma, phase); phase ^= 1;
@@ -502,8 +518,8 @@ k_chain_tc(const __grid_constant__ TcNet tc, CellBuf cb, int64_t n_cells, int S,
     // ---- GEMM4: D4 = T x B4t + A3 x B4a
     if (tid == 0) {
       tc_fence_after();
-      issue_gemm_ts(tmem_base + 128, tmem_base, s_w + tc.off_b4t, 32, idesc32);
-      issue_gemm(tmem_base + 128, s_a3h, s_a3l, s_w + tc.off_b4a, tc.K3, 32, idesc32, false);
+      issue_gemm_ts(tmem_base + 128, tmem_base, s_w, tc.b4t, idesc32);
+      issue_gemm(tmem_base + 128, s_a3h, s_a3l, s_w, tc.b4a, tc.K3, tc.K3, idesc32, false);
       umma_commit(bar_mma);
     }
     mbar_wait(bar_mma, phase); phase ^= 1;
@@ -522,7 +538,7 @@ k_chain_tc(const __grid_constant__ TcNet tc, CellBuf cb, int64_t n_cells, int S,
     // ---- GEMM5
     if (tid == 0) {
       tc_fence_after();
-      issue_gemm(tmem_base, s_a1h, s_a1l, s_w + tc.off_b5, tc.K5, tc.N5, idescN5, true);
+      issue_gemm(tmem_base, s_a1h, s_a1l, s_w, tc.b5, tc.K5, tc.K5, idescN5, true);
       umma_commit(bar_mma);
     }
     mbar_wait(bar_mma, phase); phase ^= 1;
@@ -571,18 +587,29 @@ inline Mat matmul(const Mat& A, const Mat& B, int K, int J, int N) {
 }
 inline Mat load(const float* p, size_t n) { return Mat(p, p + n); }
 
-// append a [N x Kpad] K-major canonical f16 operand built from B[K x N] (rows >= K are zero)
-inline uint32_t append_operand(std::vector<uint8_t>& img, const Mat& B, int K, int N, int Npad, int Kpad) {
-  const uint32_t off = (uint32_t)img.size();
-  img.resize(off + (size_t)Npad * Kpad * 2, 0);
-  __half* base = reinterpret_cast<__half*>(img.data() + off);
+// append the [N x Kpad] K-major canonical f16 copies of B[K x N] (rows >= K are zero): hi = B rounded to f16, lo = the
+// remainder B - hi rounded to f16 (subnormal for the smallest weights: absolute resolution 2^-24).  cat = false: two
+// separate [Npad x Kpad] operands; cat = true: one [2 Npad x Kpad] operand [hi | lo] concatenated along N.
+inline TcOp append_operand(std::vector<uint8_t>& img, const Mat& B, int K, int N, int Npad, int Kpad, bool cat) {
+  TcOp op;
+  const size_t one = (size_t)Npad * Kpad * 2;
+  op.h = (uint32_t)img.size();
+  img.resize(img.size() + 2 * one, 0);
+  const int rows = cat ? 2 * Npad : Npad;            // operand rows per K chunk
+  op.lbo = (uint32_t)rows * 16;
+  op.l = cat ? op.h + (uint32_t)Npad * 16 : op.h + (uint32_t)one;
+  __half* base = reinterpret_cast<__half*>(img.data() + op.h);
+  const size_t lo_elems = (op.l - op.h) / 2;
   for (int k = 0; k < K; ++k)
     for (int n = 0; n < N; ++n) {
-      const size_t e = (size_t)(k / 8) * ((size_t)Npad * 8) + (size_t)n * 8 + (k % 8);
-      base[e] = __float2half_rn((float)B[(size_t)k * N + n]);
+      const size_t e = (size_t)(k / 8) * ((size_t)rows * 8) + (size_t)n * 8 + (k % 8);
+      const double w = B[(size_t)k * N + n];
+      const __half h = __float2half_rn((float)w);
+      base[e] = h;
+      base[lo_elems + e] = __float2half_rn((float)(w - (double)__half2float(h)));
     }
   while (img.size() % 1024) img.push_back(0);
-  return off;
+  return op;
 }
 }  // namespace tc_detail
 
@@ -641,7 +668,7 @@ inline int tc_build(TcNet& tc, const NetW& net, const MrviDims& d, const tc_deta
   Mat Wout0 = load(P(pm, b0 + "/Dense_2/kernel"), (size_t)R * M);
   Mat B2a = matmul(Bs, Wout0, K1r, R, M);
   { const float* bb = P(pm, b0 + "/Dense_2/bias"); for (int n = 0; n < M; ++n) B2a[(size_t)(K1r - 1) * M + n] += bb[n]; }
-  // A3 = [t2 (M) | u_ln (Lq) | 1]
+  // A3 = [t2 (M) | 1 | u_ln (Lq)]   (the constant column sits at k = M in A1, A3 and A5 alike)
   const int K3r = M + Lq + 1;
   Mat Wfin0 = load(P(pm, ab + "/MLP_0/Dense_0/kernel"), (size_t)M * E);
   const float* bfin0 = P(pm, ab + "/MLP_0/Dense_0/bias");
@@ -651,20 +678,20 @@ inline int tc_build(TcNet& tc, const NetW& net, const MrviDims& d, const tc_deta
     Mat top = matmul(Wfin0, We, M, E, R);
     Mat B((size_t)K3r * R, 0.0);
     std::copy(top.begin(), top.end(), B.begin());
-    for (int k = 0; k < Lq; ++k)
-      for (int n = 0; n < R; ++n) B[(size_t)(M + k) * R + n] = W[(size_t)k * R + n];
-    for (int n = 0; n < R; ++n) {
+    for (int n = 0; n < R; ++n) {  // row M: the constant-one column (same position as in A1 / A5)
       double bias = bb[n];
       for (int e = 0; e < E; ++e) bias += (double)bfin0[e] * We[(size_t)e * R + n];
-      B[(size_t)(K3r - 1) * R + n] = bias;
+      B[(size_t)M * R + n] = bias;
     }
+    for (int k = 0; k < Lq; ++k)
+      for (int n = 0; n < R; ++n) B[(size_t)(M + 1 + k) * R + n] = W[(size_t)k * R + n];
     return B;
   };
   Mat B3 = fold_second(b1 + "/Dense_0");
   Mat S3 = fold_second(b1 + "/Dense_1");
   Mat Wout1 = load(P(pm, b1 + "/Dense_2/kernel"), (size_t)R * M);
   Mat B4a = matmul(S3, Wout1, K3r, R, M);
-  { const float* bb = P(pm, b1 + "/Dense_2/bias"); for (int n = 0; n < M; ++n) B4a[(size_t)(K3r - 1) * M + n] += bb[n]; }
+  { const float* bb = P(pm, b1 + "/Dense_2/bias"); for (int n = 0; n < M; ++n) B4a[(size_t)M * M + n] += bb[n]; }
   // A5 = [t4 | 1]; only the first L output columns are kept (use_map=False keeps the mean half)
   const int out_dim = d.use_map ? L : 2 * L;
   const float *Wf1 = P(pm, ab + "/MLP_1/Dense_0/kernel"), *bf1 = P(pm, ab + "/MLP_1/Dense_0/bias");
@@ -678,13 +705,13 @@ inline int tc_build(TcNet& tc, const NetW& net, const MrviDims& d, const tc_deta
   tc.K3 = round_up(K3r, 16);
   tc.N5 = round_up(L, 16) <= 32 ? 32 : 64;
   std::vector<uint8_t> img;
-  tc.off_b1 = append_operand(img, B1, K1r, R, R, tc.K1);
-  tc.off_b2t = append_operand(img, Wout0, R, M, M, R);
-  tc.off_b2a = append_operand(img, B2a, K1r, M, M, tc.K1);
-  tc.off_b3 = append_operand(img, B3, K3r, R, R, tc.K3);
-  tc.off_b4t = append_operand(img, Wout1, R, M, M, R);
-  tc.off_b4a = append_operand(img, B4a, K3r, M, M, tc.K3);
-  tc.off_b5 = append_operand(img, B5, K5r, L, tc.N5, tc.K5);
+  tc.b1 = append_operand(img, B1, K1r, R, R, tc.K1, false);
+  tc.b2t = append_operand(img, Wout0, R, M, M, R, true);
+  tc.b2a = append_operand(img, B2a, K1r, M, M, tc.K1, true);
+  tc.b3 = append_operand(img, B3, K3r, R, R, tc.K3, false);
+  tc.b4t = append_operand(img, Wout1, R, M, M, R, true);
+  tc.b4a = append_operand(img, B4a, K3r, M, M, tc.K3, true);
+  tc.b5 = append_operand(img, B5, K5r, L, tc.N5, tc.K5, false);
   tc.wimg_bytes = (uint32_t)img.size();
   int err;
   if ((err = tc_upload(arena, img.data(), img.size(), (const void**)&tc.wimg))) return err;
@@ -720,7 +747,7 @@ inline int tc_build(TcNet& tc, const NetW& net, const MrviDims& d, const tc_deta
     g_tc_error = "tensor-core chain needs more than 227 KiB of shared memory";
     return MRVI_ERR_UNSUPPORTED;
   }
-  if (cudaFuncSetAttribute(k_chain_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc.smem_bytes) != cudaSuccess) {
+  if (cudaFuncSetAttribute(k_chain_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemOptin) != cudaSuccess) {
     g_tc_error = "cudaFuncSetAttribute(k_chain_tc) failed";
     return MRVI_ERR_CUDA;
   }
@@ -964,7 +991,7 @@ inline int enc_tc_build(EncTc& enc, const NetW& net, const tc_detail::PMap& pm, 
   enc.b0 = net.enc0.b;
   enc.n_kblocks = nkb;
   enc.smem_bytes = (size_t)kEncStages * kEncStageBytes + 256 + 1024;
-  if (cudaFuncSetAttribute(k_enc_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)enc.smem_bytes) != cudaSuccess) {
+  if (cudaFuncSetAttribute(k_enc_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemOptin) != cudaSuccess) {
     g_tc_error = "cudaFuncSetAttribute(k_enc_gemm_tc) failed";
     return MRVI_ERR_CUDA;
   }

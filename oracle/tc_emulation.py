@@ -21,6 +21,11 @@ def _round(a, fmt):
         return a.astype(np.float32)
     if fmt == "f16":
         return a.astype(np.float16).astype(np.float32)
+    if fmt == "f16x2":  # (hi, lo) pair of f16: what the kernel's weight image holds since round 2 (3-term products)
+        a32 = np.asarray(a, dtype=np.float64)
+        hi = a32.astype(np.float16).astype(np.float64)
+        lo = (a32 - hi).astype(np.float16).astype(np.float64)  # subnormal for the smallest weights, as on the device
+        return (hi + lo).astype(np.float32)
     if fmt == "bf16":
         b = np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
         b = ((b + 0x7FFF + ((b >> 16) & 1)) & 0xFFFF0000).astype(np.uint32)
@@ -34,7 +39,8 @@ def _round(a, fmt):
 
 def fold_weights(flat):
     """All host-side weight folding (float64).  Returns the GEMM operand matrices [K, N] and the
-    fp32 epilogue vectors.  K layouts:  A1 = [m(h*E+i) | 1],  A3 = [t2 | u_ln | 1],  A5 = [t4 | 1]."""
+    fp32 epilogue vectors.  K layouts:  A1 = [m(h*E+i) | 1],  A3 = [t2 | u_ln | 1],  A5 = [t4 | 1]
+    (the kernel stores A3 as [t2 | 1 | u_ln]; the order of the K columns does not change the arithmetic)."""
     p = {k: np.asarray(v, dtype=np.float64) for k, v in flat.items()}
     ab = "qz/AttentionBlock_0"
     mha = f"{ab}/MultiHeadDotProductAttention_0"
@@ -104,7 +110,8 @@ def _ln_gelu(h, scale, bias):
 def tc_chain_residual(flat, u, fmt_act="f16", fmt_w="f16"):
     """Residual eps[b, s, :out_dim] of q(z|u,s) for every sample.  `fmt_act` / `fmt_w`: rounding of the
     A (activation) / B (weight) operands of every GEMM (None = fp32; the kernel's hi/lo split of the
-    activations is equivalent to fmt_act=None).  u: (B, Lq) float (the encoder output)."""
+    activations is equivalent to fmt_act=None, its (hi, lo) weight image to fmt_w="f16x2"; round 1 used
+    fmt_w="f16").  u: (B, Lq) float (the encoder output)."""
     f = fold_weights(flat)
     if not isinstance(fmt_w, dict):  # per-operand formats: {"B1": ..., "B2t": ..., ...} (design studies)
         fmt_w = {k: fmt_w for k in ("B1", "B2t", "B2a", "B3", "B4t", "B4a", "B5")}

@@ -1,0 +1,84 @@
+"""Parity at BASELINE shapes, through the path bench.py times (`mrvi_run_device`, one full device chunk).
+
+The oracle cannot process 100k cells x 128 samples in a test's time budget, so each case checks
+  (a) a 512-cell stratified sample of the per-cell blocks against the float64 oracle (pins the arithmetic of the
+      big launch: first / last tiles, both ends of every CTA's range);
+  (b) size-independent identities over ALL cells: group sums of the groupby-only launch (the benchmarked mode: runs of
+      ~n/n_groups sorted cells accumulated in TMEM / registers, float64 atomics at run boundaries) == float64 sums of
+      the per-cell blocks of the keep_cell launch; exact symmetry and zero diagonal of every block; output order ==
+      input order (the sampled cells sit at their own indices).
+Reference: src/mrvi/_model.py:469-504 (group sums), :542-584 (distances).
+"""
+import numpy as np
+import pytest
+
+import mrvi_b200
+from mrvi_b200 import _capi
+from oracle import mrvi_oracle as orc
+from oracle.parity import distance_error_stats, stratified_indices
+
+pytestmark = pytest.mark.gpu
+
+SCALE_CASES = [
+    # name, G, S, L, n_cells, n_groups   (BASELINE.json configs[1], configs[3] per-GPU shard, configs[4] shard)
+    ("C2_100k_S32", 2000, 32, 30, 100_000, 20),
+    ("C4_125k_S128", 2000, 128, 30, 125_000, 50),
+    ("C5_20k_S256_L50", 5000, 256, 50, 20_000, 50),
+]
+BAR = {"tc": 1e-3, "fp32": 1e-5}
+
+
+@pytest.mark.parametrize("precision", ["tc", "fp32"])
+@pytest.mark.parametrize("name,G,S,L,n,ng", SCALE_CASES, ids=[c[0] for c in SCALE_CASES])
+def test_parity_at_baseline_scale(built_library, name, G, S, L, n, ng, precision):
+    import torch
+
+    dev = torch.device("cuda", 0)
+    dims = mrvi_b200.MrviDims(n_input=G, n_sample=S, n_latent=L)
+    params = mrvi_b200.init_params(dims, seed=0)
+    h = _capi.Handle(dims, params, device=0, precision=_capi.PRECISION_TC if precision == "tc" else _capi.PRECISION_FP32)
+    X = mrvi_b200.synthetic_counts(n, G, seed=1000)
+    rng = np.random.default_rng(1101)
+    sid = rng.integers(0, S, size=n).astype(np.int32)
+    codes = rng.integers(0, ng, size=n).astype(np.int32)
+    Xd, sidd, codesd = (torch.from_numpy(a).to(dev) for a in (X, sid, codes))
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    # ---- the benchmarked launch: groupby only
+    sums_g = torch.zeros((ng, S, S), dtype=torch.float64, device=dev)
+    h.run_device(n, Xd.data_ptr(), G, sidd.data_ptr(), [codesd.data_ptr()], [ng], "l2", 0, [sums_g.data_ptr()], 0, 0, stream)
+    # ---- keep_cell + groupby over the same cells
+    cell = torch.empty((n, S, S), dtype=torch.float32, device=dev)
+    sums_k = torch.zeros((ng, S, S), dtype=torch.float64, device=dev)
+    h.run_device(n, Xd.data_ptr(), G, sidd.data_ptr(), [codesd.data_ptr()], [ng], "l2", cell.data_ptr(), [sums_k.data_ptr()], 0, 0,
+                 stream)
+    torch.cuda.synchronize(dev)
+    # (b) identities over all cells
+    ref_sums = torch.zeros((ng, S * S), dtype=torch.float64, device=dev)
+    step = 8192
+    for lo in range(0, n, step):  # float64 sums of the per-cell blocks, in slabs (n x S x S float64 would not fit)
+        blk = cell[lo:lo + step].reshape(-1, S * S).to(torch.float64)
+        ref_sums.index_add_(0, codesd[lo:lo + step].to(torch.int64), blk)
+        blk32 = cell[lo:lo + step]
+        if precision == "fp32":   # direct differences: exactly symmetric
+            assert bool((blk32 == blk32.transpose(1, 2)).all()), "block not exactly symmetric"
+        else:  # Gram on the tensor cores: entries (i, j) and (j, i) add the same three products in a different order
+            asym = float(((blk32 - blk32.transpose(1, 2)).abs().amax(dim=(1, 2)) / blk32.amax(dim=(1, 2)).clamp_min(1e-30)).max())
+            assert asym < 2e-6, asym   # reference test: allclose(d, d.T, atol=1e-6) (tests/test_model.py:241)
+        assert bool((torch.diagonal(cell[lo:lo + step], dim1=1, dim2=2) == 0).all()), "non-zero diagonal"
+    ref_sums = ref_sums.reshape(ng, S, S)
+    scale = float(ref_sums.abs().max())
+    err_g = float((sums_g - ref_sums).abs().max()) / scale
+    err_k = float((sums_k - ref_sums).abs().max()) / scale
+    # (a) stratified sample against the float64 oracle
+    idx = stratified_indices(n, 512)
+    got = cell[torch.from_numpy(idx).to(dev)].cpu().numpy()
+    zref = orc.counterfactual_z(params, X[idx], sid[idx], dtype=np.float64)
+    st = distance_error_stats(got, orc.pairwise_distances(zref))
+    print(f"\n[scale] {name} {precision}: sample of {st['n_cells']} cells: max_norm_err {st['max_norm_err']:.2e} "
+          f"(global {st['global_norm_err']:.2e}), elementwise rel p99 {st['p99_elementwise_rel']:.2e} max {st['max_elementwise_rel']:.2e}; "
+          f"group sums vs float64 sums of the blocks: groupby-only {err_g:.2e}, keep_cell+groupby {err_k:.2e}")
+    assert st["max_norm_err"] < BAR[precision], st
+    assert st["p99_elementwise_rel"] < BAR[precision], st
+    # float32 accumulation over runs of ~n/ng cells (TMEM accumulators / registers) against float64 sums
+    assert err_g < 5e-6 and err_k < 5e-6, (err_g, err_k)
+    h.close()
