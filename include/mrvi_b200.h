@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define MRVI_B200_ABI_VERSION 3
+#define MRVI_B200_ABI_VERSION 4
 
 typedef struct MrviHandle MrviHandle;
 
@@ -68,6 +68,9 @@ int mrvi_abi_version(void);
 
 /* Message of the last error raised on this thread ("" if none). Never NULL. */
 const char* mrvi_last_error(void);
+
+/* Number of CUDA devices visible to the library (0 if none). */
+int mrvi_device_count(void);
 
 /* Number of kernels this library has launched in this process (for bench accounting). */
 int64_t mrvi_kernel_launch_count(void);
@@ -171,13 +174,14 @@ int mrvi_run_sampled_host(MrviHandle* h, int64_t n_cells, const float* X, int64_
                           int64_t* const* group_counts, float* z_out, int64_t chunk_cells);
 
 /*
- * mrvi_run_host for a dense count matrix that is ALREADY stored as small unsigned integers (raw counts kept as
- * uint8 / uint16 in adata.X or a layer): X [n_cells, ldx] elements of x_dtype, ldx >= n_input in ELEMENTS.  The
- * matrix crosses PCIe as it is (1 or 2 bytes per value, no host pass) and is widened to float32 on the GPU, i.e. the
- * result is identical to mrvi_run_host on X.astype(float32) -- what scvi's loader would hand the reference
- * (src/mrvi/_model.py:317-319, 377-384).  Other arguments as mrvi_run_host.
+ * mrvi_run_host for a dense count matrix stored as integers (raw counts in adata.X or a layer): X [n_cells, ldx]
+ * elements of x_dtype, ldx >= n_input in ELEMENTS.  uint8 / uint16 matrices cross PCIe as they are (1 or 2 bytes per
+ * value, no host pass); int32 / int64 matrices are narrowed chunk by chunk on the host to uint8 / uint16 (to float32
+ * when a chunk holds a negative value or one >= 65536) -- no float32 copy of the whole matrix is ever made.  The
+ * values are widened to float32 on the GPU, i.e. the result is identical to mrvi_run_host on X.astype(float32) -- what
+ * scvi's loader would hand the reference (src/mrvi/_model.py:317-319, 377-384).  Other arguments as mrvi_run_host.
  */
-typedef enum MrviXDtype { MRVI_X_UINT8 = 1, MRVI_X_UINT16 = 2 } MrviXDtype;
+typedef enum MrviXDtype { MRVI_X_UINT8 = 1, MRVI_X_UINT16 = 2, MRVI_X_INT32 = 3, MRVI_X_INT64 = 4 } MrviXDtype;
 int mrvi_run_host_counts(MrviHandle* h, int64_t n_cells, const void* X, int32_t x_dtype, int64_t ldx,
                          const int32_t* sample_idx, int32_t n_keys, const int32_t* const* group_codes,
                          const int32_t* n_groups, int32_t norm, float* cell_out, double* const* group_sums,
@@ -194,6 +198,27 @@ int mrvi_run_host_counts(MrviHandle* h, int64_t n_cells, const void* X, int32_t 
  */
 int64_t mrvi_last_h2d_bytes(MrviHandle* h);
 int mrvi_narrow_counts(const float* X, int64_t ldx, int64_t n_rows, int32_t n_cols, void* out, int32_t n_threads);
+
+/*
+ * Multi-GPU: cells shard over ranks in contiguous ranges, every rank runs mrvi_run_device on its
+ * shard with its own handle, and the ONLY exchange step of the path is the sum of the per-category accumulators of
+ * src/mrvi/_model.py:469-484 over ranks: one ncclAllReduce(sum, float64) per key, grouped into a single NCCL launch,
+ * over NVLink / NVSwitch.  NCCL is resolved at run time (dlopen of libnccl.so.2: no link-time dependency).
+ *
+ *   mrvi_comm_unique_id   fills 128 bytes (an ncclUniqueId) on one rank; the caller distributes them to every rank
+ *   mrvi_comm_create      ncclCommInitRank on the handle's device; the communicator belongs to the handle
+ *   mrvi_allreduce_groups in-place all-reduce of group_sums[k] ([n_groups[k], S, S] float64, DEVICE memory) for every
+ *                         key, enqueued on `stream`; nccl_comm: an ncclComm_t of the caller, or NULL = the handle's own
+ */
+int mrvi_comm_unique_id(void* out128);
+int mrvi_comm_create(MrviHandle* h, const void* id128, int32_t n_ranks, int32_t rank);
+int mrvi_allreduce_groups(MrviHandle* h, void* nccl_comm, int32_t n_keys, double* const* group_sums, const int32_t* n_groups,
+                          void* stream);
+
+/* Page-locked host memory for the big outputs (keep_cell blocks, representations): device->host copies into it run at
+ * PCIe speed and overlap the kernels; the Python host side allocates `cell_out` / `z_out` through these. */
+int mrvi_alloc_pinned(int64_t bytes, void** out);
+int mrvi_free_pinned(void* p);
 
 /* Timing taps: device milliseconds spent in each stage of the most recent mrvi_run_* call
  * (CUDA events on the launching stream; valid after that stream is synchronised).

@@ -12,7 +12,7 @@ import numpy as np
 
 from ._params import MrviDims
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 PRECISION_FP32 = 0
 PRECISION_TC = 1
 NORMS = {"l2": 0, "l1": 1, "linf": 2}
@@ -25,6 +25,7 @@ EXPORTED_SYMBOLS = (
     "mrvi_abi_version",
     "mrvi_last_error",
     "mrvi_kernel_launch_count",
+    "mrvi_device_count",
     "mrvi_create",
     "mrvi_destroy",
     "mrvi_run_device",
@@ -36,7 +37,15 @@ EXPORTED_SYMBOLS = (
     "mrvi_last_stage_ms",
     "mrvi_last_h2d_bytes",
     "mrvi_narrow_counts",
+    "mrvi_comm_unique_id",
+    "mrvi_comm_create",
+    "mrvi_allreduce_groups",
+    "mrvi_alloc_pinned",
+    "mrvi_free_pinned",
 )
+
+#: MrviXDtype of include/mrvi_b200.h: integer count matrices the host entry points take as they are
+_X_DTYPES = {np.dtype(np.uint8): 1, np.dtype(np.uint16): 2, np.dtype(np.int32): 3, np.dtype(np.int64): 4}
 
 
 class MrviError(RuntimeError):
@@ -54,7 +63,8 @@ class _CDims(C.Structure):
 
 
 def library_path() -> str:
-    return os.path.join(os.path.dirname(os.path.abspath(__file__)), _LIB_NAME)
+    # MRVI_B200_LIBRARY: an alternative build of the same library (kernel A/B experiments, debug builds)
+    return os.environ.get("MRVI_B200_LIBRARY") or os.path.join(os.path.dirname(os.path.abspath(__file__)), _LIB_NAME)
 
 
 def load_library():
@@ -71,6 +81,7 @@ def load_library():
     lib.mrvi_abi_version.restype = C.c_int
     lib.mrvi_last_error.restype = C.c_char_p
     lib.mrvi_kernel_launch_count.restype = i64
+    lib.mrvi_device_count.restype = C.c_int
     lib.mrvi_create.restype = C.c_int
     lib.mrvi_create.argtypes = [C.POINTER(_CDims), i32, C.POINTER(C.c_char_p), C.POINTER(vp),
                                 C.POINTER(i64), i32, i32, C.POINTER(vp)]
@@ -100,6 +111,16 @@ def load_library():
     lib.mrvi_narrow_counts.argtypes = [vp, i64, i64, i32, vp, i32]
     lib.mrvi_last_stage_ms.restype = C.c_int
     lib.mrvi_last_stage_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    lib.mrvi_comm_unique_id.restype = C.c_int
+    lib.mrvi_comm_unique_id.argtypes = [vp]
+    lib.mrvi_comm_create.restype = C.c_int
+    lib.mrvi_comm_create.argtypes = [vp, vp, i32, i32]
+    lib.mrvi_allreduce_groups.restype = C.c_int
+    lib.mrvi_allreduce_groups.argtypes = [vp, vp, i32, C.POINTER(vp), C.POINTER(i32), vp]
+    lib.mrvi_alloc_pinned.restype = C.c_int
+    lib.mrvi_alloc_pinned.argtypes = [i64, C.POINTER(vp)]
+    lib.mrvi_free_pinned.restype = C.c_int
+    lib.mrvi_free_pinned.argtypes = [vp]
     if lib.mrvi_abi_version() != ABI_VERSION:
         raise MrviError(-101, f"ABI version mismatch: library {lib.mrvi_abi_version()}, binding {ABI_VERSION}")
     _lib = lib
@@ -141,8 +162,47 @@ def narrow_counts(X: np.ndarray, n_threads: int = 4):
     return 0, None
 
 
+def pinned_empty(shape, dtype=np.float32) -> np.ndarray:
+    """An uninitialised ndarray in page-locked host memory (``mrvi_alloc_pinned``): device->host copies into it run at
+    PCIe speed and overlap the kernels.  Freed when the array (and every view of it) is garbage collected."""
+    import weakref
+
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) if len(shape) else 1
+    nbytes = max(n * dtype.itemsize, 1)
+    lib = load_library()
+    ptr = C.c_void_p()
+    _check(lib.mrvi_alloc_pinned(nbytes, C.byref(ptr)))
+    buf = (C.c_uint8 * nbytes).from_address(ptr.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=n).reshape(shape)
+    weakref.finalize(buf, lib.mrvi_free_pinned, C.c_void_p(ptr.value))
+    return arr
+
+
+def comm_unique_id() -> bytes:
+    """128 bytes identifying a new NCCL communicator (``mrvi_comm_unique_id``); distribute them to every rank."""
+    buf = (C.c_uint8 * 128)()
+    _check(load_library().mrvi_comm_unique_id(buf))
+    return bytes(buf)
+
+
+def device_count() -> int:
+    """Number of CUDA devices visible to the library (``mrvi_device_count``)."""
+    return int(load_library().mrvi_device_count())
+
+
 def kernel_launch_count() -> int:
     return int(load_library().mrvi_kernel_launch_count())
+
+
+def _out_empty(shape) -> np.ndarray:
+    """Output buffer of ``run_host``: page-locked above 16 MiB (the D2H stream then runs at PCIe speed), else plain."""
+    if int(np.prod(shape)) * 4 >= (16 << 20):
+        try:
+            return pinned_empty(shape, np.float32)
+        except MrviError:
+            pass
+    return np.empty(shape, dtype=np.float32)
 
 
 class Handle:
@@ -202,7 +262,8 @@ class Handle:
     # ---- host-buffer pass: numpy arrays in, numpy arrays out
     def run_host(self, X: np.ndarray, sample_idx: np.ndarray, group_codes: Sequence[np.ndarray] = (),
                  n_groups: Sequence[int] = (), norm: str = "l2", keep_cell: bool = True, want_z: bool = False,
-                 want_u: bool = False, chunk_cells: int = 0, cell_out: Optional[np.ndarray] = None):
+                 want_u: bool = False, chunk_cells: int = 0, cell_out: Optional[np.ndarray] = None,
+                 z_out: Optional[np.ndarray] = None):
         if norm not in NORMS:
             raise ValueError(f"norm {norm} not supported")
         d = self.dims
@@ -214,9 +275,10 @@ class Handle:
                 X.sum_duplicates()
             csr = (np.ascontiguousarray(X.indptr, dtype=np.int64), np.ascontiguousarray(X.indices, dtype=np.int32),
                    np.ascontiguousarray(X.data, dtype=np.float32))
-        elif X.dtype in (np.uint8, np.uint16) and X.ndim == 2:
-            # raw counts stored as small unsigned integers: cross PCIe as they are, widened on the GPU
-            if X.strides[1] != X.itemsize or X.strides[0] % X.itemsize != 0:
+        elif X.dtype in _X_DTYPES and X.ndim == 2:
+            # raw counts stored as integers: uint8 / uint16 cross PCIe as they are, int32 / int64 are narrowed chunk by
+            # chunk inside the library (no float32 copy of the matrix); widened to float32 on the GPU
+            if X.strides[1] != X.itemsize or X.strides[0] % X.itemsize != 0 or X.strides[0] < 0:
                 X = np.ascontiguousarray(X)
         elif X.dtype != np.float32 or X.ndim != 2 or X.strides[1] != 4 or X.strides[0] % 4 != 0:
             X = np.ascontiguousarray(X, dtype=np.float32)
@@ -234,13 +296,15 @@ class Handle:
         out = {}
         if keep_cell:
             if cell_out is None:
-                cell_out = np.empty((n, S, S), dtype=np.float32)
+                cell_out = _out_empty((n, S, S))
             elif cell_out.shape != (n, S, S) or cell_out.dtype != np.float32 or not cell_out.flags.c_contiguous:
                 raise ValueError("cell_out must be a C-contiguous float32 array of shape (n, S, S)")
             out["cell"] = cell_out
         sums = [np.zeros((g, S, S), dtype=np.float64) for g in n_groups]
         counts = [np.zeros((g,), dtype=np.int64) for g in n_groups]
-        z = np.empty((n, S, L), dtype=np.float32) if want_z else None
+        z = (z_out if z_out is not None else _out_empty((n, S, L))) if want_z else None
+        if want_z and (z.shape != (n, S, L) or z.dtype != np.float32 or not z.flags.c_contiguous):
+            raise ValueError("z_out must be a C-contiguous float32 array of shape (n, S, L)")
         u = np.empty((n, Lq), dtype=np.float32) if want_u else None
         tail = (sid.ctypes.data, len(codes), _ptr_array([c.ctypes.data for c in codes]),
                 _i32_array(n_groups), NORMS[norm], out["cell"].ctypes.data if keep_cell else None,
@@ -248,8 +312,8 @@ class Handle:
                 z.ctypes.data if want_z else None, u.ctypes.data if want_u else None, int(chunk_cells))
         if csr is not None:
             _check(load_library().mrvi_run_host_csr(self._h, n, csr[0].ctypes.data, csr[1].ctypes.data, csr[2].ctypes.data, *tail))
-        elif X.dtype in (np.uint8, np.uint16):
-            _check(load_library().mrvi_run_host_counts(self._h, n, X.ctypes.data, 1 if X.dtype == np.uint8 else 2, ldx, *tail))
+        elif X.dtype in _X_DTYPES:
+            _check(load_library().mrvi_run_host_counts(self._h, n, X.ctypes.data, _X_DTYPES[X.dtype], ldx, *tail))
         else:
             _check(load_library().mrvi_run_host(self._h, n, X.ctypes.data, ldx, *tail))
         out["group_sums"] = sums
@@ -315,6 +379,17 @@ class Handle:
         if want_z:
             out["z"] = z
         return out
+
+    # ---- multi-GPU: the one exchange step of the path
+    def comm_create(self, unique_id: bytes, n_ranks: int, rank: int):
+        """``ncclCommInitRank`` on this handle's device (``unique_id`` from :func:`comm_unique_id` of one rank)."""
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        _check(load_library().mrvi_comm_create(self._h, buf, int(n_ranks), int(rank)))
+
+    def allreduce_groups(self, group_sum_ptrs: Sequence[int], n_groups: Sequence[int], stream: int = 0, nccl_comm: int = 0):
+        """In-place NCCL all-reduce (sum, float64) of the per-key group sums in DEVICE memory."""
+        _check(load_library().mrvi_allreduce_groups(self._h, nccl_comm or None, len(n_groups), _ptr_array(group_sum_ptrs),
+                                                    _i32_array(n_groups), stream or None))
 
     def last_h2d_bytes(self) -> int:
         """Bytes of X the last ``run_host`` copied host->device (count chunks are narrowed to uint8 / uint16)."""

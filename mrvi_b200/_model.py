@@ -58,13 +58,19 @@ class MrVI:
     precision
         ``"fp32"`` (FFMA, parity 1e-5) or ``"tc"`` (tcgen05 tensor cores, parity 1e-3).
     device
-        CUDA device index.
+        CUDA device index (single-GPU use).
+    devices
+        CUDA device indices to shard over, e.g. ``devices=range(8)`` or ``"all"``: cells are split into contiguous
+        ranges, one per device (one library handle and one host thread each); the per-group sums are added up on the
+        host in float64 and every device streams its ``keep_cell`` blocks into its slice of ONE page-locked output.
+        Results are the single-GPU ones (counts and cell order bit-exact; sums up to float64 re-association).
     seed
         Seed of the sampled paths' noise generator (see ``self.seed``).
     """
 
     def __init__(self, adata, params: Mapping, sample_key: str = "sample", sample_order: Optional[Sequence] = None,
-                 precision: str = "fp32", device: int = 0, dims: Optional[MrviDims] = None, seed: int = 0):
+                 precision: str = "fp32", device: int = 0, dims: Optional[MrviDims] = None, seed: int = 0,
+                 devices=None):
         if precision not in _PRECISIONS:
             raise ValueError(f"precision must be one of {sorted(_PRECISIONS)}, not {precision!r}")
         self.adata = adata
@@ -85,13 +91,23 @@ class MrVI:
         if adata.n_vars != self.dims.n_input:
             raise ValueError(f"adata has {adata.n_vars} genes, parameters expect {self.dims.n_input}")
         self.precision = precision
-        self.device = int(device)
+        if devices is None:
+            devices = [int(device)]
+        elif isinstance(devices, str):
+            if devices != "all":
+                raise ValueError("devices must be a sequence of CUDA device indices or 'all'")
+            devices = list(range(_capi.device_count()))
+        self.devices = [int(d) for d in devices]
+        if not self.devices or len(set(self.devices)) != len(self.devices):
+            raise ValueError(f"devices must be a non-empty list of distinct CUDA device indices, not {devices!r}")
+        self.device = self.devices[0]
         #: seed of the device Philox generator of the sampled paths (use_mean=False / normalize_distances=True).
         #: Draws depend on (seed, cell index, draw, sample) only, so results are reproducible and independent of
         #: chunking / sharding; the reference's JAX threefry streams are NOT reproduced (statistical parity).
         self.seed = int(seed)
         self.is_trained_ = True
-        self._handle = _capi.Handle(self.dims, self.params, device=self.device, precision=_PRECISIONS[precision])
+        self._handles = [_capi.Handle(self.dims, self.params, device=d, precision=_PRECISIONS[precision]) for d in self.devices]
+        self._handle = self._handles[0]
         self.last_stage_ms: dict = {}
 
     # ------------------------------------------------------------------ construction helpers
@@ -106,7 +122,8 @@ class MrVI:
         pass
 
     def close(self):
-        self._handle.close()
+        for h in self._handles:
+            h.close()
 
     # ------------------------------------------------------------------ host helpers
     def _check_if_trained(self, warn: bool = False):
@@ -123,15 +140,81 @@ class MrVI:
         return np.asarray(codes, dtype=np.int32)
 
     def _group_codes(self, adata, key: str, indices: np.ndarray):
-        """Per-cell int32 group code in ``value_counts()`` order plus (labels, counts)."""
+        """Per-cell int32 group code in ``value_counts()`` order plus (labels, counts).  Vectorised: one hash pass over
+        the labels (or one table look-up of the category codes), no Python loop over cells."""
         vc = adata.obs[key].value_counts()  # reference `_model.py:494-495`
         cats = list(vc.index)
         counts = vc.to_numpy().astype(np.int64)
         # labels come from self.adata, positionally (reference quirk, `_model.py:470`; pandas>=3 needs to_numpy)
-        labels = self.adata.obs[key].to_numpy()[indices]
-        lookup = {c: i for i, c in enumerate(cats)}
-        codes = np.fromiter((lookup.get(l, -1) for l in labels.tolist()), dtype=np.int32, count=len(labels))
+        col = self.adata.obs[key]
+        whole = len(indices) == len(col) and (len(indices) == 0 or (indices[0] == 0 and indices[-1] == len(col) - 1
+                                                                    and np.all(np.diff(indices) == 1)))
+        if isinstance(col.dtype, pd.CategoricalDtype):
+            # category code -> position in value_counts() order (-1: not in `adata`'s categories / NaN)
+            lut = pd.Categorical(col.cat.categories, categories=cats).codes.astype(np.int32)
+            old = col.cat.codes.to_numpy()
+            if not whole:
+                old = old[indices]
+            codes = np.where(old >= 0, lut[np.maximum(old, 0)], -1).astype(np.int32)
+        else:
+            labels = col.to_numpy() if whole else col.to_numpy()[indices]
+            codes = pd.Categorical(labels, categories=cats).codes.astype(np.int32)
         return codes, cats, counts
+
+    def _host_matrix(self, X, idx: np.ndarray, whole: bool):
+        """``adata.X`` (or its rows ``idx``) in a form the C-ABI takes WITHOUT a float32 copy of the matrix where
+        possible: CSR stays sparse (densified on the GPU), integer count matrices (uint8 / uint16 / int32 / int64) are
+        narrowed chunk by chunk inside the library, C-contiguous float32 is passed as it is."""
+        if hasattr(X, "tocsr") and not isinstance(X, np.ndarray):
+            return X.tocsr() if whole else X.tocsr()[idx]
+        if isinstance(X, np.ndarray) and X.dtype in _capi._X_DTYPES:
+            return X if whole else X[idx]
+        if whole and isinstance(X, np.ndarray) and X.dtype == np.float32 and X.ndim == 2 and X.strides[1] == 4 and X.strides[0] > 0:
+            return X
+        return dense_float32(X) if whole else dense_float32(X[idx])
+
+    def _run_sharded(self, Xh, sample_codes, group_codes, n_groups, norm, keep_cell, want_z, want_u=False):
+        """One ``run_host`` per device over contiguous cell ranges (host threads; ctypes releases the GIL), group sums
+        added on the host (float64: the path's only exchange step), keep_cell / z blocks written by
+        every device straight into its slice of one page-locked output."""
+        n = Xh.shape[0]
+        P = min(len(self._handles), max(1, n))
+        if P <= 1:
+            res = self._handle.run_host(Xh, sample_codes, group_codes, n_groups, norm=norm, keep_cell=keep_cell, want_z=want_z,
+                                        want_u=want_u)
+            self.last_stage_ms = self._handle.last_stage_ms()
+            return res
+        from concurrent.futures import ThreadPoolExecutor
+
+        from ._dist import shard_range
+
+        d = self.dims
+        S, L = d.n_sample, d.n_latent
+        cell = _capi._out_empty((n, S, S)) if keep_cell else None
+        z = _capi._out_empty((n, S, L)) if want_z else None
+        u = np.empty((n, d.n_latent_q), dtype=np.float32) if want_u else None
+
+        def work(r):
+            lo, hi = shard_range(n, r, P)
+            res = self._handles[r].run_host(Xh[lo:hi], sample_codes[lo:hi], [c[lo:hi] for c in group_codes], n_groups, norm=norm,
+                                            keep_cell=keep_cell, want_z=want_z, want_u=want_u,
+                                            cell_out=cell[lo:hi] if keep_cell else None, z_out=z[lo:hi] if want_z else None)
+            if want_u:
+                u[lo:hi] = res["u"]
+            return res
+
+        with ThreadPoolExecutor(max_workers=P) as ex:
+            parts = list(ex.map(work, range(P)))
+        out = {"group_sums": [np.sum([p["group_sums"][k] for p in parts], axis=0) for k in range(len(n_groups))],
+               "group_counts": [np.sum([p["group_counts"][k] for p in parts], axis=0) for k in range(len(n_groups))]}
+        if keep_cell:
+            out["cell"] = cell
+        if want_z:
+            out["z"] = z
+        if want_u:
+            out["u"] = u
+        self.last_stage_ms = self._handle.last_stage_ms()
+        return out
 
     # ------------------------------------------------------------------ reference API
     def compute_local_statistics(self, reductions: list, adata=None, indices: Optional[Sequence[int]] = None,
@@ -159,17 +242,7 @@ class MrVI:
         idx = np.arange(adata.n_obs) if indices is None else np.asarray(indices).astype(int).reshape(-1)
         sample_codes = self._sample_codes(adata)[idx]
         whole = indices is None
-        X = adata.X
-        if hasattr(X, "tocsr") and not isinstance(X, np.ndarray):
-            Xh = X.tocsr() if whole else X.tocsr()[idx]  # stays sparse: densified on the GPU (mrvi_run_host_csr)
-        elif isinstance(X, np.ndarray) and X.dtype in (np.uint8, np.uint16):
-            Xh = X if whole else X[idx]     # raw counts kept as small integers: sent as they are (mrvi_run_host_counts)
-        elif whole and isinstance(X, np.ndarray) and X.dtype == np.float32 and X.flags.c_contiguous:
-            Xh = X
-        elif whole:
-            Xh = dense_float32(X)
-        else:
-            Xh = dense_float32(X[idx])
+        Xh = self._host_matrix(adata.X, idx, whole)
 
         generic = [r for r in reductions if not _is_identity_fn(r.fn)]
         if generic:
@@ -182,9 +255,7 @@ class MrVI:
         want_z = any(r.input == "mean_representations" for r in reductions)
         if any(r.input == "mean_representations" for r in reqs.grouped_reductions):
             return self._compute_generic(reductions, adata, idx, Xh, sample_codes, batch_size, norm)
-        res = self._handle.run_host(Xh, sample_codes, [p[0] for p in plans], [len(p[1]) for p in plans], norm=norm,
-                                    keep_cell=keep_cell, want_z=want_z)
-        self.last_stage_ms = self._handle.last_stage_ms()
+        res = self._run_sharded(Xh, sample_codes, [p[0] for p in plans], [len(p[1]) for p in plans], norm, keep_cell, want_z)
         cell_names = self.adata.obs_names[idx].values
         final = OrderedDict()
         for ur in reqs.ungrouped_reductions:
@@ -338,13 +409,8 @@ class MrVI:
         adata = self.adata if adata is None else adata
         idx = np.arange(adata.n_obs) if indices is None else np.asarray(indices).astype(int).reshape(-1)
         sample_codes = self._sample_codes(adata)[idx]
-        X = adata.X
-        if hasattr(X, "tocsr") and not isinstance(X, np.ndarray):
-            Xh = X.tocsr() if indices is None else X.tocsr()[idx]
-        else:
-            Xh = dense_float32(X) if indices is None else dense_float32(X[idx])
-        res = self._handle.run_host(Xh, sample_codes, keep_cell=False, want_u=not give_z, want_z=give_z)
-        self.last_stage_ms = self._handle.last_stage_ms()
+        Xh = self._host_matrix(adata.X, idx, indices is None)
+        res = self._run_sharded(Xh, sample_codes, [], [], "l2", False, give_z, want_u=not give_z)
         if give_z:
             return np.ascontiguousarray(res["z"][np.arange(len(idx)), sample_codes])
         return res["u"]

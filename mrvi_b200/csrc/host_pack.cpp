@@ -204,4 +204,53 @@ int narrow_counts(PackPool& pool, const float* X, int64_t ldx, int64_t n_rows, i
   return (f & 3u) ? 0 : 2;
 }
 
+
+namespace {
+template <typename SRC, typename T>
+uint32_t narrow_rows_int(const SRC* X, int64_t ldx, int64_t r0, int64_t r1, int G, T* out) {
+  uint64_t ored = 0;
+  for (int64_t r = r0; r < r1; ++r) {
+    const SRC* x = X + r * ldx;
+    T* o = out + r * G;
+    for (int k = 0; k < G; ++k) {
+      const SRC v = x[k];
+      ored |= (uint64_t)(int64_t)v;   // a negative value sets the high bits
+      o[k] = (T)v;
+    }
+  }
+  const uint64_t limit = sizeof(T) == 1 ? ~uint64_t(0xFF) : ~uint64_t(0xFFFF);
+  return (ored & limit) ? 2u : 0u;
+}
+template <typename SRC>
+void rows_to_f32(const SRC* X, int64_t ldx, int64_t r0, int64_t r1, int G, float* out) {
+  for (int64_t r = r0; r < r1; ++r) {
+    const SRC* x = X + r * ldx;
+    float* o = out + r * G;
+    for (int k = 0; k < G; ++k) o[k] = (float)x[k];
+  }
+}
+template <typename SRC>
+int narrow_counts_int_t(PackPool& pool, const SRC* X, int64_t ldx, int64_t n_rows, int G, void* out) {
+  if (n_rows == 0) return 1;
+  std::vector<uint32_t> flags(pool.size(), 0u);
+  auto span = [&](int t, int nt, int64_t* r0, int64_t* r1) {
+    const int64_t per = (n_rows + nt - 1) / nt;
+    *r0 = std::min<int64_t>(n_rows, (int64_t)t * per);
+    *r1 = std::min<int64_t>(n_rows, *r0 + per);
+  };
+  auto any = [&]() { uint32_t f = 0; for (uint32_t v : flags) f |= v; return f != 0; };
+  pool.run([&](int t, int nt) { int64_t r0, r1; span(t, nt, &r0, &r1); flags[t] = narrow_rows_int<SRC, uint8_t>(X, ldx, r0, r1, G, static_cast<uint8_t*>(out)); });
+  if (!any()) return 1;
+  pool.run([&](int t, int nt) { int64_t r0, r1; span(t, nt, &r0, &r1); flags[t] = narrow_rows_int<SRC, uint16_t>(X, ldx, r0, r1, G, static_cast<uint16_t*>(out)); });
+  if (!any()) return 2;
+  pool.run([&](int t, int nt) { int64_t r0, r1; span(t, nt, &r0, &r1); rows_to_f32<SRC>(X, ldx, r0, r1, G, static_cast<float*>(out)); });
+  return 4;
+}
+}  // namespace
+
+int narrow_counts_int(PackPool& pool, const void* X, int elem_bytes, int64_t ldx, int64_t n_rows, int G, void* out) {
+  return elem_bytes == 8 ? narrow_counts_int_t<int64_t>(pool, static_cast<const int64_t*>(X), ldx, n_rows, G, out)
+                         : narrow_counts_int_t<int32_t>(pool, static_cast<const int32_t*>(X), ldx, n_rows, G, out);
+}
+
 }  // namespace mrvi

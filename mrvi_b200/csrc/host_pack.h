@@ -24,4 +24,9 @@ class PackPool {  // small persistent thread pool; run() executes fn(thread, n_t
 // Returns 1: written as uint8, 2: written as uint16, 0: not narrowable (out is garbage; send the float32 rows).
 int narrow_counts(PackPool& pool, const float* X, int64_t ldx, int64_t n_rows, int G, void* out);
 
+// The same for a count matrix stored as int32 (elem_bytes = 4) or int64 (elem_bytes = 8) -- raw counts are often kept
+// that way in adata.X / a layer.  Returns 1 / 2 as above; when a value is negative or >= 65536 the rows are written to
+// `out` as float32 instead (the exact conversion scvi's loader would do) and 4 is returned.  `out`: 4 bytes per value.
+int narrow_counts_int(PackPool& pool, const void* X, int elem_bytes, int64_t ldx, int64_t n_rows, int G, void* out);
+
 }  // namespace mrvi

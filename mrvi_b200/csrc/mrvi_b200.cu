@@ -2,6 +2,8 @@
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
 #include <cub/device/device_radix_sort.cuh>
 
+#include <dlfcn.h>
+
 #include <atomic>
 #include <chrono>
 #include <cstdarg>
@@ -20,6 +22,7 @@
 #include "tc_kernels.cuh"
 #include "tc_encoder.cuh"
 #include "tc_fused.cuh"
+#include "tc_fused3.cuh"
 #include "tc_dist.cuh"
 #include "sampled_kernels.cuh"
 
@@ -159,6 +162,7 @@ struct MrviHandle {
   int ev_used = 0;
   cudaEvent_t ev_call[2] = {nullptr, nullptr};
   HostStage hs;
+  void* nccl_comm = nullptr;   // created by mrvi_comm_create (NCCL through dlopen: no link-time dependency)
   ~MrviHandle() {
     for (cudaEvent_t e : ev) cudaEventDestroy(e);
     for (int i = 0; i < 2; ++i) if (ev_call[i]) cudaEventDestroy(ev_call[i]);
@@ -516,11 +520,13 @@ static int run_device_impl(MrviHandle* h, int64_t n, const float* X, int64_t ldx
     float* z = z_out ? z_out + lo * net.S * net.L : h->zbuf;
     if ((err = launch_encoder(h, X + lo * ldx, ldx, sid + lo, m, st))) return err;
     if (time_stages) cudaEventRecord(e1, st);
-    if (h->precision == MRVI_PRECISION_TC && need_dist && h->tc.fused_smem_bytes && tc_fused_supported(h->tc, net.S, norm)) {
+    const bool f3 = h->precision == MRVI_PRECISION_TC && tc_fused3_supported(h->tc, net.S, net.L, norm);
+    if (h->precision == MRVI_PRECISION_TC && need_dist && (f3 || (h->tc.fused_smem_bytes && tc_fused_supported(h->tc, net.S, norm)))) {
       // fused: chain + distances + group sums in one kernel; z never leaves the SM unless asked for
       GroupPlan gp;
       if ((err = plan_groups(h, m, n_keys, codes, lo, n_groups, sums, &gp, st))) return err;
-      tc_launch_fused(h->tc, h->net, m, h->cb, z_out ? z : nullptr, cell_out ? cell_out + lo * net.S * net.S : nullptr, gp, st);
+      if (f3) tc_launch_fused3(h->tc, h->net, m, h->cb, z_out ? z : nullptr, cell_out ? cell_out + lo * net.S * net.S : nullptr, gp, st);
+      else tc_launch_fused(h->tc, h->net, m, h->cb, z_out ? z : nullptr, cell_out ? cell_out + lo * net.S * net.S : nullptr, gp, st);
       LAUNCH_CHECK();
       if (time_stages) { cudaEventRecord(e2, st); cudaEventRecord(e3, st); }
       if (u_out) CUDA_TRY(cudaMemcpyAsync(u_out + lo * net.Lq, h->cb.u, m * net.Lq * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -528,7 +534,8 @@ static int run_device_impl(MrviHandle* h, int64_t n, const float* X, int64_t ldx
     }
     if (need_z) {
       if (h->precision == MRVI_PRECISION_TC) {
-        if (h->tc.fused_smem_bytes) tc_launch_fused_chain(h->tc, h->net, m, h->cb, z, st);  // two threads per row, 1 CTA / SM
+        if (h->tc.fused3_smem_bytes) { GroupPlan none; memset(&none, 0, sizeof(none)); tc_launch_fused3(h->tc, h->net, m, h->cb, z, nullptr, none, st); }
+        else if (h->tc.fused_smem_bytes) tc_launch_fused_chain(h->tc, h->net, m, h->cb, z, st);  // two threads per row, 1 CTA / SM
         else if ((err = tc_launch_qz(h->tc, h->net, m, h->cb, z, st))) return err;
         LAUNCH_CHECK();
       } else {
@@ -556,14 +563,17 @@ static int chain_and_dist(MrviHandle* h, const CellBuf& cb, int64_t n, int norm,
   const NetW& net = h->net;
   const bool need_dist = cell_out != nullptr || gp.n_keys > 0;
   int err;
-  if (h->precision == MRVI_PRECISION_TC && need_dist && h->tc.fused_smem_bytes && tc_fused_supported(h->tc, net.S, norm)) {
-    tc_launch_fused(h->tc, net, n, cb, z_out, cell_out, gp, st);
+  const bool f3 = h->precision == MRVI_PRECISION_TC && tc_fused3_supported(h->tc, net.S, net.L, norm);
+  if (h->precision == MRVI_PRECISION_TC && need_dist && (f3 || (h->tc.fused_smem_bytes && tc_fused_supported(h->tc, net.S, norm)))) {
+    if (f3) tc_launch_fused3(h->tc, net, n, cb, z_out, cell_out, gp, st);
+    else tc_launch_fused(h->tc, net, n, cb, z_out, cell_out, gp, st);
     LAUNCH_CHECK();
     return 0;
   }
   float* z = z_out ? z_out : z_scratch;
   if (h->precision == MRVI_PRECISION_TC) {
-    if (h->tc.fused_smem_bytes) tc_launch_fused_chain(h->tc, net, n, cb, z, st);
+    if (h->tc.fused3_smem_bytes) { GroupPlan none; memset(&none, 0, sizeof(none)); tc_launch_fused3(h->tc, net, n, cb, z, nullptr, none, st); }
+    else if (h->tc.fused_smem_bytes) tc_launch_fused_chain(h->tc, net, n, cb, z, st);
     else if ((err = tc_launch_qz(h->tc, net, n, cb, z, st))) return err;
     LAUNCH_CHECK();
   } else if ((err = launch_qz(h, cb, n, net.S, z, st))) return err;
@@ -736,6 +746,45 @@ static int run_sampled_host_impl(MrviHandle* h, int64_t n_cells, const float* X,
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------
+// NCCL, resolved at run time (dlopen): the library has no link-time dependency on it, and inside a torch process the
+// already loaded libnccl.so.2 is picked up.
+struct NcclApi {
+  typedef struct { char internal[128]; } UniqueId;
+  int (*GetUniqueId)(UniqueId*) = nullptr;
+  int (*CommInitRank)(void**, int, UniqueId, int) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool ok = false;
+};
+static NcclApi& nccl_api() {
+  static NcclApi api;
+  static bool tried = false;
+  if (tried) return api;
+  tried = true;
+  void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) return api;
+  api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(dlsym(lib, "ncclGetUniqueId"));
+  api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(dlsym(lib, "ncclCommInitRank"));
+  api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(lib, "ncclCommDestroy"));
+  api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(dlsym(lib, "ncclAllReduce"));
+  api.GroupStart = reinterpret_cast<decltype(api.GroupStart)>(dlsym(lib, "ncclGroupStart"));
+  api.GroupEnd = reinterpret_cast<decltype(api.GroupEnd)>(dlsym(lib, "ncclGroupEnd"));
+  api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(dlsym(lib, "ncclGetErrorString"));
+  api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.GroupStart && api.GroupEnd;
+  return api;
+}
+#define NCCL_TRY(expr)                                                                              \
+  do {                                                                                              \
+    int _r = (expr);                                                                                \
+    if (_r != 0)                                                                                    \
+      return fail(MRVI_ERR_CUDA, "%s failed: %s", #expr, nccl_api().GetErrorString ? nccl_api().GetErrorString(_r) : "NCCL error"); \
+  } while (0)
+
 }  // namespace mrvi
 
 // ==========================================================================================
@@ -798,6 +847,9 @@ int mrvi_create(const MrviDims* dims, int32_t n_params, const char* const* names
     if ((err = enc_tc_build(h->enc_tc, h->net, pt.m, h->arena))) return fail(err, "%s", tc_error());
     if (h->enc_tc.ready) CUDA_TRY(h->arena.alloc((void**)&h->h1buf, (size_t)h->chunk_cells * 128 * sizeof(float)));
     if ((err = tc_fused_prepare(h->tc, h->dims.n_latent))) return fail(err, "%s", tc_error());
+    // tc_fused3.cuh (dedicated issuer warp + attention producer warps, setmaxnreg) is an opt-in experiment: measured
+    // slower than the two-warpgroup kernel once that one issues its MMAs from a warp-uniform branch
+    if (getenv("MRVI_B200_FUSED") && atoi(getenv("MRVI_B200_FUSED")) == 3 && (err = tc_fused3_prepare(h->tc))) return fail(err, "%s", tc_error());
     if (dist_tc_supported(h->net.S, h->net.L, MRVI_NORM_L2) && (err = dist_tc_prepare(h->net.L, h->net.S, &h->dist_tc_smem)))
       return fail(err, "%s", tc_error());
     if (h->enc_tc.ready && !getenv("MRVI_B200_FP32_ENCODER_TAIL")) {
@@ -814,6 +866,7 @@ int mrvi_destroy(MrviHandle* h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
+  if (h->nccl_comm && nccl_api().ok) nccl_api().CommDestroy(h->nccl_comm);
   delete h;
   return 0;
 }
@@ -854,8 +907,8 @@ int mrvi_distances_device(MrviHandle* h, int64_t n_cells, const float* z, int32_
   return 0;
 }
 
-// x_elem: bytes per element of a dense X: 4 = float32, 1 / 2 = uint8 / uint16 counts (mrvi_run_host_counts)
-static int run_host_impl(MrviHandle* h, int64_t n_cells, const float* X, int x_elem, int64_t ldx, const int64_t* indptr,
+// x_kind: element type of a dense X: 0 = float32, 1 / 2 = uint8 / uint16, 3 / 4 = int32 / int64 counts (mrvi_run_host_counts)
+static int run_host_impl(MrviHandle* h, int64_t n_cells, const float* X, int x_kind, int64_t ldx, const int64_t* indptr,
                          const int32_t* indices, const float* data, const int32_t* sample_idx,
                          int32_t n_keys, const int32_t* const* group_codes, const int32_t* n_groups, int32_t norm,
                          float* cell_out, double* const* group_sums, int64_t* const* group_counts, float* z_out,
@@ -900,8 +953,11 @@ static int run_host_impl(MrviHandle* h, int64_t n_cells, const float* X, int x_e
   // lossless narrowing of count chunks before the copy (host_pack.cpp): dense input, big enough to matter
   static const bool pack_disabled = getenv("MRVI_B200_NO_HOST_PACK") != nullptr;
   static const double pack_min_gbps = getenv("MRVI_B200_PACK_MIN_GBPS") ? atof(getenv("MRVI_B200_PACK_MIN_GBPS")) : 45.0;
-  const bool narrow_in = !csr && x_elem < 4;  // the caller's matrix is already uint8 / uint16: copied as it is, widened on the GPU
-  const bool use_pack = !csr && !narrow_in && !pack_disabled && n_cells * (int64_t)G >= (1ll << 22);
+  const int x_elem = x_kind == 1 ? 1 : x_kind == 2 ? 2 : x_kind == 4 ? 8 : 4;  // bytes per element of the caller's matrix
+  const bool narrow_in = !csr && (x_kind == 1 || x_kind == 2);  // already uint8 / uint16: copied as it is, widened on the GPU
+  const bool int_in = !csr && (x_kind == 3 || x_kind == 4);     // int32 / int64 counts: always narrowed (or converted) on the host
+  const bool use_pack = !csr && !narrow_in && (int_in || (!pack_disabled && n_cells * (int64_t)G >= (1ll << 22)));
+  const size_t pack_elem = int_in ? 4 : 2;   // staging bytes per value: the int path may have to fall back to float32
   if (use_pack && !hs.pool) {
     int nt = (int)std::thread::hardware_concurrency();
     if (const char* e = getenv("LOCAL_WORLD_SIZE")) nt /= std::max(1, atoi(e));  // one process per GPU shares the host cores
@@ -915,7 +971,7 @@ static int run_host_impl(MrviHandle* h, int64_t n_cells, const float* X, int x_e
   if (csr)
     for (int64_t lo = 0; lo < n_cells; lo += ch) max_nnz = std::max(max_nnz, indptr[std::min(n_cells, lo + ch)] - indptr[lo]);
   if (hs.chunk < ch || hs.n_keys < n_keys || (cell_out && !hs.has_cell) || (z_out && !hs.has_z) || (u_out && !hs.has_u) || !sums_ok ||
-      (csr && hs.csr_nnz_cap < max_nnz) || (use_pack && !hs.pack_unavailable && hs.pack_bytes < (size_t)ch * G * 2) ||
+      (csr && hs.csr_nnz_cap < max_nnz) || (use_pack && !hs.pack_unavailable && hs.pack_bytes < (size_t)ch * G * pack_elem) ||
       (narrow_in && hs.dpack_bytes < (size_t)ch * G * 2)) {
     CUDA_TRY(cudaDeviceSynchronize());
     hs.free_buffers();
@@ -931,12 +987,12 @@ static int run_host_impl(MrviHandle* h, int64_t n_cells, const float* X, int x_e
         hs.dpack_bytes = (size_t)ch * G * 2;
       }
       if (use_pack && !hs.pack_unavailable) {
-        if (cudaHostAlloc((void**)&hs.hpack[b], (size_t)ch * G * 2, cudaHostAllocDefault) != cudaSuccess) {
+        if (cudaHostAlloc((void**)&hs.hpack[b], (size_t)ch * G * pack_elem, cudaHostAllocDefault) != cudaSuccess) {
           cudaGetLastError();          // no pinned memory to spare: the narrowing is an optimisation, not a requirement
           hs.hpack[b] = nullptr;
           hs.pack_unavailable = true;
         } else {
-          hs.pack_bytes = (size_t)ch * G * 2;
+          hs.pack_bytes = (size_t)ch * G * pack_elem;
         }
       }
       hs.csr_ptr[b] = nullptr; hs.csr_idx[b] = nullptr; hs.csr_val[b] = nullptr;
@@ -961,6 +1017,8 @@ static int run_host_impl(MrviHandle* h, int64_t n_cells, const float* X, int x_e
     hs.chunk = ch; hs.n_keys = n_keys; hs.has_cell = cell_out != nullptr; hs.has_z = z_out != nullptr; hs.has_u = u_out != nullptr;
   }
   ch = std::min(ch, hs.chunk);
+  if (int_in && (hs.pack_unavailable || !hs.hpack[0] || !hs.hpack[1]))
+    return fail(MRVI_ERR_CUDA, "no pinned host memory for the staging of an int32 / int64 count matrix");
   for (int k = 0; k < n_keys; ++k)
     CUDA_TRY(cudaMemsetAsync(hs.sums[k], 0, (size_t)n_groups[k] * S * S * sizeof(double), hs.s_comp));
   h->ev_used = 0;
@@ -990,6 +1048,18 @@ static int run_host_impl(MrviHandle* h, int64_t n_cells, const float* X, int x_e
                                    (size_t)G * x_elem, (size_t)m, cudaMemcpyHostToDevice, hs.s_h2d));
       pack_mode[b] = x_elem;
       h->last_h2d_bytes += (int64_t)m * G * x_elem;
+    } else if (int_in) {
+      if (c >= 2) CUDA_TRY(cudaEventSynchronize(hs.ev_h2d[b]));  // the copy of chunk c-2 has left the pinned staging buffer
+      const int mode = narrow_counts_int(*hs.pool, reinterpret_cast<const uint8_t*>(X) + (size_t)lo * ldx * x_elem, x_elem, ldx, m, G, hs.hpack[b]);
+      if (mode == 4) {  // negative or >= 65536 somewhere: the chunk travels as the float32 values the loader would hand
+        CUDA_TRY(cudaMemcpyAsync(hs.X[b], hs.hpack[b], (size_t)m * G * sizeof(float), cudaMemcpyHostToDevice, hs.s_h2d));
+        pack_mode[b] = 0;
+        h->last_h2d_bytes += (int64_t)m * G * 4;
+      } else {
+        CUDA_TRY(cudaMemcpyAsync(hs.dpack[b], hs.hpack[b], (size_t)m * G * mode, cudaMemcpyHostToDevice, hs.s_h2d));
+        pack_mode[b] = mode;
+        h->last_h2d_bytes += (int64_t)m * G * mode;
+      }
     } else {
       int narrow = 0;
       // The narrowing pays only if the host reads X faster than PCIe would carry it raw (~47 GB/s measured): keep it
@@ -1067,7 +1137,7 @@ int mrvi_run_host(MrviHandle* h, int64_t n_cells, const float* X, int64_t ldx, c
                   int32_t n_keys, const int32_t* const* group_codes, const int32_t* n_groups, int32_t norm,
                   float* cell_out, double* const* group_sums, int64_t* const* group_counts, float* z_out,
                   float* u_out, int64_t chunk_cells) {
-  return run_host_impl(h, n_cells, X, 4, ldx, nullptr, nullptr, nullptr, sample_idx, n_keys, group_codes, n_groups, norm, cell_out,
+  return run_host_impl(h, n_cells, X, 0, ldx, nullptr, nullptr, nullptr, sample_idx, n_keys, group_codes, n_groups, norm, cell_out,
                        group_sums, group_counts, z_out, u_out, chunk_cells);
 }
 
@@ -1075,8 +1145,8 @@ int mrvi_run_host_counts(MrviHandle* h, int64_t n_cells, const void* X, int32_t 
                          int32_t n_keys, const int32_t* const* group_codes, const int32_t* n_groups, int32_t norm,
                          float* cell_out, double* const* group_sums, int64_t* const* group_counts, float* z_out,
                          float* u_out, int64_t chunk_cells) {
-  if (x_dtype != MRVI_X_UINT8 && x_dtype != MRVI_X_UINT16) return fail(MRVI_ERR_INVALID_ARG, "x_dtype must be MRVI_X_UINT8 or MRVI_X_UINT16");
-  return run_host_impl(h, n_cells, reinterpret_cast<const float*>(X), x_dtype == MRVI_X_UINT8 ? 1 : 2, ldx, nullptr, nullptr, nullptr,
+  if (x_dtype < MRVI_X_UINT8 || x_dtype > MRVI_X_INT64) return fail(MRVI_ERR_INVALID_ARG, "x_dtype must be one of MrviXDtype");
+  return run_host_impl(h, n_cells, reinterpret_cast<const float*>(X), x_dtype, ldx, nullptr, nullptr, nullptr,
                        sample_idx, n_keys, group_codes, n_groups, norm, cell_out, group_sums, group_counts, z_out, u_out, chunk_cells);
 }
 
@@ -1085,7 +1155,7 @@ int mrvi_run_host_csr(MrviHandle* h, int64_t n_cells, const int64_t* indptr, con
                       int32_t norm, float* cell_out, double* const* group_sums, int64_t* const* group_counts, float* z_out,
                       float* u_out, int64_t chunk_cells) {
   if (!indptr) return fail(MRVI_ERR_INVALID_ARG, "indptr is null");
-  return run_host_impl(h, n_cells, nullptr, 4, h ? h->dims.n_input : 0, indptr, indices, data, sample_idx, n_keys, group_codes, n_groups,
+  return run_host_impl(h, n_cells, nullptr, 0, h ? h->dims.n_input : 0, indptr, indices, data, sample_idx, n_keys, group_codes, n_groups,
                        norm, cell_out, group_sums, group_counts, z_out, u_out, chunk_cells);
 }
 
@@ -1098,6 +1168,9 @@ int mrvi_run_sampled_host(MrviHandle* h, int64_t n_cells, const float* X, int64_
                                group_codes, n_groups, norm, normalize, cell_out, group_sums, group_counts, z_out, chunk_cells);
 }
 
+#ifdef MRVI_DBG_F3
+int mrvi_dbg_f3_read(long long* out, int n) { return (int)cudaMemcpyFromSymbol(out, mrvi::g_dbg_f3, sizeof(long long) * n); }
+#endif
 #ifdef MRVI_DBG_ENC
 int mrvi_dbg_enc_read(long long* out, int n) { return (int)cudaMemcpyFromSymbol(out, mrvi::g_dbg_enc, sizeof(long long) * n); }
 #endif
@@ -1113,6 +1186,66 @@ int mrvi_narrow_counts(const float* X, int64_t ldx, int64_t n_rows, int32_t n_co
   if (!X || !out || n_rows < 0 || n_cols <= 0 || ldx < n_cols) return fail(MRVI_ERR_INVALID_ARG, "mrvi_narrow_counts: bad argument");
   PackPool pool(std::max(1, (int)n_threads));
   return narrow_counts(pool, X, ldx, n_rows, n_cols, out);
+}
+
+int mrvi_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int mrvi_alloc_pinned(int64_t bytes, void** out) {
+  if (!out || bytes < 0) return fail(MRVI_ERR_INVALID_ARG, "mrvi_alloc_pinned: bad argument");
+  *out = nullptr;
+  CUDA_TRY(cudaHostAlloc(out, (size_t)std::max<int64_t>(bytes, 16), cudaHostAllocPortable));
+  return 0;
+}
+
+int mrvi_free_pinned(void* p) {
+  if (p) CUDA_TRY(cudaFreeHost(p));
+  return 0;
+}
+
+int mrvi_comm_unique_id(void* out128) {
+  if (!out128) return fail(MRVI_ERR_INVALID_ARG, "mrvi_comm_unique_id: null argument");
+  NcclApi& api = nccl_api();
+  if (!api.ok) return fail(MRVI_ERR_UNSUPPORTED, "libnccl.so.2 could not be loaded");
+  NcclApi::UniqueId id;
+  NCCL_TRY(api.GetUniqueId(&id));
+  memcpy(out128, id.internal, 128);
+  return 0;
+}
+
+int mrvi_comm_create(MrviHandle* h, const void* id128, int32_t n_ranks, int32_t rank) {
+  if (!h || !id128 || n_ranks <= 0 || rank < 0 || rank >= n_ranks) return fail(MRVI_ERR_INVALID_ARG, "mrvi_comm_create: bad argument");
+  NcclApi& api = nccl_api();
+  if (!api.ok) return fail(MRVI_ERR_UNSUPPORTED, "libnccl.so.2 could not be loaded");
+  CUDA_TRY(cudaSetDevice(h->device));
+  if (h->nccl_comm) { api.CommDestroy(h->nccl_comm); h->nccl_comm = nullptr; }
+  NcclApi::UniqueId id;
+  memcpy(id.internal, id128, 128);
+  NCCL_TRY(api.CommInitRank(&h->nccl_comm, n_ranks, id, rank));
+  return 0;
+}
+
+int mrvi_allreduce_groups(MrviHandle* h, void* nccl_comm, int32_t n_keys, double* const* group_sums, const int32_t* n_groups,
+                          void* stream) {
+  if (!h || n_keys < 0 || n_keys > kMaxKeys || (n_keys > 0 && (!group_sums || !n_groups)))
+    return fail(MRVI_ERR_INVALID_ARG, "mrvi_allreduce_groups: bad argument");
+  void* comm = nccl_comm ? nccl_comm : h->nccl_comm;
+  if (!comm) return fail(MRVI_ERR_INVALID_ARG, "mrvi_allreduce_groups: no communicator (pass one or call mrvi_comm_create)");
+  NcclApi& api = nccl_api();
+  if (!api.ok) return fail(MRVI_ERR_UNSUPPORTED, "libnccl.so.2 could not be loaded");
+  CUDA_TRY(cudaSetDevice(h->device));
+  const size_t SS = (size_t)h->dims.n_sample * h->dims.n_sample;
+  NCCL_TRY(api.GroupStart());
+  for (int k = 0; k < n_keys; ++k) {
+    if (!group_sums[k] || n_groups[k] <= 0) { api.GroupEnd(); return fail(MRVI_ERR_INVALID_ARG, "group key %d: null pointer or n_groups <= 0", k); }
+    NCCL_TRY(api.AllReduce(group_sums[k], group_sums[k], (size_t)n_groups[k] * SS, /*ncclDouble*/ 8, /*ncclSum*/ 0, comm,
+                           static_cast<cudaStream_t>(stream)));
+  }
+  NCCL_TRY(api.GroupEnd());
+  return 0;
 }
 
 int mrvi_last_stage_ms(MrviHandle* h, float out_ms[4]) {

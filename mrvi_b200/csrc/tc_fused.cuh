@@ -260,6 +260,70 @@ __device__ __forceinline__ void ep32(uint32_t t_lane32, int half, int r, int wg,
   }
 }
 
+// LayerNorm + gelu of the 32-wide accumulator stored as two halves [A.W_hi | A.W_lo] (columns [0,32) / [32,64) of the D2
+// region, see TcOp): this thread's 16 columns -> two 16-byte K chunks (hi and lo) of the next A operand in shared memory.
+__device__ __forceinline__ void ep32x(uint32_t t_d2_lane, int half, int r, int wg, const float* g_s, const float* b_s, float2* xch,
+                                      uint8_t* row_h, uint8_t* row_l) {
+  float v[16], w[16];
+  tmem_ld16(t_d2_lane + half * 16, v);
+  tmem_ld16(t_d2_lane + 32 + half * 16, w);
+  tmem_ld_wait();
+  float2 a1 = make_float2(0.f, 0.f), a2 = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float2 x = __fadd2_rn(make_float2(v[2 * i], v[2 * i + 1]), make_float2(w[2 * i], w[2 * i + 1]));
+    v[2 * i] = x.x; v[2 * i + 1] = x.y;
+    a1 = __fadd2_rn(a1, x);
+    a2 = __ffma2_rn(x, x, a2);
+  }
+  float s1 = a1.x + a1.y, s2 = a2.x + a2.y;
+  xch[half * 128 + r] = make_float2(s1, s2);
+  wg_sync(wg);
+  const float2 o = xch[(half ^ 1) * 128 + r];
+  s1 += o.x; s2 += o.y;
+  const float mean = s1 * (1.0f / 32);
+  const float var = fmaxf(fmaf(s2, 1.0f / 32, -mean * mean), 0.f);
+  const float rstd = rsqrt_approx(var + kLnEps);
+  const float2 rs2 = make_float2(rstd, rstd), nb2 = make_float2(-mean * rstd, -mean * rstd);
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int i0 = c * 8 + 2 * j;
+      const float2 gg = *reinterpret_cast<const float2*>(g_s + half * 16 + i0);
+      const float2 bb = *reinterpret_cast<const float2*>(b_s + half * 16 + i0);
+      float2 x = __ffma2_rn(make_float2(v[i0], v[i0 + 1]), rs2, nb2);
+      x = gelu_fast2(__ffma2_rn(x, gg, bb));
+      split2v(x, h[j], l[j]);
+    }
+    *reinterpret_cast<uint4*>(row_h + (half * 2 + c) * 2048) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(row_l + (half * 2 + c) * 2048) = make_uint4(l[0], l[1], l[2], l[3]);
+  }
+}
+
+// [128 x 128] (A in TMEM, chunked [hi16 | lo16] layout) x concatenated [128 x (32 | 32)]: T_hi.[W_hi | W_lo] as ONE N = 64
+// instruction per K slice + T_lo.W_hi (N = 32): 16 MMAs instead of 24 (an MMA costs ~42 clk for N <= 64 whatever N)
+__device__ __forceinline__ void issue_gemm_ts2_cat(uint32_t d_tmem, uint32_t a_tmem, uint32_t s_w, const TcOp& b, uint32_t idesc64, uint32_t idesc32) {
+#pragma unroll
+  for (int ks = 0; ks < 8; ++ks) {
+    const uint64_t bd = umma_desc(s_w + b.h + ks * 2 * b.lbo, b.lbo, 128);
+    const uint32_t a = a_tmem + (ks >> 1) * 32 + (ks & 1) * 8;
+    umma_f16_ts(d_tmem, a, bd, idesc64, ks == 0 ? 0u : 1u);
+    umma_f16_ts(d_tmem, a + 16, bd, idesc32, 1u);
+  }
+}
+// [128 x K] (hi, lo in shared memory) x concatenated [K x (32 | 32)], accumulating: A_hi.[W_hi | W_lo] + A_lo.W_hi
+__device__ __forceinline__ void issue_gemm_cat(uint32_t d_tmem, uint32_t a_h, uint32_t a_l, uint32_t s_w, const TcOp& b, int K, int K_lo,
+                                               uint32_t idesc64, uint32_t idesc32) {
+  const uint32_t a_lbo = 128 * 16;
+  for (int ks = 0; ks < K / 16; ++ks) {
+    const uint64_t bd = umma_desc(s_w + b.h + ks * 2 * b.lbo, b.lbo, 128);
+    umma_f16(d_tmem, umma_desc(a_h + ks * 2 * a_lbo, a_lbo, 128), bd, idesc64, 1u);
+    if (ks * 16 < K_lo) umma_f16(d_tmem, umma_desc(a_l + ks * 2 * a_lbo, a_lbo, 128), bd, idesc32, 1u);
+  }
+}
+
 // [128 x 128] (A in TMEM, chunked [hi16|lo16] layout) x [128 x N], weights (hi, lo): Ah.Wh + Al.Wh + Ah.Wl
 __device__ __forceinline__ void issue_gemm_ts2(uint32_t d_tmem, uint32_t a_tmem, uint32_t s_w, const TcOp& b, uint32_t idesc) {
 #pragma unroll
@@ -336,10 +400,10 @@ k_chain_fused_tc(const __grid_constant__ TcNet tc, CellBuf cb, int64_t n_cells, 
   }
   const float *g1 = lnv, *b1 = lnv + 128, *g2 = lnv + 256, *b2 = lnv + 288, *g3 = lnv + 320, *b3 = lnv + 448,
               *g4 = lnv + 576, *b4 = lnv + 608;
-  // TMEM columns: warpgroup g: [g*160, +128) = D1/T/D3/T/D5/Gram, [g*160+128, +32) = D2/D4; accumulator [320, 448)
-  const uint32_t t_r0 = tmem_base + wg * 160, t_d2 = t_r0 + 128;
+  // TMEM columns: warpgroup g: [g*192, +128) = D1/T/D3/T/D5/Gram, [g*192+128, +64) = D2/D4 as [A.W_hi | A.W_lo]; accumulator [384, 512)
+  const uint32_t t_r0 = tmem_base + wg * 192, t_d2 = t_r0 + 128;
   const uint32_t lane_off = (uint32_t)(warp_q * 32) << 16;
-  const uint32_t t_lane = t_r0 + lane_off, t_d2_lane = t_d2 + lane_off, t_acc_lane = tmem_base + 320 + lane_off;
+  const uint32_t t_lane = t_r0 + lane_off, t_d2_lane = t_d2 + lane_off, t_acc_lane = tmem_base + 384 + lane_off;
   uint8_t* scratch = smem + sm.wg[wg];
   const uint32_t s_w = smem_u32(smem + sm.w);
   const uint32_t s_a1h = smem_u32(scratch), s_a1l = s_a1h + sm.off_a1l, s_a3h = s_a1h + sm.off_a3h, s_a3l = s_a1h + sm.off_a3l;
@@ -355,10 +419,18 @@ k_chain_fused_tc(const __grid_constant__ TcNet tc, CellBuf cb, int64_t n_cells, 
   float* nrm_s = reinterpret_cast<float*>(smem + sm.nrm[wg]);
   float2* xch = reinterpret_cast<float2*>(smem + sm.xch[wg]);
   uint64_t* bar_mma = &ctrl->bar_mma[wg];
-  const uint32_t idesc128 = umma_idesc_f16(128), idesc32 = umma_idesc_f16(32), idescN5 = umma_idesc_f16(tc.N5);
+  const uint32_t idesc128 = umma_idesc_f16(128), idesc64 = umma_idesc_f16(64), idesc32 = umma_idesc_f16(32), idescN5 = umma_idesc_f16(tc.N5);
   uint32_t phase = 0;
   const bool need_dist = (cell_out != nullptr) || (gp.n_keys > 0);
-  const bool issuer = wt == 0;
+  const bool issuer = wt == 0;   // lock / run-state bookkeeping of the warpgroup
+  // MMA issue: the first warp of each warpgroup, as a warp-uniform branch with elect.sync inside (see elect_one); every
+  // address the issue code uses is derived from the shuffled (= provably uniform) warp index
+  const int warp_u = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const bool issue_warp = (warp_u & 7) == 0;
+  const uint32_t iu_tr0 = __shfl_sync(0xffffffffu, tmem_base, 0) + (uint32_t)(warp_u >> 3) * 192u, iu_td2 = iu_tr0 + 128u;
+  const uint32_t iu_a1h = smem_u32(smem + sm.wg[warp_u >> 3]), iu_a1l = iu_a1h + sm.off_a1l, iu_a3h = iu_a1h + sm.off_a3h,
+                 iu_a3l = iu_a1h + sm.off_a3l, iu_zh = iu_a1h + sm.off_zh, iu_zl = iu_a1h + sm.off_zl;
+  uint64_t* iu_bar = &ctrl->bar_mma[warp_u >> 3];
 
   // static row -> (local cell, sample) map of this thread
   const int lc = r / S, s = r - lc * S, c0 = lc * S;
@@ -411,13 +483,16 @@ k_chain_fused_tc(const __grid_constant__ TcNet tc, CellBuf cb, int64_t n_cells, 
         kv2[2 * q + 1] = make_float2(t4.z, t4.w);
       }
       const float rmax = __ldg(tc.kvref + ss * 2), rmin = __ldg(tc.kvref + ss * 2 + 1);
-      const float* qp = cb.q_tok + fi * 16;
+      const float2* qp = reinterpret_cast<const float2*>(cb.q_tok + fi * 16);
+      float2 qn = __ldg(qp);
 #pragma unroll 1
       for (int it = 0; it < 8; ++it) {  // one packed word (two features) per iteration
         float mm[2];
+        const float2 qc = qn;
+        if (it < 7) qn = __ldg(qp + it + 1);   // the next pair's tokens travel while this pair's 32 exponentials run
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-          const float t = fmaf(a_h, __ldg(qp + it * 2 + e), b_h);
+          const float t = fmaf(a_h, e ? qc.y : qc.x, b_h);
           const float off = -t * (t >= 0.f ? rmax : rmin);  // exponent <= 0 for every j
           const float2 t2 = make_float2(t, t), off2 = make_float2(off, off);
           float2 den = make_float2(0.f, 0.f), num = make_float2(0.f, 0.f);
@@ -459,10 +534,13 @@ k_chain_fused_tc(const __grid_constant__ TcNet tc, CellBuf cb, int64_t n_cells, 
     wg_sync(wg);
 
     // ================= GEMM1 / epilogue 1 =================
-    if (issuer) {
+    if (issue_warp) {
       tc_fence_after();
-      issue_gemm(t_r0, s_a1h, s_a1l, s_w, tc.b1, tc.K1, 32, idesc128, true);
-      umma_commit(bar_mma);
+      if (elect_one()) {
+        issue_gemm(iu_tr0, iu_a1h, iu_a1l, s_w, tc.b1, tc.K1, 32, idesc128, true);
+        umma_commit(iu_bar);
+      }
+      __syncwarp();
     }
     mbar_wait(bar_mma, phase); phase ^= 1;
     tc_fence_after();
@@ -470,23 +548,29 @@ k_chain_fused_tc(const __grid_constant__ TcNet tc, CellBuf cb, int64_t n_cells, 
     tc_fence_before();
     wg_sync(wg);
     // ================= GEMM2 / epilogue 2 =================
-    if (issuer) {
+    if (issue_warp) {
       tc_fence_after();
-      issue_gemm_ts2(t_d2, t_r0, s_w, tc.b2t, idesc32);
-      issue_gemm(t_d2, s_a1h, s_a1l, s_w, tc.b2a, tc.K1, 32, idesc32, false);
-      umma_commit(bar_mma);
+      if (elect_one()) {
+        issue_gemm_ts2_cat(iu_td2, iu_tr0, s_w, tc.b2t, idesc64, idesc32);
+        issue_gemm_cat(iu_td2, iu_a1h, iu_a1l, s_w, tc.b2a, tc.K1, 32, idesc64, idesc32);
+        umma_commit(iu_bar);
+      }
+      __syncwarp();
     }
     mbar_wait(bar_mma, phase); phase ^= 1;
     tc_fence_after();
-    ep32(t_d2_lane, half, r, wg, g2, b2, xch, row_a3h, row_a3l);
+    ep32x(t_d2_lane, half, r, wg, g2, b2, xch, row_a3h, row_a3l);
     tc_fence_before();
     fence_proxy_async();
     wg_sync(wg);
     // ================= GEMM3 / epilogue 3 =================
-    if (issuer) {
+    if (issue_warp) {
       tc_fence_after();
-      issue_gemm(t_r0, s_a3h, s_a3l, s_w, tc.b3, tc.K3, tc.K3, idesc128, true);
-      umma_commit(bar_mma);
+      if (elect_one()) {
+        issue_gemm(iu_tr0, iu_a3h, iu_a3l, s_w, tc.b3, tc.K3, tc.K3, idesc128, true);
+        umma_commit(iu_bar);
+      }
+      __syncwarp();
     }
     mbar_wait(bar_mma, phase); phase ^= 1;
     tc_fence_after();
@@ -494,24 +578,30 @@ k_chain_fused_tc(const __grid_constant__ TcNet tc, CellBuf cb, int64_t n_cells, 
     tc_fence_before();
     wg_sync(wg);
     // ================= GEMM4 / epilogue 4 =================
-    if (issuer) {
+    if (issue_warp) {
       tc_fence_after();
-      issue_gemm_ts2(t_d2, t_r0, s_w, tc.b4t, idesc32);
-      issue_gemm(t_d2, s_a3h, s_a3l, s_w, tc.b4a, tc.K3, tc.K3, idesc32, false);
-      umma_commit(bar_mma);
+      if (elect_one()) {
+        issue_gemm_ts2_cat(iu_td2, iu_tr0, s_w, tc.b4t, idesc64, idesc32);
+        issue_gemm_cat(iu_td2, iu_a3h, iu_a3l, s_w, tc.b4a, tc.K3, tc.K3, idesc64, idesc32);
+        umma_commit(iu_bar);
+      }
+      __syncwarp();
     }
     mbar_wait(bar_mma, phase); phase ^= 1;
     tc_fence_after();
     // A5 = [t4 | 1 | 0] reuses the A1 buffers (GEMM2 was their last reader); the one / zero columns are still in place
-    ep32(t_d2_lane, half, r, wg, g4, b4, xch, row_a1h, row_a1l);
+    ep32x(t_d2_lane, half, r, wg, g4, b4, xch, row_a1h, row_a1l);
     tc_fence_before();
     fence_proxy_async();
     wg_sync(wg);
     // ================= GEMM5 / residual rows =================
-    if (issuer) {
+    if (issue_warp) {
       tc_fence_after();
-      issue_gemm(t_r0, s_a1h, s_a1l, s_w, tc.b5, tc.K5, 32, idescN5, true);
-      umma_commit(bar_mma);
+      if (elect_one()) {
+        issue_gemm(iu_tr0, iu_a1h, iu_a1l, s_w, tc.b5, tc.K5, 32, idescN5, true);
+        umma_commit(iu_bar);
+      }
+      __syncwarp();
     }
     mbar_wait(bar_mma, phase); phase ^= 1;
     tc_fence_after();
@@ -601,16 +691,19 @@ k_chain_fused_tc(const __grid_constant__ TcNet tc, CellBuf cb, int64_t n_cells, 
     fence_proxy_async();
     wg_sync(wg);
     // ================= Gram on the tensor cores =================
-    if (issuer) {
+    if (issue_warp) {
       tc_fence_after();
-      const uint32_t lbo = 128 * 16;
-      for (int ks = 0; ks < Kz / 16; ++ks) {
-        const uint64_t dh = umma_desc(s_zh + ks * 2 * lbo, lbo, 128), dl = umma_desc(s_zl + ks * 2 * lbo, lbo, 128);
-        umma_f16(t_r0, dh, dh, idesc128, ks == 0 ? 0u : 1u);
-        umma_f16(t_r0, dh, dl, idesc128, 1u);
-        umma_f16(t_r0, dl, dh, idesc128, 1u);
+      if (elect_one()) {
+        const uint32_t lbo = 128 * 16;
+        for (int ks = 0; ks < Kz / 16; ++ks) {
+          const uint64_t dh = umma_desc(iu_zh + ks * 2 * lbo, lbo, 128), dl = umma_desc(iu_zl + ks * 2 * lbo, lbo, 128);
+          umma_f16(iu_tr0, dh, dh, idesc128, ks == 0 ? 0u : 1u);
+          umma_f16(iu_tr0, dh, dl, idesc128, 1u);
+          umma_f16(iu_tr0, dl, dh, idesc128, 1u);
+        }
+        umma_commit(iu_bar);
       }
-      umma_commit(bar_mma);
+      __syncwarp();
     }
     const float n_i = xch[r].x + xch[128 + r].x;
     if (half == 0) nrm_s[r] = n_i;

@@ -74,6 +74,7 @@ struct TcNet {
   int sm_count = 148;
   size_t smem_bytes = 0;
   size_t fused_smem_bytes = 0;  // 0: fused kernel unavailable for this shape
+  size_t fused3_smem_bytes = 0; // 0: warp-specialised fused kernel (tc_fused3.cuh) unavailable for this shape
   bool ready = false;
 };
 
@@ -187,6 +188,14 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, ui
       : "memory");
 }
 
+// one lane of a converged warp (elect.sync): `if (warp_uniform_condition) { if (elect_one()) { tcgen05.mma ... } }` lets
+// the compiler keep the MMA descriptors in uniform registers -- issued from `if (lane == 0)` code every UTCHMMA is
+// wrapped in an ELECT / R2UR waterfall loop and costs ~92 clk instead of 42-61 (tools/mma_microbench.cu)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
