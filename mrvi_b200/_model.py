@@ -133,9 +133,22 @@ class MrVI:
     def _sample_codes(self, adata) -> np.ndarray:
         """Sample label -> code through the registered mapping (scvi ``_validate_anndata`` + CategoricalObsField)."""
         col = adata.obs[self.sample_key]
-        codes = pd.Categorical(col, categories=list(self.sample_order)).codes
-        if (codes < 0).any():
-            bad = pd.unique(np.asarray(col)[codes < 0])[:5]
+        order = self.sample_order
+        vals = col.to_numpy() if not isinstance(col.dtype, pd.CategoricalDtype) else None
+        if (vals is not None and vals.dtype.kind in "iu" and order.dtype.kind in "iu"
+                and np.array_equal(order, np.arange(len(order)))):
+            codes = vals.astype(np.int64, copy=False)   # labels ARE the codes: one range check instead of a hash pass
+            bad_mask = (codes < 0) | (codes >= len(order))
+        else:
+            if vals is None:   # categorical column: translate the category table, then one table look-up per cell
+                lut = pd.Index(order).get_indexer(col.cat.categories)
+                old = col.cat.codes.to_numpy()
+                codes = np.where(old >= 0, lut[np.maximum(old, 0)], -1)
+            else:
+                codes = pd.Index(order).get_indexer(vals)
+            bad_mask = codes < 0
+        if bad_mask.any():
+            bad = pd.unique(np.asarray(col)[bad_mask])[:5]
             raise ValueError(f"Category {list(bad)} not found in source registry for sample key {self.sample_key!r}.")
         return np.asarray(codes, dtype=np.int32)
 
@@ -256,7 +269,10 @@ class MrVI:
         if any(r.input == "mean_representations" for r in reqs.grouped_reductions):
             return self._compute_generic(reductions, adata, idx, Xh, sample_codes, batch_size, norm)
         res = self._run_sharded(Xh, sample_codes, [p[0] for p in plans], [len(p[1]) for p in plans], norm, keep_cell, want_z)
-        cell_names = self.adata.obs_names[idx].values
+        # (cell coordinates only when a per-cell output exists: indexing 10^6 string labels is milliseconds of pure overhead)
+        cell_names = None
+        if reqs.ungrouped_reductions:
+            cell_names = self.adata.obs_names.values if (whole and self.adata.n_obs == len(idx)) else self.adata.obs_names[idx].values
         final = OrderedDict()
         for ur in reqs.ungrouped_reductions:
             if ur.input == "mean_distances":

@@ -217,21 +217,31 @@ k_dist_gram_tc(const float* __restrict__ z, int64_t n_cells, int S, int L, float
   // (descriptor of address a + off = descriptor of a + (off >> 4): the address field holds a >> 4 and cannot carry
   //  out of its 14 bits for shared-memory addresses)
   const uint64_t dbase0 = umma_desc(smem_u32(smem + sm.z[0]), kDistLbo, 128), dbase1 = umma_desc(smem_u32(smem + sm.z[1]), kDistLbo, 128);
-  auto issue_block = [&](int g_, int buf, int bi, int bj) {
+  auto issue_block = [&](int g_, int buf, int bi, int bj, uint32_t tb) {
     // only the 14-bit address field (low word) differs between the descriptors
     const uint32_t hi = (uint32_t)(dbase0 >> 32);
     const uint32_t lo_h = (uint32_t)(buf ? dbase1 : dbase0), lo_l = lo_h + (zbytes >> 4);
     const uint32_t a16 = (uint32_t)bi * 128u, b16 = (uint32_t)bj * 128u + (uint32_t)g_ * 64u;  // row offsets, 16-byte units
     uint32_t ah = lo_h + a16, al = lo_l + a16, bh = lo_h + b16, bl = lo_l + b16;
-    const uint32_t d = tmem_base + g_ * 64;
+    const uint32_t d = tb + g_ * 64;
     auto mk = [hi](uint32_t lo) { return ((uint64_t)hi << 32) | lo; };
+    // cross terms first, the hi.hi term last: entries (i, j) and (j, i) of the diagonal blocks then differ by one ulp in rare
+    // cases only (see the Gram issue of tc_fused.cuh)
+    const uint32_t ah0 = ah, bh0 = bh;
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
       if (ks < Kz / 16) {
-        umma_f16(d, mk(ah), mk(bh), idesc64, ks == 0 ? 0u : 1u);
-        umma_f16(d, mk(ah), mk(bl), idesc64, 1u);
+        umma_f16(d, mk(ah), mk(bl), idesc64, ks == 0 ? 0u : 1u);
         umma_f16(d, mk(al), mk(bh), idesc64, 1u);
         ah += 2u * (kDistLbo >> 4); al += 2u * (kDistLbo >> 4); bh += 2u * (kDistLbo >> 4); bl += 2u * (kDistLbo >> 4);  // two K chunks per 16-wide slice
+      }
+    }
+    ah = ah0; bh = bh0;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      if (ks < Kz / 16) {
+        umma_f16(d, mk(ah), mk(bh), idesc64, 1u);
+        ah += 2u * (kDistLbo >> 4); bh += 2u * (kDistLbo >> 4);
       }
     }
     umma_commit(&bar_mma[g_]);
@@ -271,13 +281,19 @@ k_dist_gram_tc(const float* __restrict__ z, int64_t n_cells, int S, int L, float
   };
 
   if (!worker) {
-    // ================= issuer warps: one thread each; warp 16 -> warpgroup 0 + the bulk copies of z, warp 17 -> warpgroup 1
-    if ((tid & 31) == 0) {
-      const int g_ = (tid - kDistTcWorkers) >> 5;
+    // ================= issuer warps: warp 16 -> warpgroup 0 + the bulk copies of z, warp 17 -> warpgroup 1.  The branch is
+    // warp-uniform (warp index through a shuffle) with elect.sync around the MMAs / copies: issued from `if (lane == 0)`
+    // code every tcgen05.mma costs ~92 clk instead of 42-61 (see elect_one in tc_kernels.cuh)
+    {
+      const int g_ = __shfl_sync(0xffffffffu, (tid - kDistTcWorkers) >> 5, 0);
+      const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
       auto tma = [&](int64_t p) {
         if (!use_tma || g_ != 0) return;
-        mbar_expect_tx(bar_z, zcell_bytes);
-        bulk_g2s(stage, cell_src(p), zcell_bytes, bar_z);
+        if (elect_one()) {
+          mbar_expect_tx(bar_z, zcell_bytes);
+          bulk_g2s(stage, cell_src(p), zcell_bytes, bar_z);
+        }
+        __syncwarp();
       };
       uint32_t ops_phase = 0, free_phase = 1;  // a fresh mbarrier passes a wait on parity 1
       tma(p0);
@@ -290,7 +306,8 @@ k_dist_gram_tc(const float* __restrict__ z, int64_t n_cells, int S, int L, float
           mbar_wait(&bar_free[g_], free_phase); free_phase ^= 1;
           tc_fence_after();
           if (g_ == 0) DBG_STAMP(p - p0, 0 + 2 * b);
-          issue_block(g_, buf, b == 2 ? 1 : 0, b == 0 ? 0 : 1);
+          if (elect_one()) issue_block(g_, buf, b == 2 ? 1 : 0, b == 0 ? 0 : 1, tb);
+          __syncwarp();
           if (g_ == 0) DBG_STAMP(p - p0, 1 + 2 * b);
         }
         if (p + 1 < p1) {

@@ -220,6 +220,8 @@ k_encoder_tc(const float* __restrict__ X, int64_t ldx, const int32_t* __restrict
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base_t = tmem_base;
+  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);   // provably warp-uniform (MMA issue branches)
 
   if (TMAX && warp < 8) {
     // ------------------------------------------------------------ converters: raw X stage -> (hi, lo) A stage
@@ -427,10 +429,12 @@ k_encoder_tc(const float* __restrict__ X, int64_t ldx, const int32_t* __restrict
       tc_fence_before();
       asm volatile("bar.sync 1, 256;" ::: "memory");  // head's TMEM reads are done before the next tile reuses T
     }
-  } else if (warp == 16) {
-    // ------------------------------------------------------------ phase-1 MMA issuer
-    if (lane == 0) {
+  } else if (warp_u == 16) {
+    // ------------------------------------------------------------ phase-1 MMA issuer (warp-uniform branch, elect.sync
+    // around the MMAs: 42-61 clk per tcgen05.mma instead of ~92 from `if (lane == 0)` code, see elect_one)
+    {
       const uint32_t idesc = umma_idesc_f16(128);
+      const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_t, 0);
       int64_t g = 0;
       for (int64_t ti = 0; ti < my_tiles; ++ti) {
         const uint32_t t_acc = tmem_base + (uint32_t)(ti & 1) * 128;
@@ -446,27 +450,32 @@ k_encoder_tc(const float* __restrict__ X, int64_t ldx, const int32_t* __restrict
           const uint32_t a_h = TMAX ? smem_u32(aring + (size_t)s * 2 * kEncAHalf) : smem_u32(smem + s * kEncStageBytes);
           const uint32_t a_l = a_h + kEncAHalf;
           const uint32_t b_h = TMAX ? smem_u32(w0ring + (size_t)sw * kEncBBytes) : a_h + 2 * kEncAHalf, b_l = b_h + 4 * 2048;
+          if (elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < 2; ++ks) {
-            const uint64_t ah = umma_desc(a_h + ks * 2 * kEncALbo, kEncALbo, 128);
-            const uint64_t al = umma_desc(a_l + ks * 2 * kEncALbo, kEncALbo, 128);
-            const uint64_t bh = umma_desc(b_h + ks * 2 * 2048, 2048, 128);
-            const uint64_t bl = umma_desc(b_l + ks * 2 * 2048, 2048, 128);
-            umma_f16(t_acc, ah, bh, idesc, (kb | ks) ? 1u : 0u);
-            umma_f16(t_acc, al, bh, idesc, 1u);
-            umma_f16(t_acc, ah, bl, idesc, 1u);
+            for (int ks = 0; ks < 2; ++ks) {
+              const uint64_t ah = umma_desc(a_h + ks * 2 * kEncALbo, kEncALbo, 128);
+              const uint64_t al = umma_desc(a_l + ks * 2 * kEncALbo, kEncALbo, 128);
+              const uint64_t bh = umma_desc(b_h + ks * 2 * 2048, 2048, 128);
+              const uint64_t bl = umma_desc(b_l + ks * 2 * 2048, 2048, 128);
+              umma_f16(t_acc, ah, bh, idesc, (kb | ks) ? 1u : 0u);
+              umma_f16(t_acc, al, bh, idesc, 1u);
+              umma_f16(t_acc, ah, bl, idesc, 1u);
+            }
+            umma_commit(empty + s);
+            if (TMAX) umma_commit(w_empty + sw);
           }
-          umma_commit(empty + s);
-          if (TMAX) umma_commit(w_empty + sw);
+          __syncwarp();
           ENC_STAMP(g, 8);
         }
-        umma_commit(acc_full + (ti & 1));
+        if (elect_one()) umma_commit(acc_full + (ti & 1));
+        __syncwarp();
       }
     }
-  } else if (warp == 17) {
-    // ------------------------------------------------------------ tail MMA issuer: A from TMEM
-    if (lane == 0) {
+  } else if (warp_u == 17) {
+    // ------------------------------------------------------------ tail MMA issuer: A from TMEM (warp-uniform, as above)
+    {
       const uint32_t s_wb = smem_u32(wbuf);
+      const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_t, 0);
       int64_t c = 0;
       for (int64_t ti = 0; ti < my_tiles; ++ti) {
         for (int li = 0; li <= NL; ++li, ++c) {
@@ -478,16 +487,19 @@ k_encoder_tc(const float* __restrict__ X, int64_t ldx, const int32_t* __restrict
           tc_fence_after();
           const uint32_t t_a = li == 0 ? tmem_base + (uint32_t)(ti & 1) * 128 : tmem_base + 256 + (uint32_t)((li - 1) & 1) * 128;
           const uint32_t t_d = tmem_base + 256 + (uint32_t)(li & 1) * 128;
+          if (elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks) {
-            const uint32_t a = t_a + ks * 16;  // [8 hi words | 8 lo words] per 16-column chunk
-            const uint64_t bh = umma_desc(w_hi + ks * 2 * lbo, lbo, 128), bl = umma_desc(w_lo + ks * 2 * lbo, lbo, 128);
-            umma_f16_ts(t_d, a, bh, idn, ks == 0 ? 0u : 1u);
-            umma_f16_ts(t_d, a + 8, bh, idn, 1u);
-            umma_f16_ts(t_d, a, bl, idn, 1u);
+            for (int ks = 0; ks < 8; ++ks) {
+              const uint32_t a = t_a + ks * 16;  // [8 hi words | 8 lo words] per 16-column chunk
+              const uint64_t bh = umma_desc(w_hi + ks * 2 * lbo, lbo, 128), bl = umma_desc(w_lo + ks * 2 * lbo, lbo, 128);
+              umma_f16_ts(t_d, a, bh, idn, ks == 0 ? 0u : 1u);
+              umma_f16_ts(t_d, a + 8, bh, idn, 1u);
+              umma_f16_ts(t_d, a, bl, idn, 1u);
+            }
+            umma_commit(bar_d);
+            if (li == 0) umma_commit(acc_free + (ti & 1));  // the accumulator region has been consumed
           }
-          umma_commit(bar_d);
-          if (li == 0) umma_commit(acc_free + (ti & 1));  // the accumulator region has been consumed
+          __syncwarp();
         }
       }
     }

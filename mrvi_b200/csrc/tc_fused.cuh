@@ -694,12 +694,18 @@ k_chain_fused_tc(const __grid_constant__ TcNet tc, CellBuf cb, int64_t n_cells, 
     if (issue_warp) {
       tc_fence_after();
       if (elect_one()) {
+        // The two cross terms first, the Zh.Zh^T term last: G[i][j] and G[j][i] then differ only through the rounding of the
+        // tiny (2^-11 relative) cross-term sum, i.e. by one ulp in rare cases, instead of through the order in which two
+        // cross terms are added to a large accumulator in EVERY entry (near-symmetric output: D vs D^T)
         const uint32_t lbo = 128 * 16;
         for (int ks = 0; ks < Kz / 16; ++ks) {
           const uint64_t dh = umma_desc(iu_zh + ks * 2 * lbo, lbo, 128), dl = umma_desc(iu_zl + ks * 2 * lbo, lbo, 128);
-          umma_f16(iu_tr0, dh, dh, idesc128, ks == 0 ? 0u : 1u);
-          umma_f16(iu_tr0, dh, dl, idesc128, 1u);
+          umma_f16(iu_tr0, dh, dl, idesc128, ks == 0 ? 0u : 1u);
           umma_f16(iu_tr0, dl, dh, idesc128, 1u);
+        }
+        for (int ks = 0; ks < Kz / 16; ++ks) {
+          const uint64_t dh = umma_desc(iu_zh + ks * 2 * lbo, lbo, 128);
+          umma_f16(iu_tr0, dh, dh, idesc128, 1u);
         }
         umma_commit(iu_bar);
       }

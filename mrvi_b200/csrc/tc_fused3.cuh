@@ -390,13 +390,15 @@ k_chain_fused3_tc(const __grid_constant__ TcNet tc, CellBuf cb, int64_t n_cells,
             } else {
               const uint32_t zh = sa1h + sm.off_zh, zl = sa1h + sm.off_zl;
               uint64_t dh = umma_desc(zh, 2048, 128), dl = umma_desc(zl, 2048, 128);
+              const uint64_t dh0 = dh;
 #pragma unroll
-              for (int ks = 0; ks < 2; ++ks) {
-                umma_f16(t_d1, dh, dh, idesc128, ks == 0 ? 0u : 1u);
-                umma_f16(t_d1, dh, dl, idesc128, 1u);
+              for (int ks = 0; ks < 2; ++ks) {   // cross terms first, Zh.Zh^T last (see tc_fused.cuh: near-symmetric output)
+                umma_f16(t_d1, dh, dl, idesc128, ks == 0 ? 0u : 1u);
                 umma_f16(t_d1, dl, dh, idesc128, 1u);
                 dh = desc_adv(dh, 4096); dl = desc_adv(dl, 4096);
               }
+              umma_f16(t_d1, dh0, dh0, idesc128, 1u);
+              umma_f16(t_d1, desc_adv(dh0, 4096), desc_adv(dh0, 4096), idesc128, 1u);
               umma_commit(&ctrl->mma_done[s]);
             }
           }

@@ -1,0 +1,75 @@
+"""BASELINE configs 3 and 5 IN FULL on one GPU, through the host-buffer C-ABI (what a user's call does), with an oracle
+spot-check of the result.  Writes one JSON line per config to stdout.
+  C3: 500k cells x 2k genes x 128 samples, keep_cell=True: 32.8 GB of S x S blocks streamed to page-locked host memory.
+  C5: 2M cells x 5k genes x 256 samples, n_latent=50, groupby 50 (adata.X kept as uint8 raw counts: 10 GB on the host).
+  python tools/run_full_configs.py [c3] [c5] [--cells N]"""
+import json, os, sys, time
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import mrvi_b200
+from mrvi_b200 import _capi
+from oracle import mrvi_oracle as orc
+from oracle.parity import distance_error_stats, stratified_indices
+
+which = [a for a in sys.argv[1:] if a in ("c3", "c5")] or ["c3", "c5"]
+cells = int(sys.argv[sys.argv.index("--cells") + 1]) if "--cells" in sys.argv else 0
+
+for wl in which:
+    if wl == "c3":
+        n, G, S, L, ng, keep = cells or 500_000, 2000, 128, 30, 0, True
+    else:
+        n, G, S, L, ng, keep = cells or 2_000_000, 5000, 256, 50, 50, False
+    dims = mrvi_b200.MrviDims(n_input=G, n_sample=S, n_latent=L)
+    params = mrvi_b200.init_params(dims, seed=0)
+    t0 = time.perf_counter()
+    X = mrvi_b200.synthetic_counts(n, G, seed=1000, dtype=np.uint8 if wl == "c5" else np.float32)
+    t_gen = time.perf_counter() - t0
+    rng = np.random.default_rng(1101)
+    sid = rng.integers(0, S, size=n).astype(np.int32)
+    codes = rng.integers(0, ng, size=n).astype(np.int32) if ng else None
+    h = _capi.Handle(dims, params, device=0, precision=_capi.PRECISION_TC)
+    cell = None
+    t_alloc = 0.0
+    if keep:
+        t0 = time.perf_counter()
+        cell = _capi.pinned_empty((n, S, S))
+        t_alloc = time.perf_counter() - t0
+    kw = dict(group_codes=[codes] if ng else [], n_groups=[ng] if ng else [], keep_cell=keep, cell_out=cell)
+    warm = min(n, 20000)
+    h.run_host(X[:warm], sid[:warm], [codes[:warm]] if ng else [], [ng] if ng else [], keep_cell=keep, cell_out=cell[:warm] if keep else None)
+    times = []
+    for _ in range(2):
+        t0 = time.perf_counter()
+        res = h.run_host(X, sid, **kw)
+        times.append(time.perf_counter() - t0)
+    t = min(times)
+    idx = stratified_indices(n, 256)
+    line = {"config": wl, "cells": n, "genes": G, "samples": S, "n_latent": L, "n_groups": ng, "keep_cell": keep,
+            "x_dtype": str(X.dtype), "x_host_gb": X.nbytes / 1e9, "seconds": t, "seconds_runs": times, "cells_per_s": n / t,
+            "h2d_bytes": h.last_h2d_bytes(), "h2d_gbs": h.last_h2d_bytes() / t / 1e9, "gen_seconds": t_gen, "pinned_alloc_seconds": t_alloc}
+    if keep:
+        out_bytes = n * S * S * 4
+        line.update({"d2h_bytes": out_bytes, "d2h_gbs": out_bytes / t / 1e9})
+        zref = orc.counterfactual_z(params, np.asarray(X[idx], dtype=np.float32), sid[idx], dtype=np.float64)
+        st = distance_error_stats(res["cell"][idx], orc.pairwise_distances(zref))
+        line["parity"] = {k: st[k] for k in ("n_cells", "max_norm_err", "p99_elementwise_rel")}
+        # output order == input order, every block symmetric with a zero diagonal (sampled)
+        blk = res["cell"][idx]
+        line["parity"]["max_asym"] = float(np.abs(blk - np.swapaxes(blk, 1, 2)).max())
+        line["parity"]["diag_zero"] = bool(np.all(np.diagonal(blk, axis1=1, axis2=2) == 0))
+    else:
+        # group sums against the oracle on a sample of 2 groups' cells is not affordable at S = 256; check counts exactly and
+        # the sums against an independent keep_cell pass over a stratified subset that is re-grouped on the host
+        sub = stratified_indices(n, 2048)
+        r2 = h.run_host(np.ascontiguousarray(X[sub]), sid[sub], [codes[sub]], [ng], keep_cell=True)
+        ref = np.zeros((ng, S, S))
+        np.add.at(ref, codes[sub], r2["cell"].astype(np.float64))
+        line["parity"] = {"counts_exact": bool(np.array_equal(res["group_counts"][0], np.bincount(codes, minlength=ng))),
+                          "subset_group_sums_vs_blocks": float(np.abs(r2["group_sums"][0] - ref).max() / np.abs(ref).max())}
+        zs = sub[:128]
+        zref = orc.counterfactual_z(params, np.asarray(X[zs], dtype=np.float32), sid[zs], dtype=np.float64)
+        st = distance_error_stats(r2["cell"][:128], orc.pairwise_distances(zref))
+        line["parity"].update({"n_cells": st["n_cells"], "max_norm_err": st["max_norm_err"], "p99_elementwise_rel": st["p99_elementwise_rel"]})
+    print(json.dumps(line), flush=True)
+    h.close()
+    del X, cell, res
