@@ -68,37 +68,6 @@ __host__ __device__ inline DistTcSmem dist_tc_smem(int L, int S = 256) {
   return m;
 }
 
-// 32 Gram entries of one row -> distances, in place; returns min over the entries of (d^2 - 2^-12 (n_i + n_j)):
-// negative = some entry is cancellation dominated (the caller recomputes those exactly).  DIAG: entry q == lane is
-// the row's diagonal entry (forced to zero, excluded from the test).
-template <bool DIAG>
-__device__ __forceinline__ float dist_chunk_fast(float (&g)[32], const float* nrm_j, float n_i, int lane) {
-  const float2 ni2 = make_float2(n_i, n_i), m2 = make_float2(-2.0f, -2.0f), thr2 = make_float2(-1.0f / 4096.0f, -1.0f / 4096.0f);
-  float tmin = 0.f;
-#pragma unroll
-  for (int q4 = 0; q4 < 8; ++q4) {
-    const float4 nj = *reinterpret_cast<const float4*>(nrm_j + 4 * q4);
-    const float2 njp[2] = {make_float2(nj.x, nj.y), make_float2(nj.z, nj.w)};
-#pragma unroll
-    for (int e2 = 0; e2 < 2; ++e2) {
-      const int q = 4 * q4 + 2 * e2;
-      const float2 sn = __fadd2_rn(ni2, njp[e2]);
-      const float2 d2 = __ffma2_rn(make_float2(g[q], g[q + 1]), m2, sn);
-      const float2 tt = __ffma2_rn(sn, thr2, d2);  // < 0: cancellation dominated
-      float t0 = tt.x, t1 = tt.y;
-      float r0 = sqrt_approx(fmaxf(d2.x, 0.f)), r1 = sqrt_approx(fmaxf(d2.y, 0.f));
-      if (DIAG) {
-        const bool dg0 = q == lane, dg1 = q + 1 == lane;
-        t0 = dg0 ? 0.f : t0; t1 = dg1 ? 0.f : t1;
-        r0 = dg0 ? 0.f : r0; r1 = dg1 ? 0.f : r1;
-      }
-      tmin = fminf(tmin, fminf(t0, t1));
-      g[q] = r0; g[q + 1] = r1;
-    }
-  }
-  return tmin;
-}
-
 // KEEP: per-cell output requested (compiled out of the groupby-only instantiation: its store path costs registers)
 template <bool KEEP>
 __global__ void __launch_bounds__(kDistTcThreads, 1)

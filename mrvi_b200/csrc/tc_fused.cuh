@@ -105,6 +105,9 @@ __device__ __forceinline__ float h2f_lo(uint32_t w) { return __half2float(__usho
 __device__ __forceinline__ float h2f_hi(uint32_t w) { return __half2float(__ushort_as_half((unsigned short)(w >> 16))); }
 
 // ---- packed fp32x2 helpers (FFMA2 / FMUL2 / FADD2 halve the issue slots of the fp32 epilogue math)
+// TWICE gelu(tanh): x + x tanh(...).  The factor 1/2 is folded into the rows of the next GEMM's weight operand that
+// multiply this activation (tc_build: exact, a power of two), which saves one packed multiply per pair of values in
+// every epilogue of the chain.
 __device__ __forceinline__ float2 gelu_fast2(float2 x) {
   const float2 c1 = make_float2(0.7978845608028654f, 0.7978845608028654f);
   const float2 c2 = make_float2(0.7978845608028654f * 0.044715f, 0.7978845608028654f * 0.044715f);
@@ -112,8 +115,7 @@ __device__ __forceinline__ float2 gelu_fast2(float2 x) {
   const float2 p = __ffma2_rn(u, c2, c1);
   const float2 y = __fmul2_rn(x, p);
   const float2 t = make_float2(tanh_approx(y.x), tanh_approx(y.y));
-  const float2 hx = __fmul2_rn(x, make_float2(0.5f, 0.5f));
-  return __ffma2_rn(hx, t, hx);
+  return __ffma2_rn(x, t, x);
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   uint32_t* r = reinterpret_cast<uint32_t*>(v);
@@ -169,6 +171,37 @@ __device__ __forceinline__ void exact_fix_warp(float (&g)[32], uint32_t flagged,
         if (mine && qq == q) g[qq] = d;
     }
   }
+}
+
+// 32 Gram entries of one row -> distances, in place; returns min over the entries of (d^2 - 2^-12 (n_i + n_j)):
+// negative = some entry is cancellation dominated (the caller recomputes those exactly).  DIAG: entry q == lane is
+// the row's diagonal entry (forced to zero, excluded from the test).
+template <bool DIAG>
+__device__ __forceinline__ float dist_chunk_fast(float (&g)[32], const float* nrm_j, float n_i, int lane) {
+  const float2 ni2 = make_float2(n_i, n_i), m2 = make_float2(-2.0f, -2.0f), thr2 = make_float2(-1.0f / 4096.0f, -1.0f / 4096.0f);
+  float tmin = 0.f;
+#pragma unroll
+  for (int q4 = 0; q4 < 8; ++q4) {
+    const float4 nj = *reinterpret_cast<const float4*>(nrm_j + 4 * q4);
+    const float2 njp[2] = {make_float2(nj.x, nj.y), make_float2(nj.z, nj.w)};
+#pragma unroll
+    for (int e2 = 0; e2 < 2; ++e2) {
+      const int q = 4 * q4 + 2 * e2;
+      const float2 sn = __fadd2_rn(ni2, njp[e2]);
+      const float2 d2 = __ffma2_rn(make_float2(g[q], g[q + 1]), m2, sn);
+      const float2 tt = __ffma2_rn(sn, thr2, d2);  // < 0: cancellation dominated
+      float t0 = tt.x, t1 = tt.y;
+      float r0 = sqrt_approx(fmaxf(d2.x, 0.f)), r1 = sqrt_approx(fmaxf(d2.y, 0.f));
+      if (DIAG) {
+        const bool dg0 = q == lane, dg1 = q + 1 == lane;
+        t0 = dg0 ? 0.f : t0; t1 = dg1 ? 0.f : t1;
+        r0 = dg0 ? 0.f : r0; r1 = dg1 ? 0.f : r1;
+      }
+      tmin = fminf(tmin, fminf(t0, t1));
+      g[q] = r0; g[q + 1] = r1;
+    }
+  }
+  return tmin;
 }
 
 // LayerNorm + gelu of the 128-column accumulator row, this thread's 64-column half, written back in
@@ -610,8 +643,11 @@ k_chain_fused_tc(const __grid_constant__ TcNet tc, CellBuf cb, int64_t n_cells, 
     float v[32];
     if (ncol == 16) tmem_ld16(t_lane + col0, v); else tmem_ld32(t_lane + col0, v);
     tmem_ld_wait();
+    // (columns >= L of D5 are exactly zero: the padded rows of the B5 operand are; only rows outside the chunk need zeroing)
+    if (!valid) {
 #pragma unroll
-    for (int l = 0; l < 32; ++l) v[l] = (l < ncol && col0 + l < L && valid) ? v[l] : 0.f;
+      for (int l = 0; l < 32; ++l) v[l] = 0.f;
+    }
     if (cb.per_row && valid) {
       const float* zb = cb.zbase + fi * L;
 #pragma unroll
@@ -743,30 +779,46 @@ k_chain_fused_tc(const __grid_constant__ TcNet tc, CellBuf cb, int64_t n_cells, 
       float g[32];
       tmem_ld32(t_lane + c * 32, g);
       tmem_ld_wait();
-      uint32_t flagged = 0u;
-      // fast path (warp-uniform): the whole chunk lies inside every lane's cell and every row is valid
+      // fast path (warp-uniform): the whole chunk lies inside every lane's cell and every row is valid -- no bounds checks;
+      // the diagonal can only sit in the chunk of this warp's own rows (entry q == lane); cancellation-dominated entries
+      // are only DETECTED here (min over the entries of d^2 - 2^-12 (n_i + n_j)) and located when there is one (rare)
       const bool full = __all_sync(0xffffffffu, valid && c * 32 >= c0 && c * 32 + 32 <= c0 + S);
       const float2 ni2 = make_float2(n_i, n_i), m2 = make_float2(-2.0f, -2.0f), thr2 = make_float2(-1.0f / 4096.0f, -1.0f / 4096.0f);
+      if (full) {
+        const float tmin = (c == warp_q) ? dist_chunk_fast<true>(g, nrm_s + c * 32, n_i, tid & 31)
+                                         : dist_chunk_fast<false>(g, nrm_s + c * 32, n_i, tid & 31);
+        if (__any_sync(0xffffffffu, tmin < 0.f)) {  // rare: near-duplicate samples -> exact direct-difference distance
+          uint32_t flagged = 0u;
+          if (tmin < 0.f) {
 #pragma unroll
-      for (int q4 = 0; q4 < 8; ++q4) {
-        const float4 nj = *reinterpret_cast<const float4*>(nrm_s + c * 32 + 4 * q4);
-        const float2 njp[2] = {make_float2(nj.x, nj.y), make_float2(nj.z, nj.w)};
-#pragma unroll
-        for (int e2 = 0; e2 < 2; ++e2) {
-          const int q = 4 * q4 + 2 * e2, j = c * 32 + q;     // columns j, j+1 = tile rows of the other samples
-          const float2 sn = __fadd2_rn(ni2, njp[e2]);
-          const float2 d2 = __ffma2_rn(make_float2(g[q], g[q + 1]), m2, sn);
-          const float2 tt = __ffma2_rn(sn, thr2, d2);        // < 0: cancellation dominated
-          const bool in0 = full ? (j != r) : (valid && (unsigned)(j - c0) < (unsigned)S && j != r);
-          const bool in1 = full ? (j + 1 != r) : (valid && (unsigned)(j + 1 - c0) < (unsigned)S && j + 1 != r);
-          if (in0 && tt.x < 0.f) flagged |= 1u << q;
-          if (in1 && tt.y < 0.f) flagged |= 2u << q;
-          g[q] = in0 ? sqrt_approx(fmaxf(d2.x, 0.f)) : 0.f;
-          g[q + 1] = in1 ? sqrt_approx(fmaxf(d2.y, 0.f)) : 0.f;
+            for (int q = 0; q < 32; ++q)
+              if (c * 32 + q != r && g[q] * g[q] < (n_i + nrm_s[c * 32 + q]) * (1.0f / 4096.0f)) flagged |= 1u << q;
+          }
+          if (__any_sync(0xffffffffu, flagged != 0u)) exact_fix_warp<2048u>(g, flagged, zh, zl, r, c * 32, L);
         }
+      } else {
+        uint32_t flagged = 0u;
+#pragma unroll
+        for (int q4 = 0; q4 < 8; ++q4) {
+          const float4 nj = *reinterpret_cast<const float4*>(nrm_s + c * 32 + 4 * q4);
+          const float2 njp[2] = {make_float2(nj.x, nj.y), make_float2(nj.z, nj.w)};
+#pragma unroll
+          for (int e2 = 0; e2 < 2; ++e2) {
+            const int q = 4 * q4 + 2 * e2, j = c * 32 + q;     // columns j, j+1 = tile rows of the other samples
+            const float2 sn = __fadd2_rn(ni2, njp[e2]);
+            const float2 d2 = __ffma2_rn(make_float2(g[q], g[q + 1]), m2, sn);
+            const float2 tt = __ffma2_rn(sn, thr2, d2);        // < 0: cancellation dominated
+            const bool in0 = valid && (unsigned)(j - c0) < (unsigned)S && j != r;
+            const bool in1 = valid && (unsigned)(j + 1 - c0) < (unsigned)S && j + 1 != r;
+            if (in0 && tt.x < 0.f) flagged |= 1u << q;
+            if (in1 && tt.y < 0.f) flagged |= 2u << q;
+            g[q] = in0 ? sqrt_approx(fmaxf(d2.x, 0.f)) : 0.f;
+            g[q + 1] = in1 ? sqrt_approx(fmaxf(d2.y, 0.f)) : 0.f;
+          }
+        }
+        if (__any_sync(0xffffffffu, flagged != 0u))  // rare: near-duplicate samples -> exact direct-difference distance
+          exact_fix_warp<2048u>(g, flagged, zh, zl, r, c * 32, L);
       }
-      if (__any_sync(0xffffffffu, flagged != 0u))  // rare: near-duplicate samples -> exact direct-difference distance
-        exact_fix_warp<2048u>(g, flagged, zh, zl, r, c * 32, L);
       if (cell_out != nullptr && (S & 3) == 0) {
         // Rows go through a per-warp shared-memory tile (the fp32 z tile is dead by now) so that every store
         // instruction writes full 32-byte sectors: a thread-per-row float4 store touches 32 rows = 32 half-used

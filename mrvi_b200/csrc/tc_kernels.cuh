@@ -225,6 +225,14 @@ __device__ __forceinline__ float gelu_fast(float x) {
   const float hx = 0.5f * x;
   return fmaf(hx, t, hx);
 }
+// TWICE gelu(tanh) for the chain kernels: the 1/2 is folded into the next GEMM's weight rows (tc_build)
+__device__ __forceinline__ float gelu2x_fast(float x) {
+  const float c1 = 0.7978845608028654f, c2 = 0.7978845608028654f * 0.044715f;
+  const float u = x * x;
+  const float p = fmaf(u, c2, c1);
+  const float t = tanh_approx(x * p);
+  return fmaf(x, t, x);
+}
 // (hi, lo) f16 split of two floats: hi = leading 11 significant bits (exact in f16 when the
 // exponent is in range), lo = remainder rounded to f16.  Returns packed f16x2 words.
 __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
@@ -275,8 +283,8 @@ __device__ __forceinline__ void ln_gelu_store(float (&v)[NCH * 32], const float*
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int i0 = c * 8 + 2 * j, i1 = i0 + 1;
-      const float y0 = gelu_fast(fmaf(fmaf(v[i0], rstd, nb), g[i0], b[i0]));
-      const float y1 = gelu_fast(fmaf(fmaf(v[i1], rstd, nb), g[i1], b[i1]));
+      const float y0 = gelu2x_fast(fmaf(fmaf(v[i0], rstd, nb), g[i0], b[i0]));
+      const float y1 = gelu2x_fast(fmaf(fmaf(v[i1], rstd, nb), g[i1], b[i1]));
       split2(y0, y1, h[j], l[j]);
     }
     *reinterpret_cast<uint4*>(dst_h + c * 2048) = make_uint4(h[0], h[1], h[2], h[3]);
@@ -303,8 +311,8 @@ __device__ __forceinline__ void ln_gelu_store_tmem(float (&v)[128], const float*
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
       const int i0 = c * 64 + 2 * j, i1 = i0 + 1;
-      const float y0 = gelu_fast(fmaf(fmaf(v[i0], rstd, nb), g[i0], b[i0]));
-      const float y1 = gelu_fast(fmaf(fmaf(v[i1], rstd, nb), g[i1], b[i1]));
+      const float y0 = gelu2x_fast(fmaf(fmaf(v[i0], rstd, nb), g[i0], b[i0]));
+      const float y1 = gelu2x_fast(fmaf(fmaf(v[i1], rstd, nb), g[i1], b[i1]));
       split2(y0, y1, h[j], l[j]);
     }
     tmem_st32(t_lane + c * 32, h);
@@ -713,6 +721,17 @@ inline int tc_build(TcNet& tc, const NetW& net, const MrviDims& d, const tc_deta
   tc.K1 = 48; tc.K5 = 48;
   tc.K3 = round_up(K3r, 16);
   tc.N5 = round_up(L, 16) <= 32 ? 32 : 64;
+  // The epilogues emit TWICE gelu (gelu_fast2 / gelu2x_fast): the factor 1/2 goes into the weight rows that multiply a
+  // gelu output -- all of B2t / B4t (the 128-wide hidden activations) and the first M rows of B3, B4a, B5 (t2 / t4).
+  // Exact: a power of two.
+  {
+    auto half_rows = [](Mat& B, int rows, int N) { for (size_t i = 0; i < (size_t)rows * N; ++i) B[i] *= 0.5; };
+    half_rows(Wout0, R, M);
+    half_rows(Wout1, R, M);
+    half_rows(B3, M, R);
+    half_rows(B4a, M, M);
+    half_rows(B5, M, L);
+  }
   std::vector<uint8_t> img;
   tc.b1 = append_operand(img, B1, K1r, R, R, tc.K1, false);
   tc.b2t = append_operand(img, Wout0, R, M, M, R, true);
