@@ -403,6 +403,25 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    # stdout carries exactly ONE line, the JSON line of rank 0: everything else any library prints (NCCL's version
+    # banner, warnings) goes to stderr
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
+
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+    all_cores = sorted(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else None
+    if local_world > 1 and hasattr(os, "sched_setaffinity"):
+        # one process per GPU: a contiguous slice of the host cores each, so that the packing threads and the pages they
+        # first touch stay on one socket (GPUs and cores are enumerated socket by socket on the HGX boards)
+        try:
+            cores = sorted(os.sched_getaffinity(0))
+            per = max(1, len(cores) // local_world)
+            os.sched_setaffinity(0, cores[local_rank * per:(local_rank + 1) * per] or cores)
+        except OSError:
+            pass
     n_per, G, S, L, n_groups, keep_cell, desc = WORKLOADS[args.workload]
     if args.cells_per_gpu:
         n_per = args.cells_per_gpu
@@ -432,7 +451,7 @@ def main():
                                            "torch-CPU fp32 restatement of the reference path, batch_size=256 (JAX reference not installable here)"},
                 "e2e": {"value": val, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line), flush=True)
+        emit(line)
         return
 
     # ------------------------------------------------------------------ our arm
@@ -583,13 +602,15 @@ def main():
 
     if rank == 0:
         if not args.no_cpu_baseline:
+            if all_cores and hasattr(os, "sched_setaffinity"):
+                os.sched_setaffinity(0, all_cores)   # the CPU baseline gets every host core again
             sample = args.cpu_sample_cells or cpu_sample_cells(G, S, n_per)
             cpu_params = mrvi_b200.init_params(mrvi_b200.MrviDims(n_input=G, n_sample=S, n_latent=L), seed=0)
             val, cores, per_step, passes = cpu_reference_run(cpu_params, G, S, n_groups, keep_cell, sample, 1, 1, min_seconds=20.0)
             line["cpu_baseline"] = {"value": val, "unit": "cells/s", "cores": cores, "kind": "port",
                                     "sample": f"{sample} cells of the workload x {passes} passes ({per_step * passes:.1f} s of CPU work); "
                                               "torch-CPU fp32 restatement of the reference path, batch_size=256, all host threads"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

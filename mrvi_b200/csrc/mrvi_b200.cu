@@ -30,6 +30,12 @@ namespace mrvi {
 
 static thread_local std::string g_last_error;
 static std::atomic<int64_t> g_launches{0};
+static std::atomic<int> g_dev_handles[64];    // live handles per device of this process: GPUs fed by one process share the host's cores and memory bus
+static int live_devices() {
+  int n = 0;
+  for (int d = 0; d < 64; ++d) n += g_dev_handles[d].load() > 0;
+  return n;
+}
 
 static int fail(int code, const char* fmt, ...) {
   char buf[1024];
@@ -858,6 +864,7 @@ int mrvi_create(const MrviDims* dims, int32_t n_params, const char* const* names
   }
   CUDA_TRY(cudaEventCreate(&h->ev_call[0]));
   CUDA_TRY(cudaEventCreate(&h->ev_call[1]));
+  if (device < 64) g_dev_handles[device].fetch_add(1);
   *out = h.release();
   return 0;
 }
@@ -867,6 +874,7 @@ int mrvi_destroy(MrviHandle* h) {
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
   if (h->nccl_comm && nccl_api().ok) nccl_api().CommDestroy(h->nccl_comm);
+  if (h->device < 64) g_dev_handles[h->device].fetch_sub(1);
   delete h;
   return 0;
 }
@@ -958,12 +966,17 @@ static int run_host_impl(MrviHandle* h, int64_t n_cells, const float* X, int x_k
   const bool int_in = !csr && (x_kind == 3 || x_kind == 4);     // int32 / int64 counts: always narrowed (or converted) on the host
   const bool use_pack = !csr && !narrow_in && (int_in || (!pack_disabled && n_cells * (int64_t)G >= (1ll << 22)));
   const size_t pack_elem = int_in ? 4 : 2;   // staging bytes per value: the int path may have to fall back to float32
+  // GPUs fed from this host: ranks of a torchrun job (one process per GPU) or handles of one process (MrVI(devices=...))
+  int sharers = std::max(1, live_devices());
+  if (const char* e = getenv("LOCAL_WORLD_SIZE")) sharers = std::max(sharers, atoi(e));
   if (use_pack && !hs.pool) {
-    int nt = (int)std::thread::hardware_concurrency();
-    if (const char* e = getenv("LOCAL_WORLD_SIZE")) nt /= std::max(1, atoi(e));  // one process per GPU shares the host cores
+    int nt = (int)std::thread::hardware_concurrency() / sharers;   // they share the host cores
     if (const char* e = getenv("MRVI_B200_PACK_THREADS")) nt = atoi(e);
     hs.pool.reset(new PackPool(std::max(1, std::min(nt, 32))));
   }
+  // ... and the host memory bus / PCIe switches: with N GPUs pulling raw float32 at once each gets ~45 GB/s * 2 / N
+  // (measured 180 GB/s aggregate at N = 8, SCALE_r01), so narrowing keeps paying at a proportionally lower packing rate
+  const double pack_floor = pack_min_gbps * std::min(1.0, 2.0 / sharers);
   if (use_pack && chunk_cells <= 0) ch = std::min<int64_t>(ch, 8192);  // finer pipeline: narrowing of chunk c+1 overlaps the copy of c
   bool sums_ok = true;
   for (int k = 0; k < n_keys; ++k) sums_ok &= hs.sums_elems[k] >= (size_t)n_groups[k] * S * S;
@@ -1065,12 +1078,12 @@ static int run_host_impl(MrviHandle* h, int64_t n_cells, const float* X, int x_k
       // The narrowing pays only if the host reads X faster than PCIe would carry it raw (~47 GB/s measured): keep it
       // while the measured rate stays above the threshold.  (Mixing narrowed and raw chunks to keep both the host
       // threads and the copy engine busy was measured SLOWER: DMA reads and the packer share the host memory bus.)
-      if (use_pack && hs.pack_rate_gbps != 0.0 && hs.pack_rate_gbps < pack_min_gbps && ++hs.pack_skipped >= 64) {
+      if (use_pack && hs.pack_rate_gbps != 0.0 && hs.pack_rate_gbps < pack_floor && ++hs.pack_skipped >= 64) {
         hs.pack_rate_gbps = 0.0;  // the host may have been busy when the rate was measured: probe again now and then
         hs.pack_skipped = 0;
       }
       const bool want_pack = use_pack && !hs.pack_unavailable && hs.hpack[b] != nullptr &&
-                             (hs.pack_rate_gbps == 0.0 || hs.pack_rate_gbps >= pack_min_gbps);
+                             (hs.pack_rate_gbps == 0.0 || hs.pack_rate_gbps >= pack_floor);
       if (want_pack) {
         if (c >= 2) CUDA_TRY(cudaEventSynchronize(hs.ev_h2d[b]));  // the copy of chunk c-2 has left the pinned staging buffer
         const auto t0 = std::chrono::steady_clock::now();

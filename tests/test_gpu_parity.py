@@ -129,20 +129,27 @@ def test_host_narrowing_is_bit_transparent(built_library, precision):
     h.close()
 
 
-@pytest.mark.parametrize("dtype", [np.uint8, np.uint16])
+@pytest.mark.parametrize("dtype", [np.uint8, np.uint16, np.int32, np.int64])
 def test_integer_count_matrix_input(built_library, dtype):
-    """`mrvi_run_host_counts`: adata.X stored as uint8 / uint16 counts gives bit-identical results to its float32 copy
-    (what scvi's loader would hand the reference), with 1 / 2 bytes per value on the wire; strided rows; model API."""
+    """`mrvi_run_host_counts`: adata.X stored as integer counts gives bit-identical results to its float32 copy (what
+    scvi's loader would hand the reference).  uint8 / uint16 travel as they are (1 / 2 bytes per value on the wire);
+    int32 / int64 are narrowed chunk by chunk inside the library (no float32 copy of the matrix); strided rows; model API."""
     dims = mrvi_b200.MrviDims(n_input=300, n_sample=6)
     params, h = _model(dims, seed=2, precision="tc")
     X, sid = _inputs(900, 300, 6, seed=3)
     Xi = X.astype(dtype)
     if dtype == np.uint16:
         Xi[::5, 7] = 50000
+    if dtype in (np.int32, np.int64):
+        Xi[256:512, 3] = 70000      # one 256-cell chunk needs the float32 fall-back (>= 65536), its neighbours uint8
+        Xi[700, 5] = 300            # ... and one uint16
     codes = [(np.arange(900) % 3).astype(np.int32)]
     a = h.run_host(Xi.astype(np.float32), sid, codes, [3], keep_cell=True, want_u=True)
     b = h.run_host(Xi, sid, codes, [3], keep_cell=True, want_u=True, chunk_cells=256)
-    assert h.last_h2d_bytes() == 900 * 300 * Xi.itemsize
+    if dtype in (np.uint8, np.uint16):
+        assert h.last_h2d_bytes() == 900 * 300 * Xi.itemsize
+    else:  # 4 chunks of 256 (last: 132 cells): uint8, float32 fall-back, uint16 (cell 700), uint8
+        assert h.last_h2d_bytes() == 300 * (256 * 1 + 256 * 4 + 256 * 2 + 132 * 1)
     assert np.array_equal(a["cell"], b["cell"]) and np.array_equal(a["u"], b["u"])
     wide = np.zeros((900, 320), dtype=dtype)
     wide[:, :300] = Xi
@@ -533,3 +540,52 @@ def test_round1_fuzz_failures(built_library, name, precision, dk, n, seed):
     assert np.abs(g_only["group_sums"][0] - gref).max() / gs < bar
     assert np.array_equal(res["group_counts"][0], np.bincount(codes[codes >= 0], minlength=3))
     assert np.all(np.diagonal(res["cell"], axis1=1, axis2=2) == 0)
+
+
+def test_pinned_output_buffers(built_library):
+    """`mrvi_alloc_pinned`: the big outputs of run_host live in page-locked memory (views keep it alive; freed with the
+    last view) and caller-provided slices of one pinned array receive the shards' blocks."""
+    a = _capi.pinned_empty((1000, 8, 8))
+    a[:] = 1.0
+    v = a[10:20]
+    del a
+    assert float(v.sum()) == 10 * 64
+    dims = mrvi_b200.MrviDims(n_input=50, n_sample=8)
+    params, h = _model(dims, seed=1, precision="tc")
+    X, sid = _inputs(300, 50, 8, seed=2)
+    whole = h.run_host(X, sid, keep_cell=True, want_z=True)
+    out = _capi.pinned_empty((300, 8, 8))
+    zo = _capi.pinned_empty((300, 8, dims.n_latent))
+    for lo, hi in ((0, 100), (100, 300)):
+        h.run_host(X[lo:hi], sid[lo:hi], keep_cell=True, want_z=True, cell_out=out[lo:hi], z_out=zo[lo:hi])
+    assert np.array_equal(out, whole["cell"]) and np.array_equal(zo, whole["z"])
+    h.close()
+
+
+def test_multi_device_api_matches_single_device(built_library):
+    """`MrVI(devices=[...])`: cells sharded over the visible GPUs (contiguous ranges, one handle + host thread each), group
+    sums added on the host, keep_cell blocks written by every device into its slice of one output: counts and cell order
+    bit-exact, per-cell blocks bit-identical (same kernels on the same cells), group means equal up to float64
+    re-association.  Needs >= 2 GPUs (`gpurun --gpus 2`); with one GPU the sharding logic runs over a single device."""
+    ndev = _capi.device_count()
+    ad = mrvi_b200.synthetic_iid(n_obs=1003, n_vars=120, n_sample=16, seed=5)
+    dims = mrvi_b200.MrviDims(n_input=120, n_sample=16)
+    params = mrvi_b200.init_params(dims, seed=6)
+    single = mrvi_b200.MrVI(ad, params, sample_key="sample_str", precision="tc", device=0)
+    ref = single.get_local_sample_distances(groupby=["labels", "label_2"], keep_cell=True)
+    zref = single.get_local_sample_representation()
+    uref = single.get_latent_representation()
+    single.close()
+    devices = list(range(min(ndev, 4))) if ndev >= 2 else [0]
+    multi = mrvi_b200.MrVI(ad, params, sample_key="sample_str", precision="tc", devices=devices)
+    if ndev < 2:   # one GPU: force the sharded code path over two handles on the same device
+        multi._handles.append(_capi.Handle(multi.dims, multi.params, device=0, precision=_capi.PRECISION_TC))
+    got = multi.get_local_sample_distances(groupby=["labels", "label_2"], keep_cell=True)
+    assert np.array_equal(np.asarray(got["cell"].values), np.asarray(ref["cell"].values))
+    assert list(got["cell"].coords["cell_name"]) == list(ref["cell"].coords["cell_name"])
+    for key in ("labels", "label_2"):
+        assert list(got[key].coords[f"{key}_name"]) == list(ref[key].coords[f"{key}_name"])
+        np.testing.assert_allclose(np.asarray(got[key].values), np.asarray(ref[key].values), rtol=2e-6, atol=0)
+    assert np.array_equal(np.asarray(multi.get_local_sample_representation().values), np.asarray(zref.values))
+    assert np.array_equal(multi.get_latent_representation(), uref)
+    multi.close()

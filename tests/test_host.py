@@ -162,3 +162,47 @@ def test_host_narrowing_of_count_chunks_is_lossless(built_library):
             Y[0, 0] = bad
             assert _capi.narrow_counts(Y, n_threads=1)[0] == 0, bad
     assert _capi.narrow_counts(np.zeros((0, 5), np.float32))[0] == 1
+
+
+def test_group_and_sample_coding_is_vectorised_and_matches_the_loop():
+    """`MrVI._group_codes` / `_sample_codes` (host side of reference `_model.py:470-504`): the vectorised coding must give
+    what the per-cell dictionary look-up of round 1 gave -- value_counts() order, -1 for labels outside `adata`'s
+    categories and for NaN, labels taken positionally from self.adata -- for categorical, string and integer columns."""
+    import pandas as pd
+
+    from mrvi_b200._model import MrVI
+
+    rng = np.random.default_rng(0)
+    n = 5000
+    labels = rng.choice(["b", "a", "c", "d"], size=n, p=[0.5, 0.3, 0.15, 0.05])
+    obs = pd.DataFrame({"cat": pd.Categorical(labels, categories=["a", "b", "c", "d", "unused"]), "str": labels,
+                        "int": rng.integers(0, 7, size=n), "sample": rng.integers(0, 5, size=n)})
+    obs.loc[obs.index[::97], "str"] = None
+    ad = mrvi_b200.SimpleAnnData(np.zeros((n, 3), np.float32), obs)
+    m = MrVI.__new__(MrVI)   # host helpers only: no library handle
+    m.adata, m.sample_key, m.sample_order = ad, "sample", np.arange(5)
+    for key in ("cat", "str", "int"):
+        for idx in (np.arange(n), rng.permutation(n)[:777]):
+            codes, cats, counts = m._group_codes(ad, key, idx)
+            vc = ad.obs[key].value_counts()
+            assert cats == list(vc.index) and np.array_equal(counts, vc.to_numpy())
+            lookup = {c: i for i, c in enumerate(cats)}
+            want = np.array([lookup.get(l, -1) for l in ad.obs[key].to_numpy()[idx].tolist()], dtype=np.int32)
+            assert codes.dtype == np.int32 and np.array_equal(codes, want), key
+    assert np.array_equal(m._sample_codes(ad), ad.obs["sample"].to_numpy().astype(np.int32))
+    m.sample_order = np.array(["s3", "s1", "s4", "s0", "s2"])
+    ad.obs["sample"] = np.array([f"s{i}" for i in obs["sample"]])
+    want = pd.Categorical(ad.obs["sample"], categories=list(m.sample_order)).codes.astype(np.int32)
+    assert np.array_equal(m._sample_codes(ad), want)
+    ad.obs["sample"] = pd.Categorical(ad.obs["sample"])
+    assert np.array_equal(m._sample_codes(ad), want)
+    ad.obs.loc[ad.obs.index[3], "sample"] = np.nan
+    with pytest.raises(ValueError):
+        m._sample_codes(ad)
+
+
+def test_host_narrowing_of_integer_matrices(built_library):
+    """`narrow_counts_int` through mrvi_run_host_counts' argument checks needs a GPU; the dtype table does not."""
+    assert _capi._X_DTYPES[np.dtype(np.int32)] == 3 and _capi._X_DTYPES[np.dtype(np.int64)] == 4
+    header = open(os.path.join(ROOT, "include", "mrvi_b200.h")).read()
+    assert "MRVI_X_INT32 = 3" in header and "MRVI_X_INT64 = 4" in header
