@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define MRVI_B200_ABI_VERSION 4
+#define MRVI_B200_ABI_VERSION 5
 
 typedef struct MrviHandle MrviHandle;
 
@@ -172,6 +172,32 @@ int mrvi_run_sampled_host(MrviHandle* h, int64_t n_cells, const float* X, int64_
                           const int32_t* const* group_codes, const int32_t* n_groups, int32_t norm,
                           int32_t normalize, float* cell_out, double* const* group_sums,
                           int64_t* const* group_counts, float* z_out, int64_t chunk_cells);
+
+/*
+ * The latent-space stage of MrVI.differential_expression (src/mrvi/_model.py:1160-1218, 1283), host
+ * buffers.  For every cell, mc_samples draws of u per counterfactual sample (as in mrvi_run_sampled_host) give the
+ * residuals eps_ [mc, S_kept, L] = inference(..., use_mean=False)["eps"] (_model.py:1175-1194); per (draw, latent dim)
+ * they are standardised over the kept samples (population std, 1e-6 added to it), and
+ *   betas[a, k, d]      = sum_s Amat[cell][k, s] eps[a, s, d]                    (_model.py:1203)
+ *   betas_norm[a, l, d] = sum_k betas[a, k, d] prefactor[cell][k, l]             (_model.py:1206)
+ *   effect_size[cell, l] = mean_a sum_d betas_norm[a, l, d]^2                    (_model.py:1207)
+ *   beta[cell, k, d]     = mean_a betas[a, k, d] * std[a, d]                     (_model.py:1210, 1283)
+ * The design-matrix algebra (Amat = pinv(X^T D X + lambd I) X^T D, prefactor = sqrtm(.), _model.py:1152-1158), the chi2
+ * p-values (_model.py:1208) and the Benjamini-Hochberg adjustment (_model.py:1363) stay on the host (mrvi_b200._model).
+ *
+ *   kept_samples [n_kept_samples] sample codes (sample_subset, _model.py:1112-1119), or NULL = all n_sample samples
+ *   Amat         per_cell_design ? [n_cells][n_covariates][n_kept] : [n_covariates][n_kept]      float32
+ *   prefactor    per_cell_design ? [n_cells][n_covariates][n_covariates] : [n_covariates][n_covariates]
+ *   beta_out     [n_cells][n_covariates][n_latent] float32;  effect_size_out [n_cells][n_covariates] float32
+ *   eps_out      [n_cells][mc][n_sample][n_latent] float32 or NULL (all samples, unstandardised: for the parity tests)
+ *   u_noise / seed / cell_offset: as in mrvi_run_sampled_host.
+ * The decoder-side outputs of the reference method (lfc, pde, baseline_expression) are outside this library.
+ */
+int mrvi_run_de_host(MrviHandle* h, int64_t n_cells, const float* X, int64_t ldx, const int32_t* sample_idx,
+                     int32_t mc_samples, uint64_t seed, int64_t cell_offset, const float* u_noise,
+                     int32_t n_kept_samples, const int32_t* kept_samples, int32_t n_covariates, const float* Amat,
+                     const float* prefactor, int32_t per_cell_design, float* beta_out, float* effect_size_out,
+                     float* eps_out, int64_t chunk_cells);
 
 /*
  * mrvi_run_host for a dense count matrix stored as integers (raw counts in adata.X or a layer): X [n_cells, ldx]

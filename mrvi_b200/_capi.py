@@ -12,7 +12,7 @@ import numpy as np
 
 from ._params import MrviDims
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 PRECISION_FP32 = 0
 PRECISION_TC = 1
 NORMS = {"l2": 0, "l1": 1, "linf": 2}
@@ -33,6 +33,7 @@ EXPORTED_SYMBOLS = (
     "mrvi_run_host_csr",
     "mrvi_run_host_counts",
     "mrvi_run_sampled_host",
+    "mrvi_run_de_host",
     "mrvi_distances_device",
     "mrvi_last_stage_ms",
     "mrvi_last_h2d_bytes",
@@ -102,6 +103,8 @@ def load_library():
     lib.mrvi_run_sampled_host.restype = C.c_int
     lib.mrvi_run_sampled_host.argtypes = [vp, i64, vp, i64, vp, i32, C.c_uint64, i64, vp, vp, i32, C.POINTER(vp),
                                           C.POINTER(i32), i32, i32, vp, C.POINTER(vp), C.POINTER(vp), vp, i64]
+    lib.mrvi_run_de_host.restype = C.c_int
+    lib.mrvi_run_de_host.argtypes = [vp, i64, vp, i64, vp, i32, C.c_uint64, i64, vp, i32, vp, i32, vp, vp, i32, vp, vp, vp, i64]
     lib.mrvi_distances_device.restype = C.c_int
     lib.mrvi_distances_device.argtypes = [vp, i64, vp, i32, C.POINTER(vp), C.POINTER(i32), i32, vp,
                                           C.POINTER(vp), vp]
@@ -378,6 +381,52 @@ class Handle:
         out["group_counts"] = counts
         if want_z:
             out["z"] = z
+        return out
+
+    def run_de_host(self, X: np.ndarray, sample_idx: np.ndarray, mc_samples: int, Amat: np.ndarray, prefactor: np.ndarray,
+                    kept_samples: Optional[np.ndarray] = None, seed: int = 0, cell_offset: int = 0,
+                    u_noise: Optional[np.ndarray] = None, want_eps: bool = False, chunk_cells: int = 0):
+        """``mrvi_run_de_host``: the latent-space stage of ``differential_expression`` (reference `_model.py:1160-1218`).
+        ``Amat`` (K, S_kept) or per cell (n, K, S_kept); ``prefactor`` (K, K) or (n, K, K); returns ``beta`` (n, K, L)
+        and ``effect_size`` (n, K) (and the raw residuals ``eps`` (n, mc, S, L) with ``want_eps``)."""
+        d = self.dims
+        if hasattr(X, "toarray") and not isinstance(X, np.ndarray):
+            X = X.toarray()
+        if X.dtype != np.float32 or X.ndim != 2 or X.strides[1] != 4 or X.strides[0] % 4 != 0:
+            X = np.ascontiguousarray(X, dtype=np.float32)
+        n = X.shape[0]
+        if X.shape[1] != d.n_input:
+            raise ValueError(f"X has {X.shape[1]} genes, model expects {d.n_input}")
+        ldx = d.n_input if n <= 1 else X.strides[0] // 4
+        sid = np.ascontiguousarray(sample_idx, dtype=np.int32).reshape(-1)
+        if sid.shape[0] != n:
+            raise ValueError("sample_idx length does not match X")
+        mc, S, L, Lq = int(mc_samples), d.n_sample, d.n_latent, d.n_latent_q
+        kept = None if kept_samples is None else np.ascontiguousarray(kept_samples, dtype=np.int32).reshape(-1)
+        Sk = S if kept is None else kept.shape[0]
+        Amat = np.ascontiguousarray(Amat, dtype=np.float32)
+        prefactor = np.ascontiguousarray(prefactor, dtype=np.float32)
+        per_cell = Amat.ndim == 3
+        K = Amat.shape[-2]
+        if Amat.shape != ((n, K, Sk) if per_cell else (K, Sk)):
+            raise ValueError(f"Amat must have shape (n_covariates, {Sk}) or ({n}, n_covariates, {Sk}), not {Amat.shape}")
+        if prefactor.shape != ((n, K, K) if per_cell else (K, K)):
+            raise ValueError(f"prefactor must have shape {((n, K, K) if per_cell else (K, K))}, not {prefactor.shape}")
+        if u_noise is not None:
+            u_noise = np.ascontiguousarray(u_noise, dtype=np.float32)
+            if u_noise.shape != (S, mc, n, Lq):
+                raise ValueError(f"u_noise must have shape {(S, mc, n, Lq)}")
+        beta = np.empty((n, K, L), dtype=np.float32)
+        effect = np.empty((n, K), dtype=np.float32)
+        eps = np.empty((n, mc, S, L), dtype=np.float32) if want_eps else None
+        _check(load_library().mrvi_run_de_host(
+            self._h, n, X.ctypes.data, ldx, sid.ctypes.data, mc, int(seed) & (2 ** 64 - 1), int(cell_offset),
+            u_noise.ctypes.data if u_noise is not None else None, Sk, kept.ctypes.data if kept is not None else None, K,
+            Amat.ctypes.data, prefactor.ctypes.data, int(per_cell), beta.ctypes.data, effect.ctypes.data,
+            eps.ctypes.data if want_eps else None, int(chunk_cells)))
+        out = {"beta": beta, "effect_size": effect}
+        if want_eps:
+            out["eps"] = eps
         return out
 
     # ---- multi-GPU: the one exchange step of the path (SURVEY.md 8(e))

@@ -23,7 +23,7 @@ from . import _capi
 from ._data import dense_float32
 from ._params import MrviDims, flatten_params, infer_dims, validate_params
 from ._types import MrVIReduction, _default_fn
-from ._utils import _parse_local_statistics_requirements
+from ._utils import _parse_local_statistics_requirements, fdr_bh
 from ._xr import DataArray, Dataset
 
 _PRECISIONS = {"fp32": _capi.PRECISION_FP32, "tc": _capi.PRECISION_TC}
@@ -70,11 +70,13 @@ class MrVI:
 
     def __init__(self, adata, params: Mapping, sample_key: str = "sample", sample_order: Optional[Sequence] = None,
                  precision: str = "fp32", device: int = 0, dims: Optional[MrviDims] = None, seed: int = 0,
-                 devices=None):
+                 devices=None, batch_key: Optional[str] = None):
         if precision not in _PRECISIONS:
             raise ValueError(f"precision must be one of {sorted(_PRECISIONS)}, not {precision!r}")
         self.adata = adata
         self.sample_key = sample_key
+        #: ``obs`` column of the batch (site) of each cell; only ``differential_expression(add_batch_specific_offsets=True)`` reads it
+        self.batch_key = batch_key
         flat = flatten_params(params)
         self.dims = infer_dims(flat) if dims is None else dims
         self.params = validate_params(flat, self.dims)
@@ -413,6 +415,156 @@ class MrVI:
             final[gr.name] = DataArray(np.stack(arrs, axis=0), dims=[f"{gr.group_by}_name", *g0.dims],
                                        coords={**dict(g0.coords), f"{gr.group_by}_name": np.asarray(cats)}, name=g0.name)
         return Dataset(final)
+
+    # ------------------------------------------------------------------ differential expression (latent-space stage)
+    @property
+    def sample_info(self) -> pd.DataFrame:
+        """One row of ``adata.obs`` per sample, indexed by sample code (reference `_model.py:107-109`)."""
+        obs_df = self.adata.obs.copy()
+        obs_df["_scvi_sample"] = self._sample_codes(self.adata)
+        if self.batch_key is not None:
+            obs_df["_scvi_batch"] = pd.Categorical(obs_df[self.batch_key]).codes
+        obs_df = obs_df.loc[~obs_df._scvi_sample.duplicated("first")]
+        return obs_df.set_index("_scvi_sample").sort_index()
+
+    def _construct_design_matrix(self, sample_cov_keys, sample_mask, normalize_design_matrix, add_batch_specific_offsets,
+                                 store_lfc, store_lfc_metadata_subset=None):
+        """Reference `_model.py:1422-1529`: samples x covariates design matrix (categorical covariates one-hot encoded with
+        the first level dropped, optional 0-1 normalisation, optional per-batch offset columns in front).  Returns
+        (Xmat float32, column names, covariates_require_lfc mask, offset_indices or None)."""
+        Xmat, Xmat_names, Xmat_dim_to_key = [], [], []
+        sample_info = self.sample_info.iloc[sample_mask]
+        for key in sample_cov_keys:
+            cov = sample_info[key]
+            if (cov.dtype == str) or isinstance(cov.dtype, pd.CategoricalDtype) or cov.dtype == object or pd.api.types.is_string_dtype(cov.dtype):
+                cov = cov.astype("category").cat.remove_unused_categories()
+                cov = pd.get_dummies(cov, drop_first=True)
+                cov_names = np.array([f"{key}_{col}" for col in cov.columns])
+                cov = cov.values
+            else:
+                cov_names = np.array([key])
+                cov = cov.values[:, None]
+            Xmat.append(cov)
+            Xmat_names.append(cov_names)
+            Xmat_dim_to_key.append([key] * cov.shape[1])
+        Xmat_names = np.concatenate(Xmat_names)
+        Xmat = np.concatenate(Xmat, axis=1).astype(np.float32)
+        Xmat_dim_to_key = np.concatenate(Xmat_dim_to_key)
+        if normalize_design_matrix:
+            Xmat = (Xmat - Xmat.min(axis=0)) / (1e-6 + Xmat.max(axis=0) - Xmat.min(axis=0))
+        offset_indices = None
+        if add_batch_specific_offsets:
+            if "_scvi_batch" not in sample_info:
+                raise ValueError("add_batch_specific_offsets=True needs the model to be built with batch_key=...")
+            n_batch = int(pd.Categorical(self.adata.obs[self.batch_key]).categories.size)
+            cov = sample_info["_scvi_batch"]
+            if cov.nunique() == n_batch:
+                onehot = np.eye(n_batch)[cov.values]
+                cov_names = ["offset_batch_" + str(i) for i in range(n_batch)]
+                Xmat = np.concatenate([onehot, Xmat], axis=1).astype(np.float32)
+                Xmat_names = np.concatenate([np.array(cov_names), Xmat_names])
+                Xmat_dim_to_key = np.concatenate([np.array(cov_names), Xmat_dim_to_key])
+                offset_indices = pd.Series(np.arange(len(Xmat_names)), index=Xmat_names).loc[cov_names].values
+            else:
+                warnings.warn(
+                    "Number of batches in sample_info does not match number of batches in summary_stats. "
+                    "`add_batch_specific_offsets=True` assumes that samples are not shared across batches. "
+                    "Setting `add_batch_specific_offsets=False`...", stacklevel=2)
+        if store_lfc:
+            covariates_require_lfc = (np.isin(Xmat_dim_to_key, store_lfc_metadata_subset) if store_lfc_metadata_subset is not None
+                                      else np.isin(Xmat_dim_to_key, sample_cov_keys))
+        else:
+            covariates_require_lfc = np.zeros(len(Xmat_names), dtype=bool)
+        return Xmat, Xmat_names, covariates_require_lfc, offset_indices
+
+    @staticmethod
+    def _process_design_matrix(Xmat, admissible, lambd):
+        """``process_design_matrix`` of the reference (`_model.py:1147-1160`) in float64 on the host: per distinct
+        admissibility pattern D = diag(admissible), xtmx = X^T D X + lambd I; prefactor = real(sqrtm(xtmx)) and
+        Amat = pinv(xtmx) X^T D.  Returns (Amat, prefactor) as (K, S) / (K, K) when every cell admits every sample,
+        else per cell (n, K, S) / (n, K, K)."""
+        X = np.asarray(Xmat, dtype=np.float64)
+        K = X.shape[1]
+
+        def solve(mask):   # (P, S) bool -> (P, K, S), (P, K, K)
+            D = mask.astype(np.float64)
+            xtmx = np.einsum("sk,ps,sm->pkm", X, D, X) + lambd * np.eye(K)
+            w, V = np.linalg.eigh(xtmx)    # symmetric PSD: sqrtm = V sqrt(w) V^T (what the real part of the Schur sqrtm is)
+            pref = np.einsum("pik,pk,pjk->pij", V, np.sqrt(np.clip(w, 0.0, None)), V)
+            inv = np.linalg.pinv(xtmx, hermitian=True)
+            return np.einsum("pab,sb,ps->pas", inv, X, D), pref
+
+        adm = np.asarray(admissible, dtype=bool)
+        if adm.all():
+            A, P = solve(np.ones((1, X.shape[0]), dtype=bool))
+            return A[0], P[0]
+        pats, inverse = np.unique(adm, axis=0, return_inverse=True)
+        A, P = solve(pats)
+        inverse = np.asarray(inverse).reshape(-1)
+        return A[inverse], P[inverse]
+
+    def differential_expression(self, adata=None, sample_cov_keys: Optional[Sequence[str]] = None,
+                                sample_subset: Optional[Sequence] = None, batch_size: int = 128, use_vmap: bool = True,
+                                normalize_design_matrix: bool = True, add_batch_specific_offsets: bool = False,
+                                mc_samples: int = 100, store_lfc: bool = False, store_lfc_metadata_subset=None,
+                                store_baseline: bool = False, eps_lfc: float = 1e-4, filter_inadmissible_samples: bool = False,
+                                lambd: float = 0.0, delta: Optional[float] = 0.3, admissible_samples=None,
+                                **filter_samples_kwargs):
+        """Reference `_model.py:1012-1420`, latent-space outputs: per cell, the counterfactual shifts eps_d of every kept
+        sample (``mc_samples`` draws) are regressed on the sample covariates; returns ``beta`` (cell_name, covariate,
+        latent_dim), ``effect_size``, ``pvalue`` (chi2, df = admissible samples of the cell) and ``padj``
+        (Benjamini-Hochberg over all cells x covariates).  The device work (draws, q(z|u,s) chain, standardisation, the
+        two einsums, `_model.py:1160-1218`) is one ``mrvi_run_de_host`` call; design-matrix algebra and the tests stay on
+        the host, where the reference has them.
+
+        Not part of this path (raise): ``store_lfc`` / ``store_baseline`` (decoder), ``filter_inadmissible_samples=True``
+        (aggregated-posterior outlier detection, `_model.py:1121-1127`) -- pass its result as ``admissible_samples``
+        (n_obs, n_kept_samples) bool instead.  ``batch_size`` / ``use_vmap`` only change memory use in the reference."""
+        if store_lfc or store_baseline:
+            raise NotImplementedError("store_lfc / store_baseline evaluate the decoder, which is outside the B200 path")
+        if filter_inadmissible_samples:
+            raise NotImplementedError("filter_inadmissible_samples=True runs get_outlier_cell_sample_pairs (outside the B200 "
+                                      "path): pass its 'is_admissible' matrix as admissible_samples=")
+        if not sample_cov_keys:
+            raise ValueError("sample_cov_keys must name at least one sample covariate")
+        self._check_if_trained(warn=False)
+        if adata is not None:
+            adata.obs["_indices"] = np.arange(adata.n_obs).astype(int)   # reference `_model.py:1102-1103`
+        adata = self.adata if adata is None else adata
+        n_sample = self.dims.n_sample
+        sample_mask = np.isin(self.sample_order, sample_subset) if sample_subset is not None else np.ones(n_sample, dtype=bool)
+        sample_mask = np.array(sample_mask)
+        kept = np.where(sample_mask)[0]
+        if admissible_samples is None:
+            admissible = np.ones((adata.n_obs, len(kept)), dtype=bool)
+        else:
+            admissible = np.asarray(getattr(admissible_samples, "values", admissible_samples)).astype(bool)
+            if admissible.shape != (adata.n_obs, len(kept)):
+                raise ValueError(f"admissible_samples must have shape {(adata.n_obs, len(kept))}, not {admissible.shape}")
+        n_admissible = admissible.sum(axis=1)
+        Xmat, Xmat_names, _, _ = self._construct_design_matrix(
+            sample_cov_keys=list(sample_cov_keys), sample_mask=sample_mask, normalize_design_matrix=normalize_design_matrix,
+            add_batch_specific_offsets=add_batch_specific_offsets, store_lfc=False, store_lfc_metadata_subset=store_lfc_metadata_subset)
+        Amat, prefactor = self._process_design_matrix(Xmat, admissible, float(lambd))
+        sample_codes = self._sample_codes(adata)
+        Xh = dense_float32(adata.X)
+        res = self._handle.run_de_host(Xh, sample_codes, int(mc_samples), Amat, prefactor,
+                                       kept_samples=None if sample_subset is None else kept, seed=self.seed)
+        from scipy.stats import chi2
+
+        effect = res["effect_size"]
+        pvalue = (1.0 - chi2.cdf(effect.astype(np.float64), df=n_admissible[:, None])).astype(np.float32)   # `_model.py:1208`
+        padj = fdr_bh(pvalue.reshape(-1)).reshape(pvalue.shape)                                           # `_model.py:1363`
+        names = adata.obs_names.values
+        cov = np.asarray(Xmat_names)
+        data_vars = OrderedDict()
+        data_vars["beta"] = DataArray(res["beta"], dims=["cell_name", "covariate", "latent_dim"],
+                                      coords={"cell_name": names, "covariate": cov, "latent_dim": np.arange(res["beta"].shape[2])})
+        for name, arr in (("effect_size", effect), ("pvalue", pvalue), ("padj", padj)):
+            data_vars[name] = DataArray(arr, dims=["cell_name", "covariate"], coords={"cell_name": names, "covariate": cov})
+        if admissible_samples is not None:
+            data_vars["n_samples"] = DataArray(n_admissible, dims=["cell_name"], coords={"cell_name": names})
+        return Dataset(data_vars)
 
     def get_latent_representation(self, adata=None, indices: Optional[Sequence[int]] = None, batch_size: Optional[int] = None,
                                   use_mean: bool = True, give_z: bool = False) -> np.ndarray:

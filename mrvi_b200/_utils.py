@@ -33,3 +33,22 @@ def _parse_local_statistics_requirements(
         grouped_reductions=grouped,
         ungrouped_reductions=ungrouped,
     )
+
+
+def fdr_bh(pvals):
+    """Benjamini-Hochberg adjusted p-values: what ``multipletests(p, method="fdr_bh")[1]`` returns in the reference
+    (`_model.py:1363`; statsmodels is not a dependency here).  p_(i) * m / i over the sorted p-values, made monotone from
+    the largest downwards, clipped at 1, returned in the input's order and shape."""
+    import numpy as np
+
+    p = np.asarray(pvals, dtype=np.float64)
+    flat = p.reshape(-1)
+    m = flat.size
+    if m == 0:
+        return p.copy()
+    order = np.argsort(flat, kind="stable")
+    adj = flat[order] * (m / np.arange(1, m + 1, dtype=np.float64))
+    adj = np.minimum.accumulate(adj[::-1])[::-1]
+    out = np.empty(m, dtype=np.float64)
+    out[order] = np.minimum(adj, 1.0)
+    return out.reshape(p.shape)

@@ -753,6 +753,121 @@ static int run_sampled_host_impl(MrviHandle* h, int64_t n_cells, const float* X,
 }
 
 // ------------------------------------------------------------------------------------------
+// Differential-expression eps stage (reference _model.py:1160-1218): for every cell, mc draws of u per
+// kept counterfactual sample -> the chain's residual eps (z_base zeroed: the chain then returns eps itself, no
+// cancellation against z_base) -> per-cell standardisation over the samples, betas = Amat . eps, whitened effect sizes.
+static int run_de_host_impl(MrviHandle* h, int64_t n_cells, const float* X, int64_t ldx, const int32_t* sample_idx, int mc,
+                            uint64_t seed, int64_t cell_offset, const float* u_noise, int n_kept, const int32_t* kept,
+                            int n_cov, const float* Amat, const float* prefactor, int per_cell_design, float* beta_out,
+                            float* effect_out, float* eps_out, int64_t chunk_cells) {
+  if (!h) return fail(MRVI_ERR_INVALID_ARG, "null handle");
+  if (n_cells < 0 || (n_cells > 0 && (!X || !sample_idx))) return fail(MRVI_ERR_INVALID_ARG, "X / sample_idx is null");
+  if (ldx < h->dims.n_input) return fail(MRVI_ERR_INVALID_ARG, "ldx (%lld) < n_input (%d)", (long long)ldx, h->dims.n_input);
+  if (mc <= 0 || mc > 4096) return fail(MRVI_ERR_INVALID_ARG, "mc_samples must be in [1, 4096]");
+  if (n_cov <= 0 || n_cov > kDeMaxCov) return fail(MRVI_ERR_UNSUPPORTED, "n_covariates must be in [1, %d]", kDeMaxCov);
+  if (!Amat || !prefactor || !beta_out || !effect_out) return fail(MRVI_ERR_INVALID_ARG, "Amat / prefactor / beta_out / effect_out is null");
+  const NetW& net = h->net;
+  const int S = net.S, L = net.L, G = net.G, Lq = net.Lq, E = net.E;
+  const int Sk = kept ? n_kept : S;
+  if (Sk <= 0 || Sk > S) return fail(MRVI_ERR_INVALID_ARG, "n_kept_samples must be in [1, n_sample]");
+  for (int j = 0; kept && j < Sk; ++j)
+    if (kept[j] < 0 || kept[j] >= S) return fail(MRVI_ERR_INVALID_ARG, "kept_samples[%d] = %d outside [0, %d)", j, kept[j], S);
+  int err;
+  if ((err = validate_sample_idx(h, sample_idx, n_cells))) return err;
+  if (!h->dims.use_map) return fail(MRVI_ERR_UNSUPPORTED, "differential expression with use_map=False (sampled eps) is not implemented");
+  if (net.enc_scale.w == nullptr)
+    return fail(MRVI_ERR_PARAM, "missing parameter 'qu/NormalDistOutputNN_0/Dense_1/kernel' (scale head of q(u|x), needed by the sampled paths)");
+  if (Lq > kMaxLq) return fail(MRVI_ERR_UNSUPPORTED, "n_latent_u > %d", kMaxLq);
+  const size_t de_smem = de_stats_smem(n_cov, Sk, L);
+  if (de_smem > (size_t)kMaxSmemOptin) return fail(MRVI_ERR_UNSUPPORTED, "n_covariates x n_samples too large for the statistics kernel");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaFuncSetAttribute(k_de_stats, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemOptin));
+  // ---- chunk: (cell, draw) virtual cells of the chain; staging bounded to ~6 GiB (of 180)
+  const int64_t per_cell = (int64_t)mc * S * (Lq + E + 2 * L) * 4 + (int64_t)G * 4;
+  if (h->chunk_cells / mc < 1) return fail(MRVI_ERR_UNSUPPORTED, "mc_samples=%d too large for the workspace", mc);
+  int64_t ch = std::max<int64_t>(1, std::min<int64_t>(h->chunk_cells / mc, (6144ll << 20) / per_cell));
+  if (chunk_cells > 0) ch = std::min(ch, chunk_cells);
+  ch = std::min<int64_t>(ch, std::max<int64_t>(n_cells, 1));
+  const int64_t nvmax = ch * mc;
+
+  DeviceArena ws;
+  cudaStream_t st = nullptr;
+  float *dX, *d_scale, *d_eps, *d_A, *d_P, *d_beta, *d_eff, *d_unoise = nullptr;
+  int32_t *d_sid, *d_kept = nullptr;
+  CellBuf rcb{};
+  const int64_t design_cells = per_cell_design ? ch : 1;
+  CUDA_TRY(ws.alloc((void**)&dX, ch * G * sizeof(float)));
+  CUDA_TRY(ws.alloc((void**)&d_sid, ch * sizeof(int32_t)));
+  CUDA_TRY(ws.alloc((void**)&d_scale, ch * Lq * sizeof(float)));
+  CUDA_TRY(ws.alloc((void**)&rcb.u_ln, nvmax * S * Lq * sizeof(float)));
+  CUDA_TRY(ws.alloc((void**)&rcb.q_tok, nvmax * S * E * sizeof(float)));
+  CUDA_TRY(ws.alloc((void**)&rcb.zbase, nvmax * S * L * sizeof(float)));
+  rcb.per_row = 1;
+  CUDA_TRY(ws.alloc((void**)&d_eps, nvmax * S * L * sizeof(float)));
+  CUDA_TRY(ws.alloc((void**)&d_A, design_cells * n_cov * Sk * sizeof(float)));
+  CUDA_TRY(ws.alloc((void**)&d_P, design_cells * n_cov * n_cov * sizeof(float)));
+  CUDA_TRY(ws.alloc((void**)&d_beta, ch * n_cov * L * sizeof(float)));
+  CUDA_TRY(ws.alloc((void**)&d_eff, ch * n_cov * sizeof(float)));
+  if (kept) {
+    CUDA_TRY(ws.alloc((void**)&d_kept, Sk * sizeof(int32_t)));
+    CUDA_TRY(cudaMemcpyAsync(d_kept, kept, Sk * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  }
+  if (u_noise) {
+    CUDA_TRY(ws.alloc((void**)&d_unoise, (size_t)S * mc * n_cells * Lq * sizeof(float)));
+    CUDA_TRY(cudaMemcpyAsync(d_unoise, u_noise, (size_t)S * mc * n_cells * Lq * sizeof(float), cudaMemcpyHostToDevice, st));
+  }
+  if (!per_cell_design) {
+    CUDA_TRY(cudaMemcpyAsync(d_A, Amat, (size_t)n_cov * Sk * sizeof(float), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_P, prefactor, (size_t)n_cov * n_cov * sizeof(float), cudaMemcpyHostToDevice, st));
+  }
+  h->ev_used = 0;
+  CUDA_TRY(cudaEventRecord(h->ev_call[0], st));
+  for (int64_t lo = 0; lo < n_cells; lo += ch) {
+    const int64_t m = std::min(ch, n_cells - lo), nv = m * mc;
+    CUDA_TRY(cudaMemcpy2DAsync(dX, (size_t)G * sizeof(float), X + lo * ldx, (size_t)ldx * sizeof(float), (size_t)G * sizeof(float),
+                               (size_t)m, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(d_sid, sample_idx + lo, m * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    if (per_cell_design) {
+      CUDA_TRY(cudaMemcpyAsync(d_A, Amat + (size_t)lo * n_cov * Sk, (size_t)m * n_cov * Sk * sizeof(float), cudaMemcpyHostToDevice, st));
+      CUDA_TRY(cudaMemcpyAsync(d_P, prefactor + (size_t)lo * n_cov * n_cov, (size_t)m * n_cov * n_cov * sizeof(float), cudaMemcpyHostToDevice, st));
+    }
+    CellBuf ecb = h->cb;
+    ecb.u_scale = d_scale;
+    {
+      const float* h1 = nullptr;
+      if (h->precision == MRVI_PRECISION_TC && h->enc_tc.ready) {
+        enc_tc_launch(h->enc_tc, dX, G, m, G, h->h1buf, st);
+        LAUNCH_CHECK();
+        h1 = h->h1buf;
+      }
+      k_encoder_fp32<<<(unsigned)((m + kTM - 1) / kTM), kThreads, h->enc_smem, st>>>(h->net, dX, G, d_sid, m, ecb, h->enc_ldh,
+                                                                                    h->enc_ldhid, (G % 4) == 0, h1);
+      LAUNCH_CHECK();
+    }
+    {
+      const int64_t rows = nv * S;
+      k_sample_rows<<<(unsigned)((rows + 127) / 128), 128, 0, st>>>(h->net, ecb.u, d_scale, m, mc, S, d_unoise, lo, n_cells,
+                                                                   cell_offset + lo, seed, 0u, rcb.u_ln, rcb.q_tok, rcb.zbase);
+      LAUNCH_CHECK();
+      CUDA_TRY(cudaMemsetAsync(rcb.zbase, 0, (size_t)rows * L * sizeof(float), st));   // chain output = eps
+    }
+    GroupPlan none;
+    memset(&none, 0, sizeof(none));
+    if ((err = chain_and_dist(h, rcb, nv, MRVI_NORM_L2, d_eps, d_eps, nullptr, none, st))) return err;
+    k_de_stats<<<(unsigned)m, kDeWarps * 32, de_smem, st>>>(d_eps, m, mc, S, L, d_kept, Sk, n_cov, d_A, d_P, per_cell_design ? 1 : 0,
+                                                            d_beta, d_eff);
+    LAUNCH_CHECK();
+    CUDA_TRY(cudaMemcpyAsync(beta_out + (size_t)lo * n_cov * L, d_beta, (size_t)m * n_cov * L * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(effect_out + (size_t)lo * n_cov, d_eff, (size_t)m * n_cov * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (eps_out) CUDA_TRY(cudaMemcpyAsync(eps_out + (size_t)lo * mc * S * L, d_eps, (size_t)nv * S * L * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+  }
+  CUDA_TRY(cudaEventRecord(h->ev_call[1], st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
 // NCCL, resolved at run time (dlopen): the library has no link-time dependency on it, and inside a torch process the
 // already loaded libnccl.so.2 is picked up.
 struct NcclApi {
@@ -1179,6 +1294,14 @@ int mrvi_run_sampled_host(MrviHandle* h, int64_t n_cells, const float* X, int64_
                           float* z_out, int64_t chunk_cells) {
   return run_sampled_host_impl(h, n_cells, X, ldx, sample_idx, mc_samples, seed, cell_offset, u_noise, base_noise, n_keys,
                                group_codes, n_groups, norm, normalize, cell_out, group_sums, group_counts, z_out, chunk_cells);
+}
+
+int mrvi_run_de_host(MrviHandle* h, int64_t n_cells, const float* X, int64_t ldx, const int32_t* sample_idx, int32_t mc_samples,
+                     uint64_t seed, int64_t cell_offset, const float* u_noise, int32_t n_kept_samples, const int32_t* kept_samples,
+                     int32_t n_covariates, const float* Amat, const float* prefactor, int32_t per_cell_design, float* beta_out,
+                     float* effect_size_out, float* eps_out, int64_t chunk_cells) {
+  return run_de_host_impl(h, n_cells, X, ldx, sample_idx, mc_samples, seed, cell_offset, u_noise, n_kept_samples, kept_samples,
+                          n_covariates, Amat, prefactor, per_cell_design, beta_out, effect_size_out, eps_out, chunk_cells);
 }
 
 #ifdef MRVI_DBG_F3

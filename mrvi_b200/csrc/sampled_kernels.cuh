@@ -184,4 +184,98 @@ k_normalize_mc(const float* __restrict__ dv, const float* __restrict__ mu, const
   if (gp.n_keys && cur_cell >= 0) flush_entry(gp, cur_cell, S, e / S, e % S, acc);
 }
 
+// ----------------------------------------------------------------------------------------
+// Differential-expression eps stage (reference _model.py:1196-1215, 1283).
+// eps [n_cells * mc][S][L] are the residuals of the chain for every (cell, draw).  Per (cell, draw a, latent d):
+//   x_s = (eps[s, d] - mean_s eps[., d]) / (1e-6 + std_s eps[., d])      over the KEPT samples (population std)
+//   beta[k, d] = sum_s Amat[cell][k, s] x_s                                MLE of the per-cell linear model
+//   bn[l, d]   = sum_k beta[k, d] prefactor[cell][k, l]                    whitened coefficients
+//   effect_size[cell, l] = mean_a sum_d bn[l, d]^2 ;  beta_out[cell, k, d] = mean_a beta[k, d] * std
+// One CTA (4 warps) per cell: warps take draws round-robin, lanes take latent dims; per-warp accumulators in shared
+// memory are combined in a fixed order at the end (run-to-run deterministic).
+// ----------------------------------------------------------------------------------------
+constexpr int kDeWarps = 4;
+constexpr int kDeMaxCov = 64;
+
+inline size_t de_stats_smem(int K, int Sk, int L) {
+  const int K8 = (K + 7) / 8 * 8, Lp = (L + 31) / 32 * 32;
+  return ((size_t)K8 * Sk + (size_t)K * K + (size_t)kDeWarps * K8 * 32 + (size_t)kDeWarps * K * Lp + (size_t)kDeWarps * K) * sizeof(float) +
+         (size_t)Sk * sizeof(int);
+}
+
+__global__ void __launch_bounds__(kDeWarps * 32)
+k_de_stats(const float* __restrict__ eps, int64_t n_cells, int mc, int S, int L, const int32_t* __restrict__ kept, int Sk,
+           int K, const float* __restrict__ Amat, const float* __restrict__ pref, int per_cell,
+           float* __restrict__ beta_out, float* __restrict__ effect_out) {
+  extern __shared__ __align__(16) float de_sm[];
+  const int K8 = (K + 7) / 8 * 8, Lp = (L + 31) / 32 * 32;
+  float* A = de_sm;                              // [K8][Sk], rows >= K zero
+  float* P = A + (size_t)K8 * Sk;                // [K][K]
+  float* bw = P + (size_t)K * K;                 // [warps][K8][32] betas of the current (draw, 32 latent dims)
+  float* bacc = bw + (size_t)kDeWarps * K8 * 32; // [warps][K][Lp]
+  float* tacc = bacc + (size_t)kDeWarps * K * Lp;// [warps][K]
+  int* ks = reinterpret_cast<int*>(tacc + kDeWarps * K);
+  const int64_t cell = blockIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const float* Ac = Amat + (per_cell ? (size_t)cell * K * Sk : 0);
+  const float* Pc = pref + (per_cell ? (size_t)cell * K * K : 0);
+  for (int i = tid; i < K8 * Sk; i += blockDim.x) A[i] = (i < K * Sk) ? __ldg(Ac + i) : 0.f;
+  for (int i = tid; i < K * K; i += blockDim.x) P[i] = __ldg(Pc + i);
+  for (int i = tid; i < kDeWarps * K * Lp; i += blockDim.x) bacc[i] = 0.f;
+  for (int i = tid; i < kDeWarps * K; i += blockDim.x) tacc[i] = 0.f;
+  for (int i = tid; i < Sk; i += blockDim.x) ks[i] = kept ? kept[i] : i;
+  __syncthreads();
+  float* bww = bw + (size_t)warp * K8 * 32;
+  float* baw = bacc + (size_t)warp * K * Lp;
+  const float inv_sk = 1.0f / (float)Sk;
+  for (int a = warp; a < mc; a += kDeWarps) {
+    const float* base = eps + ((size_t)(cell * mc + a) * S) * L;
+    for (int d0 = 0; d0 < L; d0 += 32) {
+      const int d = d0 + lane;
+      const bool act = d < L;
+      const float* col = base + (act ? d : 0);
+      float s1 = 0.f;
+      for (int j = 0; j < Sk; ++j) s1 += col[(size_t)ks[j] * L];
+      const float mean = s1 * inv_sk;
+      float s2 = 0.f;
+      for (int j = 0; j < Sk; ++j) { const float dv = col[(size_t)ks[j] * L] - mean; s2 = fmaf(dv, dv, s2); }
+      const float sd = sqrtf(s2 * inv_sk);
+      const float rs = 1.0f / (1e-6f + sd);
+      for (int k0 = 0; k0 < K8; k0 += 8) {
+        float b[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int j = 0; j < Sk; ++j) {
+          const float x = (col[(size_t)ks[j] * L] - mean) * rs;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) b[q] = fmaf(A[(size_t)(k0 + q) * Sk + j], x, b[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) bww[(k0 + q) * 32 + lane] = b[q];
+      }
+      __syncwarp();
+      if (act)
+        for (int k = 0; k < K; ++k) baw[k * Lp + d] = fmaf(bww[k * 32 + lane], sd, baw[k * Lp + d]);
+      for (int l = 0; l < K; ++l) {
+        float bn = 0.f;
+        for (int k = 0; k < K; ++k) bn = fmaf(bww[k * 32 + lane], P[k * K + l], bn);
+        const float t = warp_sum(act ? bn * bn : 0.f);
+        if (lane == 0) tacc[warp * K + l] += t;
+      }
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  const float inv_mc = 1.0f / (float)mc;
+  for (int i = tid; i < K * L; i += blockDim.x) {
+    const int k = i / L, d = i % L;
+    float v = 0.f;
+    for (int w = 0; w < kDeWarps; ++w) v += bacc[((size_t)w * K + k) * Lp + d];
+    beta_out[(size_t)cell * K * L + i] = v * inv_mc;
+  }
+  for (int l = tid; l < K; l += blockDim.x) {
+    float v = 0.f;
+    for (int w = 0; w < kDeWarps; ++w) v += tacc[w * K + l];
+    effect_out[(size_t)cell * K + l] = v * inv_mc;
+  }
+}
+
 }  // namespace mrvi

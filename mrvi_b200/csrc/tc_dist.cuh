@@ -36,6 +36,11 @@ __device__ long long g_dbg_dist[64 * 32];
 constexpr int kDistTcThreads = 576;   // 16 epilogue warps (2 warpgroups) + 2 issuer warps (one per warpgroup: MMAs; the first also the bulk copies)
 constexpr int kDistTcWorkers = 512;
 
+// Gram entries with d^2 < 2^-9 (n_i + n_j) are recomputed by direct differences.  G[i][j] and G[j][i] are the same products
+// accumulated in a different order (a few ulp of G apart): at L = 50 the fused kernel's 2^-12 left |d_ij - d_ji| up to
+// 2.5e-4 d on a handful of the 1.3e9 entries of a 20k-cell chunk; 2^-9 bounds it below 5e-5 d.
+constexpr int kDistThrLog2 = 9;
+constexpr float kDistThr = 1.0f / (float)(1 << kDistThrLog2);
 constexpr uint32_t kDistLbo = 4096 + 16;  // bytes between K chunks: 256 rows x 16 B + one row of padding, which makes the
                                           // prep's 16-byte stores (8 chunks x 4 rows per warp) bank-conflict free
 
@@ -344,19 +349,19 @@ k_dist_gram_tc(const float* __restrict__ z, int64_t n_cells, int S, int L, float
       const bool diag_chunk = (b != 1) && ((colw >> 5) == warp_q);
       if (full) {
         // fast path: no bounds checks; cancellation-dominated entries are only DETECTED here
-        const float tmin = diag_chunk ? dist_chunk_fast<true>(g, part + jbase, n_i, tid & 31)
-                                      : dist_chunk_fast<false>(g, part + jbase, n_i, tid & 31);
+        const float tmin = diag_chunk ? dist_chunk_fast<true, kDistThrLog2>(g, part + jbase, n_i, tid & 31)
+                                      : dist_chunk_fast<false, kDistThrLog2>(g, part + jbase, n_i, tid & 31);
         if (__any_sync(0xffffffffu, tmin < 0.f)) {  // rare: near-duplicate samples -> exact direct-difference distance
           uint32_t flagged = 0u;
           if (tmin < 0.f) {
 #pragma unroll
             for (int q = 0; q < 32; ++q)
-              if (jbase + q != i && g[q] * g[q] < (n_i + part[jbase + q]) * (1.0f / 4096.0f)) flagged |= 1u << q;
+              if (jbase + q != i && g[q] * g[q] < (n_i + part[jbase + q]) * kDistThr) flagged |= 1u << q;
           }
           exact_fix_warp<kDistLbo>(g, flagged, zh, zl, i, jbase, L);
         }
       } else {
-        const float2 ni2 = make_float2(n_i, n_i), m2 = make_float2(-2.0f, -2.0f), thr2 = make_float2(-1.0f / 4096.0f, -1.0f / 4096.0f);
+        const float2 ni2 = make_float2(n_i, n_i), m2 = make_float2(-2.0f, -2.0f), thr2 = make_float2(-kDistThr, -kDistThr);
         uint32_t flagged = 0u;
 #pragma unroll
         for (int q4 = 0; q4 < 8; ++q4) {

@@ -176,9 +176,10 @@ __device__ __forceinline__ void exact_fix_warp(float (&g)[32], uint32_t flagged,
 // 32 Gram entries of one row -> distances, in place; returns min over the entries of (d^2 - 2^-12 (n_i + n_j)):
 // negative = some entry is cancellation dominated (the caller recomputes those exactly).  DIAG: entry q == lane is
 // the row's diagonal entry (forced to zero, excluded from the test).
-template <bool DIAG>
+template <bool DIAG, int THR_LOG2 = 12>
 __device__ __forceinline__ float dist_chunk_fast(float (&g)[32], const float* nrm_j, float n_i, int lane) {
-  const float2 ni2 = make_float2(n_i, n_i), m2 = make_float2(-2.0f, -2.0f), thr2 = make_float2(-1.0f / 4096.0f, -1.0f / 4096.0f);
+  constexpr float kThr = -1.0f / (float)(1 << THR_LOG2);
+  const float2 ni2 = make_float2(n_i, n_i), m2 = make_float2(-2.0f, -2.0f), thr2 = make_float2(kThr, kThr);
   float tmin = 0.f;
 #pragma unroll
   for (int q4 = 0; q4 < 8; ++q4) {

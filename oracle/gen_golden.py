@@ -138,6 +138,95 @@ def reference_z(flat, dims, vae_kwargs, X, sid):
     return np.stack(zs, axis=1)  # out_axes=-2  ->  (cell, sample, latent)
 
 
+def _reference_source_block(first_marker, last_marker):
+    """Dedented source lines of `_model.py` from the line containing ``first_marker`` to the one containing
+    ``last_marker`` (inclusive): the reference's own statements, executed below, never copied into this repo."""
+    import textwrap
+
+    lines = open(os.path.join(REF_SRC, "_model.py")).read().splitlines()
+    i0 = next(i for i, l in enumerate(lines) if first_marker in l)
+    i1 = next(i for i in range(i0, len(lines)) if last_marker in lines[i])
+    return textwrap.dedent("\n".join(lines[i0:i1 + 1]))
+
+
+def reference_de(flat, dims, vae_kwargs, X, sid, noise_u, Xmat, admissible, lambd, samples):
+    """The differential-expression eps stage through the reference's own code: eps_ from
+    ``MrVAE.inference(use_mean=False, mc_samples)["eps"]`` on the flax shim for every kept counterfactual sample
+    (`_model.py:1175-1194`, ``out_axes=-2``), then the reference's own statements for the design matrix
+    (`_model.py:1152-1158`) and for the statistics (`_model.py:1196-1215`) EXECUTED from its source file with
+    ``jnp`` -> numpy, ``jax.vmap`` -> a python loop, ``jax.scipy`` -> scipy."""
+    import scipy.linalg
+    import scipy.stats
+
+    components, module = load_reference_modules()
+    npd = components.dist
+    vae = module.MrVAE(n_input=dims.n_input, n_sample=dims.n_sample, n_batch=2, n_labels=1, n_continuous_cov=0,
+                       training=False, **vae_kwargs)
+    variables = {"params": _tree_with_scale_head(flat)}
+    x = np.asarray(X, dtype=np.float64)
+    sample_index = np.asarray(sid, dtype=np.float64).reshape(-1, 1)
+    mc = noise_u.shape[1]
+    eps_list = []
+    try:
+        for s in samples:
+            npd.NOISE_PROVIDER = lambda key, shape, s=s: {"u": noise_u[s]}[key]
+            cf = np.full((x.shape[0], 1), s)
+            out = vae.apply(variables, method=vae.inference, x=x, sample_index=sample_index, cf_sample=cf,
+                            use_mean=False, mc_samples=mc)
+            eps_list.append(np.asarray(out["eps"]))  # (mc, n, L)
+    finally:
+        npd.NOISE_PROVIDER = None
+    eps_ = np.stack(eps_list, axis=-2)  # (mc, n, S_kept, L)
+
+    class _NS:
+        pass
+
+    jnp = _NS()
+    jnp.einsum, jnp.eye, jnp.real = np.einsum, np.eye, np.real
+    jnp.linalg = _NS()
+    jnp.linalg.pinv = np.linalg.pinv
+    jax = _NS()
+    jax.vmap = lambda f: (lambda a: np.stack([f(ai) for ai in a]))
+    jax.scipy = _NS()
+    jax.scipy.linalg, jax.scipy.stats = scipy.linalg, scipy.stats
+    adm = np.asarray(admissible)
+    ns = {"jnp": jnp, "jax": jax, "lambd": lambd, "n_covariates": Xmat.shape[1], "Xmat": np.asarray(Xmat, dtype=np.float64),
+          "admissible_samples_dmat": np.stack([np.diag(a) for a in adm]).astype(float),   # `_model.py:1330-1332`
+          "n_samples_per_cell": adm.sum(axis=1), "eps_": eps_}
+    exec(_reference_source_block("xtmx = jnp.einsum(", "Amat = jnp.einsum("), ns)
+    exec(_reference_source_block("eps_std = eps_.std(axis=2, keepdims=True)", "betas = betas * eps_std"), ns)
+    return {"eps": eps_, "Amat": ns["Amat"], "prefactor": ns["prefactor"], "beta": ns["betas"].mean(0),   # "beta": `_model.py:1283`
+            "effect_size": ns["ts"], "pvalue": ns["pvals"]}
+
+
+DE_CASES = {
+    # name: (MrviDims kwargs, MrVAE kwargs, n_cells, mc_samples, n_covariates, sample subset or None, lambd, seeds)
+    "de_S6_mc4": (dict(n_input=80, n_sample=6), dict(), 20, 4, 2, None, 0.0, (20, 21)),
+    "de_S9_subset_mc3": (dict(n_input=50, n_sample=9, n_latent=12, n_latent_u=6), dict(n_latent=12, n_latent_u=6), 16, 3, 3,
+                         (0, 2, 3, 5, 6, 8), 0.1, (22, 23)),
+}
+
+
+def make_de_case(name):
+    sys.path.insert(0, ROOT)
+    import mrvi_b200
+
+    dk, vk, n, mc, K, subset, lambd, (pseed, xseed) = DE_CASES[name]
+    dims = mrvi_b200.MrviDims(**dk)
+    flat = mrvi_b200.init_params(dims, seed=pseed)
+    flat["qu/NormalDistOutputNN_0/Dense_1/bias"] = flat["qu/NormalDistOutputNN_0/Dense_1/bias"] - 2.0
+    X = mrvi_b200.synthetic_counts(n, dims.n_input, seed=xseed)
+    rng = np.random.default_rng(xseed)
+    sid = rng.integers(0, dims.n_sample, n).astype(np.int32)
+    noise_u = rng.standard_normal((dims.n_sample, mc, n, dims.n_latent_q))
+    samples = np.arange(dims.n_sample) if subset is None else np.asarray(subset)
+    Xmat = rng.random((len(samples), K))
+    Xmat[:, 0] = (np.arange(len(samples)) % 2).astype(float)   # one binary covariate, as a one-hot encoded category
+    admissible = rng.random((n, len(samples))) < 0.85           # some inadmissible (cell, sample) pairs
+    admissible[0] = True
+    return dims, vk, flat, X, sid, noise_u, Xmat, admissible, lambd, samples
+
+
 SAMPLED_CASES = {
     # name: (MrviDims kwargs, MrVAE kwargs, n_cells, mc_samples, seeds)
     "sampled_S4_mc3": (dict(n_input=100, n_sample=4), dict(), 24, 3, (10, 11)),
@@ -194,6 +283,13 @@ def main():
                             z=z, base_mean=mu, base_var=var,
                             **{"param|" + k.replace("/", "|"): v for k, v in flat.items()})
         print(f"{name}: sampled z {z.shape}, baseline mean {mu.mean():.4f} var {var.mean():.4f}")
+    for name in DE_CASES:
+        dims, vk, flat, X, sid, noise_u, Xmat, admissible, lambd, samples = make_de_case(name)
+        r = reference_de(flat, dims, vk, X, sid, noise_u, Xmat, admissible, lambd, samples)
+        np.savez_compressed(os.path.join(out_dir, f"{name}.npz"), X=X, sid=sid, noise_u=noise_u, Xmat=Xmat, admissible=admissible,
+                            lambd=lambd, samples=samples, **r,
+                            **{"param|" + k.replace("/", "|"): v for k, v in flat.items()})
+        print(f"{name}: eps {r['eps'].shape}, beta {r['beta'].shape}, effect_size median {np.median(r['effect_size']):.3f}")
 
 
 if __name__ == "__main__":

@@ -351,3 +351,82 @@ def sampled_local_sample_distances(flat, X, sample_idx, noise_u, noise_base=None
         return d
     mu, var = local_baseline_dists(flat, X, sample_idx, noise_base, dtype=dtype)
     return ((d - mu[:, None, None, None]) / np.sqrt(var)[:, None, None, None]).mean(axis=1)
+
+
+# --------------------------------------------------------------------------- DE eps stage
+# `MrVI.differential_expression` (`_model.py:1012-1420`) up to its latent-space outputs (beta, effect_size, pvalue,
+# padj).  The LFC / baseline-expression outputs go through the decoder and are out of the path's scope.
+
+
+def sampled_counterfactual_eps(flat, x, sid, noise_u, noise_eps=None, dtype=np.float64, samples=None):
+    """``inference(..., use_mean=False, mc_samples=mc)["eps"]`` vmapped over the counterfactual samples with
+    ``out_axes=-2`` (`_model.py:1175-1194`): (mc, n, S_kept, L).  ``noise_u[s]`` (mc, n, Lq) are the draws of the
+    vmapped call of sample s (`_module.py:315-318`); ``samples`` = the kept sample codes (`_model.py:1310-1312`)."""
+    p = cast_params(flat, dtype)
+    x = np.asarray(x, dtype=dtype)
+    sid = np.asarray(sid).astype(np.int64).reshape(-1)
+    noise_u = np.asarray(noise_u, dtype=dtype)
+    S = p["qz/Embed_0/embedding"].shape[0]
+    samples = np.arange(S) if samples is None else np.asarray(samples)
+    mean, scale = encoder_xu(p, x, sid)
+    out = []
+    for s in samples:
+        u = mean[None] + scale[None] * noise_u[s]  # (mc, n, Lq)
+        lead = u.shape[:-1]
+        cf = np.full(lead, s, dtype=np.int64).reshape(-1)
+        z_base, eps = encoder_uz(p, u.reshape(-1, u.shape[-1]), cf)
+        L = z_base.shape[-1]
+        if eps.shape[-1] == 2 * L:  # use_map=False: eps ~ Normal(loc, softplus(raw) + 1e-3) (`_module.py:326-329`)
+            loc, raw = eps[:, :L], eps[:, L:]
+            eps = loc + (softplus(raw) + loc.dtype.type(1e-3)) * np.asarray(noise_eps, dtype=dtype)[s].reshape(-1, L)
+        out.append(eps.reshape(*lead, L))
+    return np.stack(out, axis=2)
+
+
+def de_process_design_matrix(Xmat, admissible, lambd=0.0):
+    """``process_design_matrix`` (`_model.py:1147-1160`): per cell, with D = diag(admissible samples),
+    xtmx = X^T D X + lambd I, prefactor = real(sqrtm(xtmx)), Amat = pinv(xtmx) X^T D.
+    Xmat (S_kept, K), admissible (n, S_kept) bool -> Amat (n, K, S_kept), prefactor (n, K, K)."""
+    import scipy.linalg
+
+    Xmat = np.asarray(Xmat, dtype=np.float64)
+    adm = np.asarray(admissible, dtype=np.float64)
+    K = Xmat.shape[1]
+    xtmx = np.einsum("ak,nk,km->nam", Xmat.T, adm, Xmat) + lambd * np.eye(K)
+    prefactor = np.stack([np.real(scipy.linalg.sqrtm(m)) for m in xtmx])
+    inv_ = np.stack([np.linalg.pinv(m) for m in xtmx])
+    Amat = np.einsum("nab,bc,nc->nac", inv_, Xmat.T, adm)
+    return Amat, prefactor
+
+
+def de_statistics(eps_, Amat, prefactor, n_samples_per_cell):
+    """The latent-space statistics of `_model.py:1196-1215`: standardise eps over the samples (population std,
+    ``1e-6 +`` in the denominator), betas = Amat . eps, whitened by ``prefactor``; effect size = mean over the mc
+    draws of the squared norm over latent dims, p-value = chi2 survival with df = admissible samples of the cell;
+    returned betas are rescaled by the std and averaged over the draws (`:1283`).
+    eps_ (mc, n, S, L) -> beta (n, K, L), effect_size (n, K), pvalue (n, K)."""
+    import scipy.stats
+
+    eps_ = np.asarray(eps_)
+    eps_std = eps_.std(axis=2, keepdims=True)
+    eps_mean = eps_.mean(axis=2, keepdims=True)
+    eps = (eps_ - eps_mean) / (1e-6 + eps_std)
+    betas = np.einsum("nks,ansd->ankd", Amat, eps)
+    betas_norm = np.einsum("ankd,nkl->anld", betas, prefactor)
+    ts = (betas_norm ** 2).mean(axis=0).sum(axis=-1)
+    pvals = 1 - scipy.stats.chi2.cdf(ts, df=np.asarray(n_samples_per_cell)[:, None])
+    betas = betas * eps_std
+    return betas.mean(0), ts, pvals
+
+
+def fdr_bh(pvals):
+    """Benjamini-Hochberg adjusted p-values, ``statsmodels.stats.multitest.multipletests(p, method="fdr_bh")[1]``
+    (`_model.py:1363`): p_(i) * m / i, made monotone from the largest p downwards, clipped to 1."""
+    p = np.asarray(pvals, dtype=np.float64).reshape(-1)
+    m = p.size
+    order = np.argsort(p)
+    ranked = p[order] * m / np.arange(1, m + 1)
+    ranked = np.minimum.accumulate(ranked[::-1])[::-1]
+    out = np.empty(m)
+    out[order] = np.minimum(ranked, 1.0)
+    return out.reshape(np.shape(pvals))

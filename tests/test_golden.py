@@ -12,8 +12,9 @@ from oracle import gen_golden as gg
 from oracle import mrvi_oracle as orc
 
 _ALL = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
-GOLDEN = [p for p in _ALL if not os.path.basename(p).startswith("sampled_")]
+GOLDEN = [p for p in _ALL if not os.path.basename(p).startswith(("sampled_", "de_"))]
 SAMPLED = [p for p in _ALL if os.path.basename(p).startswith("sampled_")]
+DE = [p for p in _ALL if os.path.basename(p).startswith("de_")]
 
 
 def _load(path):
@@ -25,6 +26,7 @@ def _load(path):
 def test_golden_files_exist():
     assert {os.path.basename(p)[:-4] for p in GOLDEN} == set(gg.CASES)
     assert {os.path.basename(p)[:-4] for p in SAMPLED} == set(gg.SAMPLED_CASES)
+    assert {os.path.basename(p)[:-4] for p in DE} == set(gg.DE_CASES)
 
 
 def _load_sampled(path):
@@ -51,6 +53,31 @@ def test_sampled_goldens_regenerate_from_reference_source(name):
     z, mu, var = gg.reference_sampled(flat, dims, vk, X, sid, noise_u, noise_base)
     stored = np.load(os.path.join(os.path.dirname(__file__), "golden", f"{name}.npz"))
     assert np.abs(z - stored["z"]).max() < 1e-13 and np.abs(mu - stored["base_mean"]).max() < 1e-13
+
+
+@pytest.mark.parametrize("path", DE, ids=[os.path.basename(p)[:-4] for p in DE])
+def test_oracle_de_stage_matches_reference_source_goldens(path):
+    """Differential-expression eps stage: eps from the reference's inference on the shim, design-matrix
+    processing and statistics from the reference's own statements (`_model.py:1152-1158, 1196-1215`, executed from its
+    source by gen_golden.reference_de) vs the oracle restatement."""
+    flat, g = _load_sampled(path)
+    eps = orc.sampled_counterfactual_eps(flat, g["X"], g["sid"], g["noise_u"], samples=g["samples"])
+    assert eps.shape == g["eps"].shape and np.abs(eps - g["eps"]).max() < 1e-12
+    A, P = orc.de_process_design_matrix(g["Xmat"], g["admissible"], float(g["lambd"]))
+    assert np.abs(A - g["Amat"]).max() < 1e-12 and np.abs(P - g["prefactor"]).max() < 1e-12
+    beta, ts, pv = orc.de_statistics(eps, A, P, g["admissible"].sum(axis=1))
+    assert np.abs(beta - g["beta"]).max() < 1e-12 and np.abs(ts - g["effect_size"]).max() < 1e-10 * np.abs(ts).max()
+    assert np.abs(pv - g["pvalue"]).max() < 1e-12
+
+
+@pytest.mark.skipif(not gg.reference_available(), reason="/root/reference only exists in the build container")
+@pytest.mark.parametrize("name", list(gg.DE_CASES))
+def test_de_goldens_regenerate_from_reference_source(name):
+    case = gg.make_de_case(name)
+    r = gg.reference_de(case[2], case[0], case[1], *case[3:])
+    stored = np.load(os.path.join(os.path.dirname(__file__), "golden", f"{name}.npz"))
+    for k in ("eps", "Amat", "prefactor", "beta", "effect_size", "pvalue"):
+        assert np.abs(r[k] - stored[k]).max() <= 1e-13 * max(1.0, np.abs(stored[k]).max()), k
 
 
 @pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])

@@ -206,3 +206,59 @@ def test_host_narrowing_of_integer_matrices(built_library):
     assert _capi._X_DTYPES[np.dtype(np.int32)] == 3 and _capi._X_DTYPES[np.dtype(np.int64)] == 4
     header = open(os.path.join(ROOT, "include", "mrvi_b200.h")).read()
     assert "MRVI_X_INT32 = 3" in header and "MRVI_X_INT64 = 4" in header
+
+
+def test_de_design_matrix_algebra_matches_oracle():
+    """Host side of `differential_expression`: `process_design_matrix` (reference `_model.py:1147-1160`) restated with
+    eigh / hermitian pinv per distinct admissibility pattern vs the oracle's literal per-cell sqrtm / pinv."""
+    from mrvi_b200._model import MrVI
+    from oracle import mrvi_oracle as orc
+
+    rng = np.random.default_rng(0)
+    Xmat = rng.random((9, 4))
+    adm = rng.random((40, 9)) < 0.8
+    adm[0] = True
+    for lambd in (0.0, 0.3):
+        A, P = MrVI._process_design_matrix(Xmat, adm, lambd)
+        A2, P2 = orc.de_process_design_matrix(Xmat, adm, lambd)
+        assert A.shape == (40, 4, 9) and np.abs(A - A2).max() < 1e-10
+        assert np.abs(P - P2).max() < 1e-6   # scipy's Schur sqrtm itself is ~1e-8 on the ill-conditioned patterns
+    A, P = MrVI._process_design_matrix(Xmat, np.ones((40, 9), dtype=bool), 0.0)
+    A2, P2 = orc.de_process_design_matrix(Xmat, np.ones((1, 9), dtype=bool), 0.0)
+    assert A.shape == (4, 9) and np.abs(A - A2[0]).max() < 1e-10 and np.abs(P - P2[0]).max() < 1e-6
+    # least squares: Amat @ Xmat = I when every sample is admissible and X has full column rank
+    assert np.abs(A @ Xmat - np.eye(4)).max() < 1e-9
+
+
+def test_fdr_bh_known_answers():
+    from mrvi_b200._utils import fdr_bh
+    from oracle import mrvi_oracle as orc
+
+    p = np.array([0.01, 0.04, 0.03, 0.005])
+    assert np.allclose(fdr_bh(p), [0.02, 0.04, 0.04, 0.02])          # p_(i) m / i, monotone from the top
+    assert np.allclose(fdr_bh(np.array([[0.5, 0.9], [1.0, 0.2]])), [[1.0, 1.0], [1.0, 0.8]])
+    q = np.random.default_rng(1).random((7, 5)) ** 4
+    assert np.abs(fdr_bh(q) - orc.fdr_bh(q)).max() < 1e-15 and fdr_bh(q).shape == q.shape
+
+
+def test_de_construct_design_matrix_layout():
+    """`_construct_design_matrix` (reference `_model.py:1422-1529`): one-hot with the first level dropped, names
+    `{key}_{level}`, 0-1 normalisation, offset columns in front, sample subset."""
+    import pandas as pd
+
+    from mrvi_b200._model import MrVI
+
+    n = 24
+    sid = np.arange(n) % 6
+    obs = pd.DataFrame({"sample": sid, "site": (sid // 3), "grp": pd.Categorical(np.array(["a", "b", "c"])[sid % 3]),
+                        "age": (10.0 + 5.0 * sid)}, index=[f"c{i}" for i in range(n)])
+    m = MrVI.__new__(MrVI)
+    m.adata = mrvi_b200.SimpleAnnData(np.zeros((n, 3), np.float32), obs)
+    m.sample_key, m.sample_order, m.batch_key = "sample", np.arange(6), "site"
+    X, names, lfc, off = m._construct_design_matrix(["grp", "age"], np.ones(6, bool), True, False, False)
+    assert list(names) == ["grp_b", "grp_c", "age"] and X.shape == (6, 3) and X.dtype == np.float32 and off is None
+    assert np.allclose(X[:, 0], (sid[:6] % 3 == 1)) and np.allclose(X[:, 2], (np.arange(6) * 5.0) / (1e-6 + 25.0))
+    assert not lfc.any()
+    X, names, lfc, off = m._construct_design_matrix(["age"], np.array([1, 1, 0, 1, 1, 1], bool), False, True, True)
+    assert list(names) == ["offset_batch_0", "offset_batch_1", "age"] and list(off) == [0, 1] and list(lfc) == [False, False, True]
+    assert np.allclose(X[:, 2], [10, 15, 25, 30, 35]) and np.allclose(X[:, 0], [1, 1, 0, 0, 0])

@@ -15,11 +15,7 @@ using namespace mrvi;
 struct Res { long long issue, done; };
 
 // MODE 0: SS (A, B in shared memory); MODE 1: TS (A in TMEM).  n_mma is rounded to groups of 4 k-steps.
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
-  return pred != 0;
-}
+// (elect_one comes from tc_kernels.cuh)
 
 // UNI 1: the issuing branch is warp-uniform (warp index through a shuffle, elect.sync inside) so that descriptors
 // live in uniform registers; UNI 0: `if (lane == 0 && ...)` as the round-1 kernels do.
