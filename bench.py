@@ -341,7 +341,7 @@ class Job:
         clk_per_row = chain_ms * 1e-3 * 148 * sm_mhz * 1e6 / rows if chain_ms > 0 else None
         traffic, src = ncu_traffic(self.wl, self.n) if fused else (None, None)
         return {"bound": "tensor",
-                "kernel": "k_qz_fp32" if self.precision == "fp32" else ("k_chain_fused3_tc" if fused else "k_chain_fused3_tc (chain only; distances in k_dist_gram_tc)"),
+                "kernel": "k_qz_fp32" if self.precision == "fp32" else ("k_chain_fused_tc" if fused else "k_chain_fused_tc (chain only; distances in k_dist_gram_tc)"),
                 "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": (achieved / peak_tf) if achieved else None,
                 "traffic": traffic, "traffic_source": src,
                 "peak_source": f"MEASURED_PEAKS.json bf16 {'burst' if burst else 'sustained'} ({pk['source']})",

@@ -200,6 +200,13 @@ int mrvi_run_de_host(MrviHandle* h, int64_t n_cells, const float* X, int64_t ldx
                      float* eps_out, int64_t chunk_cells);
 
 /*
+ * Diagnostics of the tensor-core mode's attention table: number of intervals (0 = no table, the
+ * softmax is evaluated directly), the tabulated range of t = alpha_h q_i + beta_h (the whole range reachable through
+ * LayerNorm(u)), and the verified maximum interpolation error relative to max_j |kv_s[j]|.  Any pointer may be NULL.
+ */
+int mrvi_attention_table_info(MrviHandle* h, int32_t* n_intervals, float* t_min, float* t_max, float* max_rel_err);
+
+/*
  * mrvi_run_host for a dense count matrix stored as integers (raw counts in adata.X or a layer): X [n_cells, ldx]
  * elements of x_dtype, ldx >= n_input in ELEMENTS.  uint8 / uint16 matrices cross PCIe as they are (1 or 2 bytes per
  * value, no host pass); int32 / int64 matrices are narrowed chunk by chunk on the host to uint8 / uint16 (to float32

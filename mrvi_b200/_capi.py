@@ -37,6 +37,7 @@ EXPORTED_SYMBOLS = (
     "mrvi_distances_device",
     "mrvi_last_stage_ms",
     "mrvi_last_h2d_bytes",
+    "mrvi_attention_table_info",
     "mrvi_narrow_counts",
     "mrvi_comm_unique_id",
     "mrvi_comm_create",
@@ -108,6 +109,8 @@ def load_library():
     lib.mrvi_distances_device.restype = C.c_int
     lib.mrvi_distances_device.argtypes = [vp, i64, vp, i32, C.POINTER(vp), C.POINTER(i32), i32, vp,
                                           C.POINTER(vp), vp]
+    lib.mrvi_attention_table_info.restype = C.c_int
+    lib.mrvi_attention_table_info.argtypes = [vp, vp, vp, vp, vp]
     lib.mrvi_last_h2d_bytes.restype = i64
     lib.mrvi_last_h2d_bytes.argtypes = [vp]
     lib.mrvi_narrow_counts.restype = C.c_int
@@ -428,6 +431,13 @@ class Handle:
         if want_eps:
             out["eps"] = eps
         return out
+
+    def attention_table_info(self) -> dict:
+        """``mrvi_attention_table_info``: intervals (0 = direct softmax), tabulated t range, verified interpolation error."""
+        n = C.c_int32(0)
+        t0, t1, err = C.c_float(0), C.c_float(0), C.c_float(0)
+        _check(load_library().mrvi_attention_table_info(self._h, C.byref(n), C.byref(t0), C.byref(t1), C.byref(err)))
+        return {"n_intervals": int(n.value), "t_min": float(t0.value), "t_max": float(t1.value), "max_rel_err": float(err.value)}
 
     # ---- multi-GPU: the one exchange step of the path (SURVEY.md 8(e))
     def comm_create(self, unique_id: bytes, n_ranks: int, rank: int):

@@ -1316,6 +1316,16 @@ int mrvi_dbg_dist_read(long long* out, int n) {  // debug builds only (tools/dbg
 }
 #endif
 
+int mrvi_attention_table_info(MrviHandle* h, int32_t* n_intervals, float* t_min, float* t_max, float* max_rel_err) {
+  if (!h) return fail(MRVI_ERR_INVALID_ARG, "null handle");
+  const TcNet& tc = h->tc;
+  if (n_intervals) *n_intervals = tc.att_tab ? tc.att_n : 0;
+  if (t_min) *t_min = tc.att_t0;
+  if (t_max) *t_max = tc.att_tab ? tc.att_t0 + (float)tc.att_n / tc.att_scale : tc.att_t0;
+  if (max_rel_err) *max_rel_err = tc.att_err;
+  return 0;
+}
+
 int64_t mrvi_last_h2d_bytes(MrviHandle* h) { return h ? h->last_h2d_bytes : 0; }
 
 int mrvi_narrow_counts(const float* X, int64_t ldx, int64_t n_rows, int32_t n_cols, void* out, int32_t n_threads) {

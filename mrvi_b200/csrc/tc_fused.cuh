@@ -507,7 +507,45 @@ k_chain_fused_tc(const __grid_constant__ TcNet tc, CellBuf cb, int64_t n_cells, 
     const int64_t fi = cb.per_row ? (valid ? cell * S + sr : 0) : cell;
 
     // ================= attention features of head `half` -> A1 chunks 2*half, 2*half+1 =================
-    {
+    if (tc.att_tab != nullptr && !cb.per_row) {
+      // table path (tc_build): the 16 features of this thread are 16 look-ups of ITS sample's cubic-Hermite table; the rows
+      // of a cell share the cell's query tokens, so the lanes of a warp read consecutive 16-byte entries of one interval
+      const float4* tb = tc.att_tab + ss;
+      const float4* qp4 = reinterpret_cast<const float4*>(cb.q_tok + fi * 16);
+      const float t0s = -tc.att_t0 * tc.att_scale;
+      const float as = a_h * tc.att_scale, bs = fmaf(b_h, tc.att_scale, t0s);   // x = (alpha q + beta - t0) * scale
+#pragma unroll 1
+      for (int bt = 0; bt < 2; ++bt) {   // two batches of 8 features: 8 independent 16-byte loads in flight per thread
+        const float4 qa = __ldg(qp4 + 2 * bt), qb = __ldg(qp4 + 2 * bt + 1);
+        const float qv[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+        float4 nd[8];
+        float fr[8];
+#pragma unroll
+        for (int f = 0; f < 8; ++f) {
+          const float x = fminf(fmaxf(fmaf(as, qv[f], bs), 0.f), tc.att_xmax);
+          const int k = (int)x;
+          fr[f] = x - (float)k;
+          nd[f] = __ldg(tb + (size_t)k * S);
+        }
+#pragma unroll
+        for (int f2 = 0; f2 < 4; ++f2) {
+          float mm[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const float4 n4 = nd[2 * f2 + e];
+            const float u = fr[2 * f2 + e], df = n4.z - n4.x;
+            const float c3 = fmaf(-2.f, df, n4.y + n4.w), c2 = fmaf(3.f, df, fmaf(-2.f, n4.y, -n4.w));
+            mm[e] = fmaf(u, fmaf(u, fmaf(u, c3, c2), n4.y), n4.x);
+          }
+          uint32_t hw, lw;
+          split2(mm[0], mm[1], hw, lw);
+          const int it = bt * 4 + f2;
+          const int off = (half * 2 + (it >> 2)) * 2048 + (it & 3) * 4;
+          *reinterpret_cast<uint32_t*>(row_a1h + off) = hw;
+          *reinterpret_cast<uint32_t*>(row_a1l + off) = lw;
+        }
+      }
+    } else {
       float2 kv2[8];  // kv * log2(e), pairs
       const float4* kp = reinterpret_cast<const float4*>(tc.kvl + (size_t)ss * 16);
 #pragma unroll
@@ -545,6 +583,8 @@ k_chain_fused_tc(const __grid_constant__ TcNet tc, CellBuf cb, int64_t n_cells, 
         *reinterpret_cast<uint32_t*>(row_a1h + off) = hw;
         *reinterpret_cast<uint32_t*>(row_a1l + off) = lw;
       }
+    }
+    {
       if (half == 0) {  // constant-one column (k = 32) and zero padding of A1
         for (int c = 4; c < tc.K1 / 8; ++c)   // (the lo copy of A1 holds the feature chunks only: issue_gemm K_lo = 32)
           *reinterpret_cast<uint4*>(row_a1h + c * 2048) = make_uint4(c == 4 ? 0x00003C00u : 0u, 0u, 0u, 0u);

@@ -70,6 +70,12 @@ struct TcNet {
   TcOp b1, b2t, b2a, b3, b4t, b4a, b5;  // operands inside the image
   int K1 = 48, K3 = 48, K5 = 48, N5 = 32;
   float alpha[2] = {0, 0}, beta[2] = {0, 0};  // t[h,i] = alpha[h] * q_tok[i] + beta[h]
+  // Attention table (see tc_build): m_s(t) = sum_j softmax_j(t kv_s[j]) kv_s[j] is ONE smooth scalar function per sample;
+  // att_tab[k][s] = (f, h f', f_next, h f'_next) of interval k of a uniform grid over the whole reachable range of t.
+  const float4* att_tab = nullptr;  // [att_n][S], nullptr = evaluate the softmax directly (16 ex2 per feature)
+  int att_n = 0;                    // intervals
+  float att_t0 = 0.f, att_scale = 0.f, att_xmax = 0.f;  // x = (t - t0) * scale clamped to [0, xmax], xmax < att_n
+  float att_err = 0.f;              // verified max interpolation error / max_j |kv_s[j]|
   TcLn ln;
   int sm_count = 148;
   size_t smem_bytes = 0;
@@ -768,6 +774,79 @@ inline int tc_build(TcNet& tc, const NetW& net, const MrviDims& d, const tc_deta
   }
   if ((err = tc_upload(arena, kvl.data(), kvl.size() * sizeof(float), (const void**)&tc.kvl))) return err;
   if ((err = tc_upload(arena, kvref.data(), kvref.size() * sizeof(float), (const void**)&tc.kvref))) return err;
+
+  // ---- attention table.  The 16 x 16 x 2-head attention only enters the chain through the 32 softmax-weighted means
+  // m_s(t[h,i]) = sum_j softmax_j(t kv_s[j]) kv_s[j]: one smooth, monotone scalar function per SAMPLE (the derivative of
+  // log-sum-exp), evaluated at 32 points per (cell, sample) row -- 512 MUFU.EX2 per row, 27 % of the fused kernel's time.
+  // It is tabulated here in float64 as a cubic-Hermite table on a uniform grid over the WHOLE reachable range of t:
+  // q_i = LN(u).(g o Wq[:, i]) + b.Wq[:, i] with |LN(u)|_2 <= sqrt(Lq) and sum LN(u) = 0, so
+  // |q_i - b.Wq[:, i]| <= sqrt(Lq) |c_i - mean(c_i)|_2 (c_i = g o Wq[:, i]) -- no input can leave the table.  The grid is
+  // refined until the measured interpolation error (3 interior points of every interval of every sample) is below
+  // 2^-22 of max_j |kv_s[j]|, i.e. below the (hi, lo) f16 resolution the features are fed to the tensor cores with; when
+  // 4096 intervals do not reach it the table is dropped and the kernels evaluate the softmax directly.
+  // Layout [interval][sample]: the rows of a cell share the cell's 32 values of t, so a warp reads 32 consecutive
+  // 16-byte entries (coalesced, L2 resident: 16 B x intervals x S).
+  if (!getenv("MRVI_B200_NO_ATT_TABLE")) {
+    const float *g = P(pm, "qz/u_ln/scale"), *bb = P(pm, "qz/u_ln/bias"), *Wq = P(pm, ab + "/DenseGeneral_0/kernel");  // (Lq, E, 1)
+    double T0 = INFINITY, T1 = -INFINITY;
+    for (int i = 0; i < E; ++i) {
+      double mean = 0, ctr = 0, ss = 0;
+      for (int l = 0; l < Lq; ++l) { mean += (double)g[l] * Wq[(size_t)l * E + i]; ctr += (double)bb[l] * Wq[(size_t)l * E + i]; }
+      mean /= Lq;
+      for (int l = 0; l < Lq; ++l) { const double c = (double)g[l] * Wq[(size_t)l * E + i] - mean; ss += c * c; }
+      const double rad = std::sqrt((double)Lq) * std::sqrt(ss);
+      for (int h = 0; h < nh; ++h)
+        for (double q : {ctr - rad, ctr + rad}) {
+          const double t = (double)tc.alpha[h] * q + (double)tc.beta[h];
+          T0 = std::min(T0, t); T1 = std::max(T1, t);
+        }
+    }
+    const double pad = 1e-3 * (T1 - T0) + 1e-4;   // float32 rounding of q / t
+    T0 -= pad; T1 += pad;
+    auto feval = [&](int s, double t, double* deriv) {   // value (and derivative) in the kernel's units: kv * log2(e)
+      double mx = -INFINITY;
+      for (int j = 0; j < E; ++j) mx = std::max(mx, t * (double)kvl[(size_t)s * E + j]);
+      double den = 0, num = 0, num2 = 0;
+      for (int j = 0; j < E; ++j) {
+        const double k = kvl[(size_t)s * E + j], w = std::exp2(t * k - mx);
+        den += w; num += w * k; num2 += w * k * k;
+      }
+      const double m = num / den;
+      if (deriv) *deriv = ln2 * (num2 / den - m * m);
+      return m;
+    };
+    for (int N = 128; N <= 4096 && std::isfinite(T0) && T1 > T0; N *= 2) {
+      const double hstep = (T1 - T0) / N;
+      std::vector<float4> tab((size_t)N * S);
+      double worst = 0;
+      for (int s = 0; s < S && worst <= 2.4e-7; ++s) {
+        double scale_s = 0;
+        for (int j = 0; j < E; ++j) scale_s = std::max(scale_s, std::fabs((double)kvl[(size_t)s * E + j]));
+        double d0, f0 = feval(s, T0, &d0);
+        for (int k = 0; k < N; ++k) {
+          double d1;
+          const double f1 = feval(s, T0 + (k + 1) * hstep, &d1);
+          const float4 e = make_float4((float)f0, (float)(d0 * hstep), (float)f1, (float)(d1 * hstep));
+          tab[(size_t)k * S + s] = e;
+          for (double u : {0.25, 0.5, 0.75}) {   // the float32 entry, evaluated as the kernel does
+            const double df = (double)e.z - e.x, c3 = (double)e.y + e.w - 2 * df, c2 = 3 * df - 2 * (double)e.y - e.w;
+            const double val = e.x + u * (e.y + u * (c2 + u * c3));
+            worst = std::max(worst, std::fabs(val - feval(s, T0 + (k + u) * hstep, nullptr)) / std::max(scale_s, 1e-30));
+          }
+          f0 = f1; d0 = d1;
+        }
+      }
+      if (worst <= 2.4e-7) {
+        if ((err = tc_upload(arena, tab.data(), tab.size() * sizeof(float4), (const void**)&tc.att_tab))) return err;
+        tc.att_n = N;
+        tc.att_t0 = (float)T0;
+        tc.att_scale = (float)(1.0 / hstep);
+        tc.att_xmax = std::nextafter((float)N, 0.0f);
+        tc.att_err = (float)worst;
+        break;
+      }
+    }
+  }
 
   tc.sm_count = sm_count;
   tc.smem_bytes = tc_smem_map(tc.wimg_bytes, tc.K1, tc.K3).total + 1024;

@@ -1,12 +1,11 @@
 #!/bin/bash
-# A/B of library builds / fused-kernel versions: device-resident bench lines (ms per step, fused stage ms)
-# usage: gpu_ab.sh <lib|-> [FUSED version] ...   ("-" = the in-tree library)
-while [ $# -gt 0 ]; do
-  lib=$1; ver=${2:-3}; shift; shift
-  for w in "c2" "c4 --cells-per-gpu 20000" "c3 --cells-per-gpu 20000"; do
-    if [ "$lib" = "-" ]; then L=""; else L=$PWD/$lib; fi
-    MRVI_B200_FUSED=$ver MRVI_B200_LIBRARY=$L timeout 100 python bench_old.py --workload $w --steps 10 --warmup 3 --no-cpu-baseline 2>>gpurun_out/bench_err.log | python -c "
+# A/B of the device-resident bench (ms per step, fused stage, parity) under different environment switches.
+# usage (under gpurun): bash tools/gpu_ab.sh "" "MRVI_B200_NO_ATT_TABLE=1" ...     (one argument = one environment prefix)
+for envs in "$@"; do
+  for w in "c4" "c2" "c3"; do
+    env $envs timeout 200 python bench.py --workload $w --steps 10 --warmup 3 --no-cpu-baseline --no-extras --no-api 2>>gpurun_out/ab_err.log | python -c "
 import json,sys
-d=json.loads(sys.stdin.read()); print('$lib v$ver $w', round(d['ms_per_step'],3), round(d['roofline']['stage_ms_last_step']['qz_chain'],3))"
+d=json.loads(sys.stdin.read()); p=d.get('parity') or {}
+print('[$envs] $w ms/step', round(d['ms_per_step'],3), 'stages', {k: round(v,3) for k,v in d['roofline']['stage_ms_last_step'].items()}, 'clk/row', round(d['roofline']['cuda_core_bound']['sm_clk_per_row'],1), 'parity', p.get('max_norm_err'), p.get('p99_elementwise_rel'), p.get('ok'))"
   done
 done

@@ -1,5 +1,9 @@
 o=gpurun_out; mkdir -p $o
-timeout 120 ./tools/mma_microbench > $o/r2_mma_microbench.txt 2>&1; echo "microbench exit $?"
-timeout 900 python -m pytest tests/test_gpu_de.py -x -q > $o/r2b_pytest_de.log 2>&1; echo "de exit $?"; tail -15 $o/r2b_pytest_de.log
-timeout 600 python -m pytest tests/test_gpu_scale.py -x -q -k "C5 and tc" -s > $o/r2b_pytest_c5.log 2>&1; echo "c5 exit $?"; tail -5 $o/r2b_pytest_c5.log
-timeout 1200 python tools/fuzz_parity.py 220 7 > $o/r2_fuzz_parity_220.log 2>&1; echo "fuzz exit $?"; tail -4 $o/r2_fuzz_parity_220.log
+python -c "
+import mrvi_b200
+from mrvi_b200 import _capi
+for S,L in ((128,30),(32,30),(256,50)):
+    d=mrvi_b200.MrviDims(n_input=2000,n_sample=S,n_latent=L); h=_capi.Handle(d, mrvi_b200.init_params(d,seed=0), device=0, precision=_capi.PRECISION_TC); print(S, h.attention_table_info()); h.close()
+"
+bash tools/gpu_ab.sh "A=1" "MRVI_B200_NO_ATT_TABLE=1" 2>&1 | tee $o/r2c_ab_table.txt
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_golden.py -x -q -m gpu -k "tc" > $o/r2c_pytest_tc.log 2>&1; echo "tc tests exit $?"; tail -3 $o/r2c_pytest_tc.log
