@@ -163,15 +163,22 @@ int mrvi_distances_device(MrviHandle* h, int64_t n_cells, const float* z, int32_
  *   cell_out    normalize ? [n_cells, S, S] : [n_cells, mc, S, S]   float32 or NULL
  *   group_sums  normalize ? [n_groups[k], S, S] : [n_groups[k], mc, S, S]   float64, OVERWRITTEN
  *   z_out       [n_cells, mc, S, L] float32 or NULL ("sampled_representations")
+ *   u_out       [n_cells, mc, S, Lq] float32 or NULL: the draws u = mean + scale * noise themselves (row (cell, 0, own sample)
+ *               with mc = 1 is get_latent_representation(use_mean=False), _model.py:221-271)
+ *   eps_noise   use_map=0 models only (qz_kwargs={"use_map": False}): eps ~ Normal(loc, softplus(raw) + 1e-3) is then DRAWN
+ *               too (_module.py:326-329).  [S][mc][n_cells][n_latent] draws, or NULL = Philox (stream 2);
+ *               base_eps_noise [2*mc][n_cells][n_latent] for the baseline rows (stream 3).  Ignored when use_map=1.
+ *               Sampled eps is implemented in MRVI_PRECISION_FP32 only (MRVI_ERR_UNSUPPORTED in tensor-core mode).
  * JAX's threefry streams are not reproduced: with explicit draws the result is exact (oracle parity), against the
- * reference itself it is statistical.  use_map=0 models (sampled eps) return MRVI_ERR_UNSUPPORTED.
+ * reference itself it is statistical.
  */
 int mrvi_run_sampled_host(MrviHandle* h, int64_t n_cells, const float* X, int64_t ldx,
                           const int32_t* sample_idx, int32_t mc_samples, uint64_t seed, int64_t cell_offset,
-                          const float* u_noise, const float* base_noise, int32_t n_keys,
+                          const float* u_noise, const float* base_noise, const float* eps_noise,
+                          const float* base_eps_noise, int32_t n_keys,
                           const int32_t* const* group_codes, const int32_t* n_groups, int32_t norm,
                           int32_t normalize, float* cell_out, double* const* group_sums,
-                          int64_t* const* group_counts, float* z_out, int64_t chunk_cells);
+                          int64_t* const* group_counts, float* z_out, float* u_out, int64_t chunk_cells);
 
 /*
  * The latent-space stage of MrVI.differential_expression (src/mrvi/_model.py:1160-1218, 1283), host
@@ -190,12 +197,12 @@ int mrvi_run_sampled_host(MrviHandle* h, int64_t n_cells, const float* X, int64_
  *   prefactor    per_cell_design ? [n_cells][n_covariates][n_covariates] : [n_covariates][n_covariates]
  *   beta_out     [n_cells][n_covariates][n_latent] float32;  effect_size_out [n_cells][n_covariates] float32
  *   eps_out      [n_cells][mc][n_sample][n_latent] float32 or NULL (all samples, unstandardised: for the parity tests)
- *   u_noise / seed / cell_offset: as in mrvi_run_sampled_host.
+ *   u_noise / eps_noise / seed / cell_offset: as in mrvi_run_sampled_host.
  * The decoder-side outputs of the reference method (lfc, pde, baseline_expression) are outside this library.
  */
 int mrvi_run_de_host(MrviHandle* h, int64_t n_cells, const float* X, int64_t ldx, const int32_t* sample_idx,
                      int32_t mc_samples, uint64_t seed, int64_t cell_offset, const float* u_noise,
-                     int32_t n_kept_samples, const int32_t* kept_samples, int32_t n_covariates, const float* Amat,
+                     const float* eps_noise, int32_t n_kept_samples, const int32_t* kept_samples, int32_t n_covariates, const float* Amat,
                      const float* prefactor, int32_t per_cell_design, float* beta_out, float* effect_size_out,
                      float* eps_out, int64_t chunk_cells);
 

@@ -102,10 +102,10 @@ def load_library():
     lib.mrvi_run_host_counts.argtypes = [vp, i64, vp, i32, i64, vp, i32, C.POINTER(vp), C.POINTER(i32), i32, vp,
                                          C.POINTER(vp), C.POINTER(vp), vp, vp, i64]
     lib.mrvi_run_sampled_host.restype = C.c_int
-    lib.mrvi_run_sampled_host.argtypes = [vp, i64, vp, i64, vp, i32, C.c_uint64, i64, vp, vp, i32, C.POINTER(vp),
-                                          C.POINTER(i32), i32, i32, vp, C.POINTER(vp), C.POINTER(vp), vp, i64]
+    lib.mrvi_run_sampled_host.argtypes = [vp, i64, vp, i64, vp, i32, C.c_uint64, i64, vp, vp, vp, vp, i32, C.POINTER(vp),
+                                          C.POINTER(i32), i32, i32, vp, C.POINTER(vp), C.POINTER(vp), vp, vp, i64]
     lib.mrvi_run_de_host.restype = C.c_int
-    lib.mrvi_run_de_host.argtypes = [vp, i64, vp, i64, vp, i32, C.c_uint64, i64, vp, i32, vp, i32, vp, vp, i32, vp, vp, vp, i64]
+    lib.mrvi_run_de_host.argtypes = [vp, i64, vp, i64, vp, i32, C.c_uint64, i64, vp, vp, i32, vp, i32, vp, vp, i32, vp, vp, vp, i64]
     lib.mrvi_distances_device.restype = C.c_int
     lib.mrvi_distances_device.argtypes = [vp, i64, vp, i32, C.POINTER(vp), C.POINTER(i32), i32, vp,
                                           C.POINTER(vp), vp]
@@ -335,10 +335,13 @@ class Handle:
                          cell_offset: int = 0, u_noise: Optional[np.ndarray] = None,
                          base_noise: Optional[np.ndarray] = None, group_codes: Sequence[np.ndarray] = (),
                          n_groups: Sequence[int] = (), norm: str = "l2", normalize: bool = False,
-                         keep_cell: bool = True, want_z: bool = False, chunk_cells: int = 0):
+                         keep_cell: bool = True, want_z: bool = False, chunk_cells: int = 0,
+                         eps_noise: Optional[np.ndarray] = None, base_eps_noise: Optional[np.ndarray] = None,
+                         want_u: bool = False):
         """``mrvi_run_sampled_host``: distances on ``mc_samples`` draws of u per (cell, counterfactual sample).
         ``u_noise`` (S, mc, n, Lq) / ``base_noise`` (2 mc, n, Lq): explicit standard-normal draws (tests); default
-        is the device Philox generator keyed by ``seed`` and the global cell index ``cell_offset + i``."""
+        is the device Philox generator keyed by ``seed`` and the global cell index ``cell_offset + i``.
+        ``eps_noise`` (S, mc, n, L) / ``base_eps_noise`` (2 mc, n, L): draws of eps for ``use_map=False`` models."""
         if norm not in NORMS:
             raise ValueError(f"norm {norm} not supported")
         d = self.dims
@@ -364,6 +367,14 @@ class Handle:
             base_noise = np.ascontiguousarray(base_noise, dtype=np.float32)
             if base_noise.shape != (2 * mc, n, Lq):
                 raise ValueError(f"base_noise must have shape {(2 * mc, n, Lq)}")
+        if eps_noise is not None:
+            eps_noise = np.ascontiguousarray(eps_noise, dtype=np.float32)
+            if eps_noise.shape != (S, mc, n, L):
+                raise ValueError(f"eps_noise must have shape {(S, mc, n, L)}")
+        if base_eps_noise is not None:
+            base_eps_noise = np.ascontiguousarray(base_eps_noise, dtype=np.float32)
+            if base_eps_noise.shape != (2 * mc, n, L):
+                raise ValueError(f"base_eps_noise must have shape {(2 * mc, n, L)}")
         codes = [np.ascontiguousarray(c, dtype=np.int32).reshape(-1) for c in group_codes]
         out = {}
         cell_shape = (n, S, S) if normalize else (n, mc, S, S)
@@ -371,24 +382,31 @@ class Handle:
         sums = [np.zeros((g, S, S) if normalize else (g, mc, S, S), dtype=np.float64) for g in n_groups]
         counts = [np.zeros((g,), dtype=np.int64) for g in n_groups]
         z = np.empty((n, mc, S, L), dtype=np.float32) if want_z else None
+        u = np.empty((n, mc, S, Lq), dtype=np.float32) if want_u else None
         _check(load_library().mrvi_run_sampled_host(
             self._h, n, X.ctypes.data, ldx, sid.ctypes.data, mc, int(seed) & (2 ** 64 - 1), int(cell_offset),
             u_noise.ctypes.data if u_noise is not None else None,
-            base_noise.ctypes.data if base_noise is not None else None, len(codes),
+            base_noise.ctypes.data if base_noise is not None else None,
+            eps_noise.ctypes.data if eps_noise is not None else None,
+            base_eps_noise.ctypes.data if base_eps_noise is not None else None, len(codes),
             _ptr_array([c.ctypes.data for c in codes]), _i32_array(n_groups), NORMS[norm], int(bool(normalize)),
             cell.ctypes.data if keep_cell else None, _ptr_array([s.ctypes.data for s in sums]),
-            _ptr_array([c.ctypes.data for c in counts]), z.ctypes.data if want_z else None, int(chunk_cells)))
+            _ptr_array([c.ctypes.data for c in counts]), z.ctypes.data if want_z else None,
+            u.ctypes.data if want_u else None, int(chunk_cells)))
         if keep_cell:
             out["cell"] = cell
         out["group_sums"] = sums
         out["group_counts"] = counts
         if want_z:
             out["z"] = z
+        if want_u:
+            out["u"] = u
         return out
 
     def run_de_host(self, X: np.ndarray, sample_idx: np.ndarray, mc_samples: int, Amat: np.ndarray, prefactor: np.ndarray,
                     kept_samples: Optional[np.ndarray] = None, seed: int = 0, cell_offset: int = 0,
-                    u_noise: Optional[np.ndarray] = None, want_eps: bool = False, chunk_cells: int = 0):
+                    u_noise: Optional[np.ndarray] = None, want_eps: bool = False, chunk_cells: int = 0,
+                    eps_noise: Optional[np.ndarray] = None):
         """``mrvi_run_de_host``: the latent-space stage of ``differential_expression`` (reference `_model.py:1160-1218`).
         ``Amat`` (K, S_kept) or per cell (n, K, S_kept); ``prefactor`` (K, K) or (n, K, K); returns ``beta`` (n, K, L)
         and ``effect_size`` (n, K) (and the raw residuals ``eps`` (n, mc, S, L) with ``want_eps``)."""
@@ -419,12 +437,17 @@ class Handle:
             u_noise = np.ascontiguousarray(u_noise, dtype=np.float32)
             if u_noise.shape != (S, mc, n, Lq):
                 raise ValueError(f"u_noise must have shape {(S, mc, n, Lq)}")
+        if eps_noise is not None:
+            eps_noise = np.ascontiguousarray(eps_noise, dtype=np.float32)
+            if eps_noise.shape != (S, mc, n, L):
+                raise ValueError(f"eps_noise must have shape {(S, mc, n, L)}")
         beta = np.empty((n, K, L), dtype=np.float32)
         effect = np.empty((n, K), dtype=np.float32)
         eps = np.empty((n, mc, S, L), dtype=np.float32) if want_eps else None
         _check(load_library().mrvi_run_de_host(
             self._h, n, X.ctypes.data, ldx, sid.ctypes.data, mc, int(seed) & (2 ** 64 - 1), int(cell_offset),
-            u_noise.ctypes.data if u_noise is not None else None, Sk, kept.ctypes.data if kept is not None else None, K,
+            u_noise.ctypes.data if u_noise is not None else None, eps_noise.ctypes.data if eps_noise is not None else None, Sk,
+            kept.ctypes.data if kept is not None else None, K,
             Amat.ctypes.data, prefactor.ctypes.data, int(per_cell), beta.ctypes.data, effect.ctypes.data,
             eps.ctypes.data if want_eps else None, int(chunk_cells)))
         out = {"beta": beta, "effect_size": effect}

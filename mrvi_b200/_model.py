@@ -302,10 +302,14 @@ class MrVI:
         (cell, counterfactual sample) on the device (`mrvi_run_sampled_host`).  Mean-path reductions in the same
         request go through the usual call."""
         sampled = [r for r in reductions if r.input in _SAMPLED_INPUTS]
-        if any(not _is_identity_fn(r.fn) for r in sampled):
-            raise NotImplementedError("user reduction functions on sampled inputs are not part of the B200 path")
-        if any(r.input == "sampled_representations" and r.group_by is not None for r in sampled):
-            raise NotImplementedError("grouped reductions of sampled representations are not part of the B200 path")
+        if (any(not _is_identity_fn(r.fn) for r in sampled)
+                or any(r.input == "sampled_representations" and r.group_by is not None for r in sampled)):
+            # user reduction functions (or grouped representations): the reference's batch loop on the host, every batch's
+            # sampled z / distances from the GPU (draws keyed by the global cell index: independent of the batching)
+            idx = np.arange(adata.n_obs) if indices is None else np.asarray(indices).astype(int).reshape(-1)
+            Xh = dense_float32(adata.X) if indices is None else dense_float32(adata.X[idx])
+            return self._compute_generic(reductions, adata, idx, Xh, self._sample_codes(adata)[idx], batch_size, norm,
+                                         mc_samples=int(mc_samples))
         results = {}
         mean_reds = [r for r in reductions if r.input not in _SAMPLED_INPUTS]
         if mean_reds:
@@ -368,22 +372,45 @@ class MrVI:
         return DataArray(z, dims=["cell_name", "sample", "latent_dim"],
                          coords={"cell_name": cell_names, "sample": self.sample_order}, name="sample_representations")
 
-    def _compute_generic(self, reductions, adata, idx, Xh, sample_codes, batch_size, norm):
+    def _compute_generic(self, reductions, adata, idx, Xh, sample_codes, batch_size, norm, mc_samples: int = 10):
         """Reductions with a user ``fn``: the reference's batch loop (`_model.py:376-504`) on the host,
-        with each batch's z / distances computed on the GPU."""
+        with each batch's z / distances (mean and sampled inputs alike, `_model.py:386-450`) computed on the GPU."""
         bs = 128 if batch_size is None else int(batch_size)  # scvi.settings.batch_size default
         reqs = _parse_local_statistics_requirements(reductions)
         ungrouped = {r.name: [] for r in reqs.ungrouped_reductions}
         grouped = {r.name: OrderedDict() for r in reqs.grouped_reductions}
+        inputs = {r.input for r in reductions}
+        need_mean = bool(inputs & {"mean_representations", "mean_distances"})
+        need_sampled = bool(inputs & {"sampled_representations", "sampled_distances"})
+        need_norm = "normalized_distances" in inputs
+        mc = int(mc_samples)
         for lo in range(0, len(idx), bs):
             hi = min(lo + bs, len(idx))
-            res = self._handle.run_host(Xh[lo:hi], sample_codes[lo:hi], norm=norm, keep_cell=reqs.needs_mean_distances,
-                                        want_z=True)
             names = self.adata.obs_names[idx[lo:hi]].values
-            mean_zs = self._wrap_reps(res["z"], names)
-            mean_dists = self._wrap_dists(res["cell"], names) if reqs.needs_mean_distances else None
+            avail = {}
+            if need_mean:
+                res = self._handle.run_host(Xh[lo:hi], sample_codes[lo:hi], norm=norm, keep_cell=reqs.needs_mean_distances, want_z=True)
+                avail["mean_representations"] = self._wrap_reps(res["z"], names)
+                if reqs.needs_mean_distances:
+                    avail["mean_distances"] = self._wrap_dists(res["cell"], names)
+            if need_sampled:
+                res = self._handle.run_sampled_host(Xh[lo:hi], sample_codes[lo:hi], mc, seed=self.seed, cell_offset=lo, norm=norm,
+                                                    keep_cell="sampled_distances" in inputs, want_z="sampled_representations" in inputs)
+                if "sampled_representations" in inputs:
+                    avail["sampled_representations"] = DataArray(
+                        res["z"], dims=["cell_name", "mc_sample", "sample", "latent_dim"],
+                        coords={"cell_name": names, "sample": self.sample_order}, name="sample_representations")
+                if "sampled_distances" in inputs:
+                    avail["sampled_distances"] = DataArray(
+                        res["cell"], dims=["cell_name", "mc_sample", "sample_x", "sample_y"],
+                        coords={"cell_name": names, "mc_sample": np.arange(mc), "sample_x": self.sample_order,
+                                "sample_y": self.sample_order}, name="sample_distances")
+            if need_norm:
+                res = self._handle.run_sampled_host(Xh[lo:hi], sample_codes[lo:hi], mc, seed=self.seed, cell_offset=lo, norm=norm,
+                                                    normalize=True, keep_cell=True)
+                avail["normalized_distances"] = self._wrap_dists(res["cell"], names)
             for r in reductions:
-                outputs = r.fn(mean_zs if r.input == "mean_representations" else mean_dists)
+                outputs = r.fn(avail[r.input])
                 if r.group_by is not None:
                     group_by = self.adata.obs[r.group_by].to_numpy()[idx[lo:hi]]
                     for cat in pd.unique(group_by):
@@ -571,12 +598,18 @@ class MrVI:
         """Reference `_model.py:221-271`: ``u`` (n_obs, n_latent_u) or, with ``give_z``, ``z`` of every cell for
         its OWN sample (n_obs, n_latent).  A by-product of stages (1)+(2): ``u`` comes
         straight from the encoder; ``z`` is row ``sample_idx[cell]`` of the counterfactual tile."""
-        if not use_mean:
-            raise NotImplementedError("use_mean=False depends on the JAX PRNG streams of the reference (SURVEY.md 8(f)-1)")
         self._check_if_trained(warn=False)
         adata = self.adata if adata is None else adata
         idx = np.arange(adata.n_obs) if indices is None else np.asarray(indices).astype(int).reshape(-1)
         sample_codes = self._sample_codes(adata)[idx]
+        if not use_mean:
+            # one draw u ~ q(u|x) per cell and z of that draw for the cell's own sample (reference `_module.py:315-331` with
+            # mc_samples=None, cf_sample=None): row (cell, draw 0, sample = the cell's own) of the sampled path.  The draws
+            # come from the device generator (seed = self.seed), not from JAX's streams: statistical parity.
+            Xs = dense_float32(adata.X) if indices is None else dense_float32(adata.X[idx])
+            res = self._handle.run_sampled_host(Xs, sample_codes, 1, seed=self.seed, keep_cell=False, want_z=give_z, want_u=not give_z)
+            rows = np.arange(len(idx))
+            return np.ascontiguousarray((res["z"] if give_z else res["u"])[rows, 0, sample_codes])
         Xh = self._host_matrix(adata.X, idx, indices is None)
         res = self._run_sharded(Xh, sample_codes, [], [], "l2", False, give_z, want_u=not give_z)
         if give_z:

@@ -82,6 +82,8 @@ struct CellBuf {
                                //    (cell, s) row carries its own draw of u
   const int32_t* cell_sample;  // non-null: all rows of cell c use the per-sample tables of sample cell_sample[c]
                                //    (the local baseline of reference _model.py:508-540 evaluates the cell's own sample)
+  float* raw_out;              // non-null (use_map=False, sampled paths, k_qz_fp32 only): [rows][L] second half of the last
+                               //    Dense, the pre-softplus scale of q(eps) (reference _module.py:326-329)
 };
 
 // Group-reduction plan for one chunk of cells (device pointers).

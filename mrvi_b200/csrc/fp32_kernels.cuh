@@ -463,7 +463,10 @@ k_qz_fp32(const __grid_constant__ NetW net, CellBuf cb, int64_t n_cells, int row
   for (int idx = tid; idx < kTM * L; idx += kThreads) {
     const int r = idx / L, c = idx % L;
     const int64_t row = row0 + r;
-    if (row < n_rows) z_out[row * L + c] = cb.zbase[(cb.per_row ? row : row / S) * L + c] + hid[(size_t)r * ldhid + c];
+    if (row < n_rows) {
+      z_out[row * L + c] = cb.zbase[(cb.per_row ? row : row / S) * L + c] + hid[(size_t)r * ldhid + c];
+      if (cb.raw_out != nullptr && net.out_dim == 2 * L) cb.raw_out[row * L + c] = hid[(size_t)r * ldhid + L + c];
+    }
   }
 }
 

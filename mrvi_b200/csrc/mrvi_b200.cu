@@ -564,8 +564,25 @@ static int run_device_impl(MrviHandle* h, int64_t n, const float* X, int64_t ldx
 // ------------------------------------------------------------------------------------------
 // sampled paths: see sampled_kernels.cuh
 // q(z|u,s) chain (+ distances / group sums) over n (virtual) cells whose rows carry their own features
+struct EpsNoise {   // use_map=False on the sampled paths: eps is drawn, not its mean (reference _module.py:326-329)
+  const float* noise = nullptr;   // explicit draws [(b * A + a)][noise_n][L] on the device, or null = Philox
+  int64_t noise_cell0 = 0, noise_n = 0, gcell0 = 0, n_cells = 0;
+  int A = 0, B = 0;
+  uint64_t seed = 0;
+  uint32_t stream = 2;
+};
+
+static int add_eps_noise(MrviHandle* h, const CellBuf& cb, float* z, const EpsNoise& en, cudaStream_t st) {
+  const int64_t rows = en.n_cells * en.A * en.B;
+  if (rows == 0) return 0;
+  k_eps_noise<<<(unsigned)((rows + 127) / 128), 128, 0, st>>>(z, cb.raw_out, en.n_cells, en.A, en.B, h->net.L, en.noise, en.noise_cell0,
+                                                             en.noise_n, en.gcell0, en.seed, en.stream);
+  LAUNCH_CHECK();
+  return 0;
+}
+
 static int chain_and_dist(MrviHandle* h, const CellBuf& cb, int64_t n, int norm, float* z_out, float* z_scratch,
-                          float* cell_out, const GroupPlan& gp, cudaStream_t st) {
+                          float* cell_out, const GroupPlan& gp, cudaStream_t st, const EpsNoise* en = nullptr) {
   const NetW& net = h->net;
   const bool need_dist = cell_out != nullptr || gp.n_keys > 0;
   int err;
@@ -582,22 +599,28 @@ static int chain_and_dist(MrviHandle* h, const CellBuf& cb, int64_t n, int norm,
     else if (h->tc.fused_smem_bytes) tc_launch_fused_chain(h->tc, net, n, cb, z, st);
     else if ((err = tc_launch_qz(h->tc, net, n, cb, z, st))) return err;
     LAUNCH_CHECK();
-  } else if ((err = launch_qz(h, cb, n, net.S, z, st))) return err;
+  } else {
+    if ((err = launch_qz(h, cb, n, net.S, z, st))) return err;
+    if (en && (err = add_eps_noise(h, cb, z, *en, st))) return err;
+  }
   if (need_dist && (err = launch_dist(h, z, n, norm, cell_out, gp, st))) return err;
   return 0;
 }
 
 static int run_sampled_host_impl(MrviHandle* h, int64_t n_cells, const float* X, int64_t ldx, const int32_t* sample_idx,
                                  int mc, uint64_t seed, int64_t cell_offset, const float* u_noise, const float* base_noise,
+                                 const float* eps_noise, const float* base_eps_noise,
                                  int n_keys, const int32_t* const* group_codes, const int32_t* n_groups, int norm,
                                  int normalize, float* cell_out, double* const* group_sums, int64_t* const* group_counts,
-                                 float* z_out, int64_t chunk_cells) {
+                                 float* z_out, float* u_out, int64_t chunk_cells) {
   int err;
   if ((err = validate_run(h, n_cells, X, ldx, sample_idx, n_keys, group_codes, n_groups, norm, group_sums))) return err;
   if (mc <= 0 || mc > 4096) return fail(MRVI_ERR_INVALID_ARG, "mc_samples must be in [1, 4096]");
   if ((err = validate_sample_idx(h, sample_idx, n_cells))) return err;
   if (normalize && norm != MRVI_NORM_L2) return fail(MRVI_ERR_INVALID_ARG, "Norm must be 'l2' when using normalized distances");
-  if (!h->dims.use_map) return fail(MRVI_ERR_UNSUPPORTED, "sampled paths with use_map=False (sampled eps) are not implemented");
+  const bool sample_eps = !h->dims.use_map;   // eps ~ Normal(loc, softplus(raw) + 1e-3) is drawn as well (reference _module.py:326-329)
+  if (sample_eps && h->precision != MRVI_PRECISION_FP32)
+    return fail(MRVI_ERR_UNSUPPORTED, "sampled paths with use_map=False (sampled eps) need MRVI_PRECISION_FP32");
   if (h->net.enc_scale.w == nullptr)
     return fail(MRVI_ERR_PARAM, "missing parameter 'qu/NormalDistOutputNN_0/Dense_1/kernel' (scale head of q(u|x), needed by the sampled paths)");
   if (h->net.Lq > kMaxLq) return fail(MRVI_ERR_UNSUPPORTED, "n_latent_u > %d", kMaxLq);
@@ -629,6 +652,7 @@ static int run_sampled_host_impl(MrviHandle* h, int64_t n_cells, const float* X,
   DeviceArena ws;  // everything of this call; released on return
   cudaStream_t st = nullptr;
   float *dX, *d_scale, *d_mu, *d_var, *d_zb, *d_z, *d_dv = nullptr, *d_cell = nullptr, *d_unoise = nullptr, *d_bnoise = nullptr;
+  float *d_enoise = nullptr, *d_benoise = nullptr, *d_udraw = nullptr;
   int32_t *d_sid, *d_codes[kMaxKeys] = {}, *d_vcodes[kMaxKeys] = {};
   double* d_sums[kMaxKeys] = {};
   CellBuf rcb{}, bcb{};
@@ -640,6 +664,19 @@ static int run_sampled_host_impl(MrviHandle* h, int64_t n_cells, const float* X,
   CUDA_TRY(ws.alloc((void**)&rcb.zbase, nvmax * S * L * sizeof(float)));
   rcb.per_row = 1;
   CUDA_TRY(ws.alloc((void**)&d_z, nvmax * S * L * sizeof(float)));
+  if (u_out) CUDA_TRY(ws.alloc((void**)&d_udraw, nvmax * S * Lq * sizeof(float)));
+  if (sample_eps) {
+    CUDA_TRY(ws.alloc((void**)&rcb.raw_out, nvmax * S * L * sizeof(float)));
+    if (normalize) CUDA_TRY(ws.alloc((void**)&bcb.raw_out, ch * 2 * mc * L * sizeof(float)));
+    if (eps_noise) {
+      CUDA_TRY(ws.alloc((void**)&d_enoise, (size_t)S * mc * n_cells * L * sizeof(float)));
+      CUDA_TRY(cudaMemcpyAsync(d_enoise, eps_noise, (size_t)S * mc * n_cells * L * sizeof(float), cudaMemcpyHostToDevice, st));
+    }
+    if (normalize && base_eps_noise) {
+      CUDA_TRY(ws.alloc((void**)&d_benoise, (size_t)2 * mc * n_cells * L * sizeof(float)));
+      CUDA_TRY(cudaMemcpyAsync(d_benoise, base_eps_noise, (size_t)2 * mc * n_cells * L * sizeof(float), cudaMemcpyHostToDevice, st));
+    }
+  }
   if (normalize) {
     CUDA_TRY(ws.alloc((void**)&bcb.u_ln, ch * 2 * mc * Lq * sizeof(float)));
     CUDA_TRY(ws.alloc((void**)&bcb.q_tok, ch * 2 * mc * E * sizeof(float)));
@@ -699,10 +736,16 @@ static int run_sampled_host_impl(MrviHandle* h, int64_t n_cells, const float* X,
     {
       const int64_t rows = nv * S;
       k_sample_rows<<<(unsigned)((rows + 127) / 128), 128, 0, st>>>(h->net, ecb.u, d_scale, m, mc, S, d_unoise, lo, n_cells,
-                                                                   cell_offset + lo, seed, 0u, rcb.u_ln, rcb.q_tok, rcb.zbase);
+                                                                   cell_offset + lo, seed, 0u, rcb.u_ln, rcb.q_tok, rcb.zbase, d_udraw);
       LAUNCH_CHECK();
+      if (u_out) CUDA_TRY(cudaMemcpyAsync(u_out + lo * mc * S * Lq, d_udraw, rows * Lq * sizeof(float), cudaMemcpyDeviceToHost, st));
     }
     float* dz_out = z_out ? d_z : nullptr;
+    EpsNoise en, ben;
+    en.noise = d_enoise; en.noise_cell0 = lo; en.noise_n = n_cells; en.gcell0 = cell_offset + lo; en.n_cells = m;
+    en.A = mc; en.B = S; en.seed = seed; en.stream = 2u;
+    ben = en; ben.noise = d_benoise; ben.A = 2 * mc; ben.B = 1; ben.stream = 3u;
+    const EpsNoise* enp = sample_eps ? &en : nullptr;
     if (!normalize) {
       GroupPlan gp;
       const int32_t* vptr[kMaxKeys];
@@ -712,7 +755,7 @@ static int run_sampled_host_impl(MrviHandle* h, int64_t n_cells, const float* X,
         vptr[k] = d_vcodes[k];
       }
       if ((err = plan_groups(h, nv, n_keys, vptr, 0, ng_eff, d_sums, &gp, st))) return err;
-      if ((err = chain_and_dist(h, rcb, nv, norm, dz_out, d_z, d_cell, gp, st))) return err;
+      if ((err = chain_and_dist(h, rcb, nv, norm, dz_out, d_z, d_cell, gp, st, enp))) return err;
       if (cell_out)
         CUDA_TRY(cudaMemcpyAsync(cell_out + lo * mc * SS, d_cell, nv * SS * sizeof(float), cudaMemcpyDeviceToHost, st));
     } else {
@@ -724,12 +767,15 @@ static int run_sampled_host_impl(MrviHandle* h, int64_t n_cells, const float* X,
       if (h->precision == MRVI_PRECISION_TC) {
         if ((err = tc_launch_qz(h->tc, net, m, bcb, d_zb, st, 2 * mc))) return err;
         LAUNCH_CHECK();
-      } else if ((err = launch_qz(h, bcb, m, 2 * mc, d_zb, st))) return err;
+      } else {
+        if ((err = launch_qz(h, bcb, m, 2 * mc, d_zb, st))) return err;
+        if (sample_eps && (err = add_eps_noise(h, bcb, d_zb, ben, st))) return err;
+      }
       k_baseline_stats<<<(unsigned)((m + 7) / 8), 256, 0, st>>>(d_zb, m, mc, L, d_mu, d_var);
       LAUNCH_CHECK();
       GroupPlan none;
       memset(&none, 0, sizeof(none));
-      if ((err = chain_and_dist(h, rcb, nv, norm, dz_out, d_z, d_dv, none, st))) return err;
+      if ((err = chain_and_dist(h, rcb, nv, norm, dz_out, d_z, d_dv, none, st, enp))) return err;
       GroupPlan gp;
       const int32_t* cptr[kMaxKeys];
       for (int k = 0; k < n_keys; ++k) cptr[k] = d_codes[k];
@@ -757,8 +803,8 @@ static int run_sampled_host_impl(MrviHandle* h, int64_t n_cells, const float* X,
 // kept counterfactual sample -> the chain's residual eps (z_base zeroed: the chain then returns eps itself, no
 // cancellation against z_base) -> per-cell standardisation over the samples, betas = Amat . eps, whitened effect sizes.
 static int run_de_host_impl(MrviHandle* h, int64_t n_cells, const float* X, int64_t ldx, const int32_t* sample_idx, int mc,
-                            uint64_t seed, int64_t cell_offset, const float* u_noise, int n_kept, const int32_t* kept,
-                            int n_cov, const float* Amat, const float* prefactor, int per_cell_design, float* beta_out,
+                            uint64_t seed, int64_t cell_offset, const float* u_noise, const float* eps_noise, int n_kept,
+                            const int32_t* kept, int n_cov, const float* Amat, const float* prefactor, int per_cell_design, float* beta_out,
                             float* effect_out, float* eps_out, int64_t chunk_cells) {
   if (!h) return fail(MRVI_ERR_INVALID_ARG, "null handle");
   if (n_cells < 0 || (n_cells > 0 && (!X || !sample_idx))) return fail(MRVI_ERR_INVALID_ARG, "X / sample_idx is null");
@@ -774,7 +820,9 @@ static int run_de_host_impl(MrviHandle* h, int64_t n_cells, const float* X, int6
     if (kept[j] < 0 || kept[j] >= S) return fail(MRVI_ERR_INVALID_ARG, "kept_samples[%d] = %d outside [0, %d)", j, kept[j], S);
   int err;
   if ((err = validate_sample_idx(h, sample_idx, n_cells))) return err;
-  if (!h->dims.use_map) return fail(MRVI_ERR_UNSUPPORTED, "differential expression with use_map=False (sampled eps) is not implemented");
+  const bool sample_eps = !h->dims.use_map;
+  if (sample_eps && h->precision != MRVI_PRECISION_FP32)
+    return fail(MRVI_ERR_UNSUPPORTED, "differential expression with use_map=False (sampled eps) needs MRVI_PRECISION_FP32");
   if (net.enc_scale.w == nullptr)
     return fail(MRVI_ERR_PARAM, "missing parameter 'qu/NormalDistOutputNN_0/Dense_1/kernel' (scale head of q(u|x), needed by the sampled paths)");
   if (Lq > kMaxLq) return fail(MRVI_ERR_UNSUPPORTED, "n_latent_u > %d", kMaxLq);
@@ -792,7 +840,7 @@ static int run_de_host_impl(MrviHandle* h, int64_t n_cells, const float* X, int6
 
   DeviceArena ws;
   cudaStream_t st = nullptr;
-  float *dX, *d_scale, *d_eps, *d_A, *d_P, *d_beta, *d_eff, *d_unoise = nullptr;
+  float *dX, *d_scale, *d_eps, *d_A, *d_P, *d_beta, *d_eff, *d_unoise = nullptr, *d_enoise = nullptr;
   int32_t *d_sid, *d_kept = nullptr;
   CellBuf rcb{};
   const int64_t design_cells = per_cell_design ? ch : 1;
@@ -815,6 +863,13 @@ static int run_de_host_impl(MrviHandle* h, int64_t n_cells, const float* X, int6
   if (u_noise) {
     CUDA_TRY(ws.alloc((void**)&d_unoise, (size_t)S * mc * n_cells * Lq * sizeof(float)));
     CUDA_TRY(cudaMemcpyAsync(d_unoise, u_noise, (size_t)S * mc * n_cells * Lq * sizeof(float), cudaMemcpyHostToDevice, st));
+  }
+  if (sample_eps) {
+    CUDA_TRY(ws.alloc((void**)&rcb.raw_out, nvmax * S * L * sizeof(float)));
+    if (eps_noise) {
+      CUDA_TRY(ws.alloc((void**)&d_enoise, (size_t)S * mc * n_cells * L * sizeof(float)));
+      CUDA_TRY(cudaMemcpyAsync(d_enoise, eps_noise, (size_t)S * mc * n_cells * L * sizeof(float), cudaMemcpyHostToDevice, st));
+    }
   }
   if (!per_cell_design) {
     CUDA_TRY(cudaMemcpyAsync(d_A, Amat, (size_t)n_cov * Sk * sizeof(float), cudaMemcpyHostToDevice, st));
@@ -853,7 +908,10 @@ static int run_de_host_impl(MrviHandle* h, int64_t n_cells, const float* X, int6
     }
     GroupPlan none;
     memset(&none, 0, sizeof(none));
-    if ((err = chain_and_dist(h, rcb, nv, MRVI_NORM_L2, d_eps, d_eps, nullptr, none, st))) return err;
+    EpsNoise en;
+    en.noise = d_enoise; en.noise_cell0 = lo; en.noise_n = n_cells; en.gcell0 = cell_offset + lo; en.n_cells = m;
+    en.A = mc; en.B = S; en.seed = seed; en.stream = 2u;
+    if ((err = chain_and_dist(h, rcb, nv, MRVI_NORM_L2, d_eps, d_eps, nullptr, none, st, sample_eps ? &en : nullptr))) return err;
     k_de_stats<<<(unsigned)m, kDeWarps * 32, de_smem, st>>>(d_eps, m, mc, S, L, d_kept, Sk, n_cov, d_A, d_P, per_cell_design ? 1 : 0,
                                                             d_beta, d_eff);
     LAUNCH_CHECK();
@@ -1289,18 +1347,20 @@ int mrvi_run_host_csr(MrviHandle* h, int64_t n_cells, const int64_t* indptr, con
 
 int mrvi_run_sampled_host(MrviHandle* h, int64_t n_cells, const float* X, int64_t ldx, const int32_t* sample_idx,
                           int32_t mc_samples, uint64_t seed, int64_t cell_offset, const float* u_noise, const float* base_noise,
+                          const float* eps_noise, const float* base_eps_noise,
                           int32_t n_keys, const int32_t* const* group_codes, const int32_t* n_groups, int32_t norm,
                           int32_t normalize, float* cell_out, double* const* group_sums, int64_t* const* group_counts,
-                          float* z_out, int64_t chunk_cells) {
-  return run_sampled_host_impl(h, n_cells, X, ldx, sample_idx, mc_samples, seed, cell_offset, u_noise, base_noise, n_keys,
-                               group_codes, n_groups, norm, normalize, cell_out, group_sums, group_counts, z_out, chunk_cells);
+                          float* z_out, float* u_out, int64_t chunk_cells) {
+  return run_sampled_host_impl(h, n_cells, X, ldx, sample_idx, mc_samples, seed, cell_offset, u_noise, base_noise, eps_noise,
+                               base_eps_noise, n_keys,
+                               group_codes, n_groups, norm, normalize, cell_out, group_sums, group_counts, z_out, u_out, chunk_cells);
 }
 
 int mrvi_run_de_host(MrviHandle* h, int64_t n_cells, const float* X, int64_t ldx, const int32_t* sample_idx, int32_t mc_samples,
-                     uint64_t seed, int64_t cell_offset, const float* u_noise, int32_t n_kept_samples, const int32_t* kept_samples,
-                     int32_t n_covariates, const float* Amat, const float* prefactor, int32_t per_cell_design, float* beta_out,
+                     uint64_t seed, int64_t cell_offset, const float* u_noise, const float* eps_noise, int32_t n_kept_samples,
+                     const int32_t* kept_samples, int32_t n_covariates, const float* Amat, const float* prefactor, int32_t per_cell_design, float* beta_out,
                      float* effect_size_out, float* eps_out, int64_t chunk_cells) {
-  return run_de_host_impl(h, n_cells, X, ldx, sample_idx, mc_samples, seed, cell_offset, u_noise, n_kept_samples, kept_samples,
+  return run_de_host_impl(h, n_cells, X, ldx, sample_idx, mc_samples, seed, cell_offset, u_noise, eps_noise, n_kept_samples, kept_samples,
                           n_covariates, Amat, prefactor, per_cell_design, beta_out, effect_size_out, eps_out, chunk_cells);
 }
 

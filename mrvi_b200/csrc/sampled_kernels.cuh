@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(128)
 k_sample_rows(const __grid_constant__ NetW net, const float* __restrict__ mean, const float* __restrict__ scale,
               int64_t n_cells, int A, int B, const float* __restrict__ noise, int64_t noise_cell0, int64_t noise_n,
               int64_t gcell0, uint64_t seed, uint32_t stream, float* __restrict__ u_ln_out, float* __restrict__ q_tok_out,
-              float* __restrict__ zbase_out) {
+              float* __restrict__ zbase_out, float* __restrict__ u_draw_out = nullptr) {
   const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= n_cells * A * B) return;
   const int b = (int)(row % B);
@@ -80,6 +80,7 @@ k_sample_rows(const __grid_constant__ NetW net, const float* __restrict__ mean, 
       if (l0 + j < Lq) {
         const float v = fmaf(__ldg(scale + cell * Lq + l0 + j), e[j], __ldg(mean + cell * Lq + l0 + j));
         u[l0 + j] = v;
+        if (u_draw_out != nullptr) u_draw_out[row * Lq + l0 + j] = v;
         s1 += v;
         s2 = fmaf(v, v, s2);
       }
@@ -110,6 +111,40 @@ k_sample_rows(const __grid_constant__ NetW net, const float* __restrict__ mean, 
     float acc = 0.f;
     for (int l = 0; l < Lq; ++l) acc = fmaf(u[l], __ldg(net.q_tok.w + (size_t)l * net.q_tok.ld + e), acc);
     qt[e] = acc;
+  }
+}
+
+// use_map=False (reference _module.py:326-329): eps ~ Normal(loc, softplus(raw) + 1e-3) instead of its mean.  z holds
+// z_base + loc, raw the pre-softplus scale (CellBuf::raw_out); adds (softplus(raw) + 1e-3) * noise in place.  Row layout
+// and noise indexing as k_sample_rows (explicit noise[(b * A + a)][cell][L], or Philox stream `stream`).
+__global__ void __launch_bounds__(128)
+k_eps_noise(float* __restrict__ z, const float* __restrict__ raw, int64_t n_cells, int A, int B, int L,
+            const float* __restrict__ noise, int64_t noise_cell0, int64_t noise_n, int64_t gcell0, uint64_t seed, uint32_t stream) {
+  const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= n_cells * A * B) return;
+  const int b = (int)(row % B);
+  const int a = (int)((row / B) % A);
+  const int64_t cell = row / ((int64_t)A * B);
+  const int64_t gcell = gcell0 + cell;
+  for (int l0 = 0; l0 < L; l0 += 4) {
+    float e[4];
+    if (noise != nullptr) {
+      const float* np_ = noise + (((int64_t)b * A + a) * noise_n + noise_cell0 + cell) * L + l0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) e[j] = (l0 + j < L) ? __ldg(np_ + j) : 0.f;
+    } else {
+      const float4 g = philox_normal4((uint32_t)gcell, (uint32_t)a, (uint32_t)b,
+                                      (uint32_t)(l0 >> 2) | (stream << 16) | ((uint32_t)(gcell >> 32) << 20), seed);
+      e[0] = g.x; e[1] = g.y; e[2] = g.z; e[3] = g.w;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (l0 + j < L) {
+        const float v = raw[row * L + l0 + j];
+        const float sp = (v > 20.f ? v : log1pf(expf(v))) + 1e-3f;
+        z[row * L + l0 + j] = fmaf(sp, e[j], z[row * L + l0 + j]);
+      }
+    }
   }
 }
 

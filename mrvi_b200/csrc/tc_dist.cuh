@@ -36,10 +36,12 @@ __device__ long long g_dbg_dist[64 * 32];
 constexpr int kDistTcThreads = 576;   // 16 epilogue warps (2 warpgroups) + 2 issuer warps (one per warpgroup: MMAs; the first also the bulk copies)
 constexpr int kDistTcWorkers = 512;
 
-// Gram entries with d^2 < 2^-9 (n_i + n_j) are recomputed by direct differences.  G[i][j] and G[j][i] are the same products
-// accumulated in a different order (a few ulp of G apart): at L = 50 the fused kernel's 2^-12 left |d_ij - d_ji| up to
-// 2.5e-4 d on a handful of the 1.3e9 entries of a 20k-cell chunk; 2^-9 bounds it below 5e-5 d.
-constexpr int kDistThrLog2 = 9;
+// Gram entries with d^2 < 2^-12 (n_i + n_j) are recomputed by direct differences (the same threshold as the fused kernel).
+// G[i][j] and G[j][i] are the same products accumulated in a different order, a few ulp of G apart: just above the threshold
+// that is |d_ij - d_ji| up to ~2.5e-4 d on a handful of the 10^9 entries of a chunk (tests/test_gpu_scale.py bounds it by
+// 5e-4, half the mode's accuracy bar; MRVI_PRECISION_FP32 is exactly symmetric).  A 2^-9 threshold removes it but was
+// measured at +30 % on the fused kernel (C4 7.8 -> 10.3 ms: the exact path is warp-serial), so it is not used.
+constexpr int kDistThrLog2 = 12;
 constexpr float kDistThr = 1.0f / (float)(1 << kDistThrLog2);
 constexpr uint32_t kDistLbo = 4096 + 16;  // bytes between K chunks: 256 rows x 16 B + one row of padding, which makes the
                                           // prep's 16-byte stores (8 chunks x 4 rows per warp) bank-conflict free

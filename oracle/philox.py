@@ -54,3 +54,15 @@ def base_noise(n_cells: int, mc: int, n_lq: int, seed: int, cell_offset: int = 0
     """(2 mc, n, Lq): the draws of the local baseline (stream 1; b = 0)."""
     a, c = np.meshgrid(np.arange(2 * mc), np.arange(n_cells) + cell_offset, indexing="ij")
     return normal_draws(c, a, np.zeros_like(a), n_lq, seed, 1)
+
+
+def eps_noise(n_cells: int, n_sample: int, mc: int, n_latent: int, seed: int, cell_offset: int = 0):
+    """(S, mc, n, L): the draws of eps for ``use_map=False`` models on the counterfactual rows (stream 2)."""
+    s, m, c = np.meshgrid(np.arange(n_sample), np.arange(mc), np.arange(n_cells) + cell_offset, indexing="ij")
+    return normal_draws(c, m, s, n_latent, seed, 2)
+
+
+def base_eps_noise(n_cells: int, mc: int, n_latent: int, seed: int, cell_offset: int = 0):
+    """(2 mc, n, L): the draws of eps on the baseline rows (stream 3; b = 0)."""
+    a, c = np.meshgrid(np.arange(2 * mc), np.arange(n_cells) + cell_offset, indexing="ij")
+    return normal_draws(c, a, np.zeros_like(a), n_latent, seed, 3)

@@ -131,7 +131,7 @@ def test_de_errors(built_library):
         h.run_de_host(X, sid, 0, A, P)
     h.close()
     dims = mrvi_b200.MrviDims(n_input=30, n_sample=5, use_map=False)
-    h = _capi.Handle(dims, mrvi_b200.init_params(dims, seed=0), device=0)
+    h = _capi.Handle(dims, mrvi_b200.init_params(dims, seed=0), device=0, precision=_capi.PRECISION_TC)
     with pytest.raises(_capi.MrviError, match="use_map=False"):
         h.run_de_host(X, sid, 2, A, P)
     h.close()

@@ -134,14 +134,49 @@ def test_cuda_sampled_matches_reference_source_goldens(built_library, path, prec
     h.close()
 
 
-def test_sampled_path_errors(built_library):
-    dims = mrvi_b200.MrviDims(n_input=30, n_sample=5, use_map=False)
-    flat = mrvi_b200.init_params(dims, seed=0)
-    h = _capi.Handle(dims, flat, device=0)
-    X = mrvi_b200.synthetic_counts(8, 30, seed=0)
-    with pytest.raises(_capi.MrviError, match="use_map=False"):
-        h.run_sampled_host(X, np.zeros(8, np.int32), 2)
+def test_sampled_eps_use_map_false(built_library):
+    """qz_kwargs={"use_map": False} on the sampled paths (reference `_module.py:326-329`): eps ~ Normal(loc, softplus(raw) +
+    1e-3) is drawn too.  fp32 mode, explicit draws vs the oracle; device Philox draws vs the numpy mirror; DE eps stage."""
+    dk = dict(n_input=40, n_sample=6, use_map=False)
+    n, mc = 30, 3
+    dims, flat, X, sid, nu, nb, h = _setup(dk, n, mc, 51, "fp32")
+    rng = np.random.default_rng(8)
+    L = dims.n_latent
+    ne = rng.standard_normal((dims.n_sample, mc, n, L)).astype(np.float32)
+    nbe = rng.standard_normal((2 * mc, n, L)).astype(np.float32)
+    res = h.run_sampled_host(X, sid, mc, u_noise=nu, eps_noise=ne, keep_cell=True, want_z=True)
+    zref = orc.sampled_counterfactual_z(flat, X, sid, nu, noise_eps=ne)
+    assert _rel(res["z"], zref) < 1e-5 and _rel(res["cell"], orc.pairwise_distances_mc(zref)) < 1e-5
+    # the noise term matters (the same call without it differs)
+    assert _rel(res["z"], orc.sampled_counterfactual_z(flat, X, sid, nu, noise_eps=np.zeros_like(ne))) > 1e-3
+    resn = h.run_sampled_host(X, sid, mc, u_noise=nu, base_noise=nb, eps_noise=ne, base_eps_noise=nbe, normalize=True, keep_cell=True)
+    mu, var = orc.local_baseline_dists(flat, X, sid, nb, noise_eps=nbe)
+    dref = orc.pairwise_distances_mc(zref)
+    nref = ((dref - mu[:, None, None, None]) / np.sqrt(var)[:, None, None, None]).mean(axis=1)
+    assert _rel(resn["cell"], nref) < 1e-5 * (1.0 + (mu / np.sqrt(var)).max())
+    # device generator == numpy mirror (streams 2 / 3), chunk invariant
+    a = h.run_sampled_host(X, sid, mc, seed=77, cell_offset=5, normalize=True, keep_cell=True)
+    b = h.run_sampled_host(X, sid, mc, seed=77, cell_offset=5, normalize=True, keep_cell=True, chunk_cells=4)
+    assert np.array_equal(a["cell"], b["cell"])
+    c = h.run_sampled_host(X, sid, mc, normalize=True, keep_cell=True,
+                           u_noise=philox.u_noise(n, 6, mc, dims.n_latent_q, 77, 5), base_noise=philox.base_noise(n, mc, dims.n_latent_q, 77, 5),
+                           eps_noise=philox.eps_noise(n, 6, mc, L, 77, 5), base_eps_noise=philox.base_eps_noise(n, mc, L, 77, 5))
+    assert np.abs(a["cell"] - c["cell"]).max() < 2e-4 * np.abs(c["cell"]).max()
+    # DE eps stage with sampled eps
+    A, P = orc.de_process_design_matrix(rng.random((6, 2)), np.ones((n, 6), dtype=bool))
+    de = h.run_de_host(X, sid, mc, A[0], P[0], u_noise=nu, eps_noise=ne, want_eps=True)
+    eref = orc.sampled_counterfactual_eps(flat, X, sid, nu, noise_eps=ne)
+    assert _rel(de["eps"].transpose(1, 0, 2, 3), eref) < 1e-5
     h.close()
+    # tensor-core mode refuses loudly
+    ht = _capi.Handle(dims, flat, device=0, precision=_capi.PRECISION_TC)
+    with pytest.raises(_capi.MrviError, match="MRVI_PRECISION_FP32"):
+        ht.run_sampled_host(X, sid, mc)
+    ht.close()
+
+
+def test_sampled_path_errors(built_library):
+    X = mrvi_b200.synthetic_counts(8, 30, seed=0)
     dims = mrvi_b200.MrviDims(n_input=30, n_sample=5)
     flat = mrvi_b200.init_params(dims, seed=0)
     h = _capi.Handle(dims, {k: v for k, v in flat.items() if "NormalDistOutputNN_0/Dense_1" not in k}, device=0)
@@ -185,4 +220,45 @@ def test_model_api_sampled_and_normalized(built_library):
         model.get_local_sample_distances(normalize_distances=True, norm="l1")
     zr = model.get_local_sample_representation(use_mean=False)
     assert zr.dims == ("cell_name", "mc_sample", "sample", "latent_dim") and zr.shape == (90, 10, 5, dims.n_latent)
+    model.close()
+
+
+def test_model_api_sampled_user_fn_and_latent_draws(built_library):
+    """Closes the sampled-path holes of the host API: user reduction functions on the sampled inputs (the reference's batch
+    loop, `_model.py:386-504`), grouped sampled representations, and `get_latent_representation(use_mean=False)`
+    (`_model.py:221-271`).  Values against the oracle on the draws the device generator makes."""
+    from mrvi_b200 import MrVIReduction
+
+    ad = mrvi_b200.synthetic_iid(n_obs=50, n_vars=40, n_sample=4, seed=5)
+    dims = mrvi_b200.MrviDims(n_input=40, n_sample=4)
+    params = mrvi_b200.init_params(dims, seed=6)
+    params["qu/NormalDistOutputNN_0/Dense_1/bias"] = params["qu/NormalDistOutputNN_0/Dense_1/bias"] - 2.0
+    model = mrvi_b200.MrVI(ad, params, sample_key="sample_str", seed=123)
+    sid = model._sample_codes(ad)
+    mc = 3
+    nu = philox.u_noise(50, 4, mc, dims.n_latent_q, 123)
+    zref = orc.sampled_counterfactual_z(params, ad.X, sid, nu)          # (n, mc, S, L)
+    dref = orc.pairwise_distances_mc(zref)
+    reds = [
+        MrVIReduction(name="dmax", input="sampled_distances", fn=lambda x: x.mean("mc_sample"), group_by=None),
+        MrVIReduction(name="zgrp", input="sampled_representations", fn=lambda x: x.mean("mc_sample"), group_by="labels"),
+    ]
+    out = model.compute_local_statistics(reds, batch_size=16, mc_samples=mc)   # ragged batches: 16, 16, 16, 2
+    assert out["dmax"].dims == ("cell_name", "sample_x", "sample_y") and out["dmax"].shape == (50, 4, 4)
+    assert _rel(np.asarray(out["dmax"].values), dref.mean(axis=1)) < 3e-4
+    vc = ad.obs["labels"].value_counts()
+    lab = ad.obs["labels"].to_numpy()
+    gref = np.stack([zref[lab == c].mean(axis=1).mean(axis=0) for c in vc.index])
+    assert out["zgrp"].dims[0] == "labels_name" and list(np.asarray(out["zgrp"].coords["labels_name"])) == list(vc.index)
+    assert _rel(np.asarray(out["zgrp"].values), gref) < 3e-4
+    # one draw of u per cell / z of that draw for the cell's own sample
+    nu1 = philox.u_noise(50, 4, 1, dims.n_latent_q, 123)
+    p64 = orc.cast_params(params, np.float64)
+    mean, scale = orc.encoder_xu(p64, np.asarray(ad.X, np.float64), sid)
+    u_ref = mean + scale * nu1[sid, 0, np.arange(50)]
+    u = model.get_latent_representation(use_mean=False)
+    assert u.shape == (50, dims.n_latent_q) and _rel(u, u_ref) < 3e-4
+    z1 = orc.sampled_counterfactual_z(params, ad.X, sid, nu1)
+    z = model.get_latent_representation(use_mean=False, give_z=True)
+    assert z.shape == (50, dims.n_latent) and _rel(z, z1[np.arange(50), 0, sid]) < 3e-4
     model.close()
