@@ -96,6 +96,9 @@ __device__ __forceinline__ int wg_all(int wg, int pred) {
       : "memory");
   return out;
 }
+// the two warps that own the column halves of the same 32 rows (warps w and w + 4 of a warpgroup: same scheduler, same TMEM
+// lane quarter): the LayerNorm statistics exchange needs only them, not the whole warpgroup
+__device__ __forceinline__ void pair_sync(int wg, int r) { asm volatile("bar.sync %0, 64;" ::"r"(3 + wg * 4 + (r >> 5)) : "memory"); }
 __device__ __forceinline__ float sqrt_approx(float x) {
   float y;
   asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -210,21 +213,23 @@ __device__ __forceinline__ float dist_chunk_fast(float (&g)[32], const float* nr
 __device__ __forceinline__ void ep128(uint32_t t_lane, int half, int r, int wg, const float* g_s, const float* b_s,
                                       float2* xch) {
   float2 a1 = make_float2(0.f, 0.f), a2 = make_float2(0.f, 0.f);
-#pragma unroll 1
-  for (int pp = 0; pp < 2; ++pp) {
-    float v[32];
-    tmem_ld32(t_lane + (2 * half + pp) * 32, v);
+  {
+    float v[32], w[32];   // both chunks travel together: one TMEM round trip for the statistics pass
+    tmem_ld32(t_lane + (2 * half) * 32, v);
+    tmem_ld32(t_lane + (2 * half + 1) * 32, w);
     tmem_ld_wait();
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
-      const float2 x = make_float2(v[2 * i], v[2 * i + 1]);
+      const float2 x = make_float2(v[2 * i], v[2 * i + 1]), y = make_float2(w[2 * i], w[2 * i + 1]);
       a1 = __fadd2_rn(a1, x);
       a2 = __ffma2_rn(x, x, a2);
+      a1 = __fadd2_rn(a1, y);
+      a2 = __ffma2_rn(y, y, a2);
     }
   }
   float s1 = a1.x + a1.y, s2 = a2.x + a2.y;
   xch[half * 128 + r] = make_float2(s1, s2);
-  wg_sync(wg);
+  pair_sync(wg, r);
   const float2 o = xch[(half ^ 1) * 128 + r];
   s1 += o.x; s2 += o.y;
   const float mean = s1 * (1.0f / 128);
@@ -270,7 +275,7 @@ __device__ __forceinline__ void ep32(uint32_t t_lane32, int half, int r, int wg,
   }
   float s1 = a1.x + a1.y, s2 = a2.x + a2.y;
   xch[half * 128 + r] = make_float2(s1, s2);
-  wg_sync(wg);
+  pair_sync(wg, r);
   const float2 o = xch[(half ^ 1) * 128 + r];
   s1 += o.x; s2 += o.y;
   const float mean = s1 * (1.0f / 32);
@@ -312,7 +317,7 @@ __device__ __forceinline__ void ep32x(uint32_t t_d2_lane, int half, int r, int w
   }
   float s1 = a1.x + a1.y, s2 = a2.x + a2.y;
   xch[half * 128 + r] = make_float2(s1, s2);
-  wg_sync(wg);
+  pair_sync(wg, r);
   const float2 o = xch[(half ^ 1) * 128 + r];
   s1 += o.x; s2 += o.y;
   const float mean = s1 * (1.0f / 32);
@@ -343,17 +348,19 @@ __device__ __forceinline__ void issue_gemm_ts2_cat(uint32_t d_tmem, uint32_t a_t
   for (int ks = 0; ks < 8; ++ks) {
     const uint64_t bd = umma_desc(s_w + b.h + ks * 2 * b.lbo, b.lbo, 128);
     const uint32_t a = a_tmem + (ks >> 1) * 32 + (ks & 1) * 8;
-    umma_f16_ts(d_tmem, a, bd, idesc64, ks == 0 ? 0u : 1u);
+    umma_f16_ts(d_tmem, a, bd, idesc64, 1u);   // accumulates onto the skip part (issue_gemm_cat, issued earlier, clears)
     umma_f16_ts(d_tmem, a + 16, bd, idesc32, 1u);
   }
 }
-// [128 x K] (hi, lo in shared memory) x concatenated [K x (32 | 32)], accumulating: A_hi.[W_hi | W_lo] + A_lo.W_hi
+// [128 x K] (hi, lo in shared memory) x concatenated [K x (32 | 32)]: A_hi.[W_hi | W_lo] + A_lo.W_hi; clears D.  This is the
+// skip-connection part of GEMM2 / GEMM4: it does not depend on the epilogue in front of it, so it is issued right behind
+// GEMM1 / GEMM3 and runs under epilogue 1 / 3 (6 MMAs off the critical path of each)
 __device__ __forceinline__ void issue_gemm_cat(uint32_t d_tmem, uint32_t a_h, uint32_t a_l, uint32_t s_w, const TcOp& b, int K, int K_lo,
                                                uint32_t idesc64, uint32_t idesc32) {
   const uint32_t a_lbo = 128 * 16;
   for (int ks = 0; ks < K / 16; ++ks) {
     const uint64_t bd = umma_desc(s_w + b.h + ks * 2 * b.lbo, b.lbo, 128);
-    umma_f16(d_tmem, umma_desc(a_h + ks * 2 * a_lbo, a_lbo, 128), bd, idesc64, 1u);
+    umma_f16(d_tmem, umma_desc(a_h + ks * 2 * a_lbo, a_lbo, 128), bd, idesc64, ks == 0 ? 0u : 1u);
     if (ks * 16 < K_lo) umma_f16(d_tmem, umma_desc(a_l + ks * 2 * a_lbo, a_lbo, 128), bd, idesc32, 1u);
   }
 }
@@ -613,6 +620,7 @@ k_chain_fused_tc(const __grid_constant__ TcNet tc, CellBuf cb, int64_t n_cells, 
       if (elect_one()) {
         issue_gemm(iu_tr0, iu_a1h, iu_a1l, s_w, tc.b1, tc.K1, 32, idesc128, true);
         umma_commit(iu_bar);
+        issue_gemm_cat(iu_td2, iu_a1h, iu_a1l, s_w, tc.b2a, tc.K1, 32, idesc64, idesc32);
       }
       __syncwarp();
     }
@@ -626,7 +634,6 @@ k_chain_fused_tc(const __grid_constant__ TcNet tc, CellBuf cb, int64_t n_cells, 
       tc_fence_after();
       if (elect_one()) {
         issue_gemm_ts2_cat(iu_td2, iu_tr0, s_w, tc.b2t, idesc64, idesc32);
-        issue_gemm_cat(iu_td2, iu_a1h, iu_a1l, s_w, tc.b2a, tc.K1, 32, idesc64, idesc32);
         umma_commit(iu_bar);
       }
       __syncwarp();
@@ -643,6 +650,7 @@ k_chain_fused_tc(const __grid_constant__ TcNet tc, CellBuf cb, int64_t n_cells, 
       if (elect_one()) {
         issue_gemm(iu_tr0, iu_a3h, iu_a3l, s_w, tc.b3, tc.K3, tc.K3, idesc128, true);
         umma_commit(iu_bar);
+        issue_gemm_cat(iu_td2, iu_a3h, iu_a3l, s_w, tc.b4a, tc.K3, tc.K3, idesc64, idesc32);
       }
       __syncwarp();
     }
@@ -656,7 +664,6 @@ k_chain_fused_tc(const __grid_constant__ TcNet tc, CellBuf cb, int64_t n_cells, 
       tc_fence_after();
       if (elect_one()) {
         issue_gemm_ts2_cat(iu_td2, iu_tr0, s_w, tc.b4t, idesc64, idesc32);
-        issue_gemm_cat(iu_td2, iu_a3h, iu_a3l, s_w, tc.b4a, tc.K3, tc.K3, idesc64, idesc32);
         umma_commit(iu_bar);
       }
       __syncwarp();

@@ -81,6 +81,7 @@ struct TcNet {
   size_t smem_bytes = 0;
   size_t fused_smem_bytes = 0;  // 0: fused kernel unavailable for this shape
   size_t fused3_smem_bytes = 0; // 0: warp-specialised fused kernel (tc_fused3.cuh) unavailable for this shape
+  size_t fused4_smem_bytes = 0; // 0: ping-pong fused kernel (tc_fused4.cuh) unavailable for this shape / not selected
   bool ready = false;
 };
 
