@@ -1372,6 +1372,9 @@ int mrvi_run_de_host(MrviHandle* h, int64_t n_cells, const float* X, int64_t ldx
                           n_covariates, Amat, prefactor, per_cell_design, beta_out, effect_size_out, eps_out, chunk_cells);
 }
 
+#ifdef MRVI_DBG_FUSED
+int mrvi_dbg_fused_read(long long* out, int n) { return (int)cudaMemcpyFromSymbol(out, mrvi::g_dbg_fused, sizeof(long long) * n); }
+#endif
 #ifdef MRVI_DBG_F3
 int mrvi_dbg_f3_read(long long* out, int n) { return (int)cudaMemcpyFromSymbol(out, mrvi::g_dbg_f3, sizeof(long long) * n); }
 #endif

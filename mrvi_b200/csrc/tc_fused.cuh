@@ -28,6 +28,14 @@ namespace mrvi {
 
 constexpr int kFusedThreads = 512;
 
+#ifdef MRVI_DBG_FUSED
+// clock64 timeline of CTA 0 (tools/dbg/run_dbgf.py): [warpgroup][tile < 32][mark < 32], thread 0 of each warpgroup
+__device__ long long g_dbg_fused[2 * 32 * 32];
+#define FT(i_) do { if (blockIdx.x == 0 && wt == 0 && dbg_tile < 32) g_dbg_fused[(wg * 32 + dbg_tile) * 32 + (i_)] = clock64(); } while (0)
+#else
+#define FT(i_) do { } while (0)
+#endif
+
 struct FusedSmemMap {
   uint32_t w;            // weight image (hi | lo)
   uint32_t wg[2];        // per-warpgroup scratch: [a1h a1l a3h a3l] overlaid later by [zf] (z output only), then [zh zl | T | cref]
@@ -502,6 +510,10 @@ k_chain_fused_tc(const __grid_constant__ TcNet tc, CellBuf cb, int64_t n_cells, 
   const int64_t tile_begin = (int64_t)blockIdx.x * tiles_per_cta;
   const int64_t tile_end = min(n_tiles, tile_begin + tiles_per_cta);
   for (int64_t tile = tile_begin + wg; tile < tile_end; tile += 2) {
+#ifdef MRVI_DBG_FUSED
+    const int dbg_tile = (int)((tile - tile_begin) >> 1);
+#endif
+    FT(0);
     // tiles_per_cell > 1 (S > 128, chain only: z_out, no distances): tile -> (cell, 128-row slice of its samples)
     const int64_t pos = tiles_per_cell > 1 ? tile / tiles_per_cell : tile * cells_per_tile + lc;  // sorted position of this row's cell
     const int sr = tiles_per_cell > 1 ? (int)(tile % tiles_per_cell) * kTcRows + r : s;
@@ -611,8 +623,10 @@ k_chain_fused_tc(const __grid_constant__ TcNet tc, CellBuf cb, int64_t n_cells, 
         }
       }
     }
+    FT(1);
     fence_proxy_async();
     wg_sync(wg);
+    FT(2);
 
     // ================= GEMM1 / epilogue 1 =================
     if (issue_warp) {
@@ -624,11 +638,15 @@ k_chain_fused_tc(const __grid_constant__ TcNet tc, CellBuf cb, int64_t n_cells, 
       }
       __syncwarp();
     }
+    FT(3);
     mbar_wait(bar_mma, phase); phase ^= 1;
     tc_fence_after();
+    FT(4);
     ep128(t_lane, half, r, wg, g1, b1, xch);
     tc_fence_before();
+    FT(5);
     wg_sync(wg);
+    FT(6);
     // ================= GEMM2 / epilogue 2 =================
     if (issue_warp) {
       tc_fence_after();
@@ -638,12 +656,16 @@ k_chain_fused_tc(const __grid_constant__ TcNet tc, CellBuf cb, int64_t n_cells, 
       }
       __syncwarp();
     }
+    FT(7);
     mbar_wait(bar_mma, phase); phase ^= 1;
     tc_fence_after();
+    FT(8);
     ep32x(t_d2_lane, half, r, wg, g2, b2, xch, row_a3h, row_a3l);
     tc_fence_before();
     fence_proxy_async();
+    FT(9);
     wg_sync(wg);
+    FT(10);
     // ================= GEMM3 / epilogue 3 =================
     if (issue_warp) {
       tc_fence_after();
@@ -654,11 +676,15 @@ k_chain_fused_tc(const __grid_constant__ TcNet tc, CellBuf cb, int64_t n_cells, 
       }
       __syncwarp();
     }
+    FT(11);
     mbar_wait(bar_mma, phase); phase ^= 1;
     tc_fence_after();
+    FT(12);
     ep128(t_lane, half, r, wg, g3, b3, xch);
     tc_fence_before();
+    FT(13);
     wg_sync(wg);
+    FT(14);
     // ================= GEMM4 / epilogue 4 =================
     if (issue_warp) {
       tc_fence_after();
@@ -668,13 +694,17 @@ k_chain_fused_tc(const __grid_constant__ TcNet tc, CellBuf cb, int64_t n_cells, 
       }
       __syncwarp();
     }
+    FT(15);
     mbar_wait(bar_mma, phase); phase ^= 1;
     tc_fence_after();
+    FT(16);
     // A5 = [t4 | 1 | 0] reuses the A1 buffers (GEMM2 was their last reader); the one / zero columns are still in place
     ep32x(t_d2_lane, half, r, wg, g4, b4, xch, row_a1h, row_a1l);
     tc_fence_before();
     fence_proxy_async();
+    FT(17);
     wg_sync(wg);
+    FT(18);
     // ================= GEMM5 / residual rows =================
     if (issue_warp) {
       tc_fence_after();
@@ -684,8 +714,10 @@ k_chain_fused_tc(const __grid_constant__ TcNet tc, CellBuf cb, int64_t n_cells, 
       }
       __syncwarp();
     }
+    FT(19);
     mbar_wait(bar_mma, phase); phase ^= 1;
     tc_fence_after();
+    FT(20);
     // this thread's half of the N5 output columns stays in registers until the Gram operands are built
     const int ncol = tc.N5 >> 1, col0 = half * ncol;
     float v[32];
@@ -744,7 +776,9 @@ k_chain_fused_tc(const __grid_constant__ TcNet tc, CellBuf cb, int64_t n_cells, 
       for (int l = 0; l < 32; ++l)
         if (l < ncol) cref_s[lc * Kz + col0 + l] = v[l];
     }
+    FT(21);
     wg_sync(wg);  // reference rows visible; with z output: every thread is done with zf / rowinfo
+    FT(22);
     {
       const float* crow = cref_s + (row_in_tile ? lc : 0) * Kz + col0;
       float nrm_p = 0.f;
@@ -772,8 +806,10 @@ k_chain_fused_tc(const __grid_constant__ TcNet tc, CellBuf cb, int64_t n_cells, 
       }
       xch[half * 128 + r].x = nrm_p;
     }
+    FT(23);
     fence_proxy_async();
     wg_sync(wg);
+    FT(24);
     // ================= Gram on the tensor cores =================
     if (issue_warp) {
       tc_fence_after();
@@ -797,8 +833,10 @@ k_chain_fused_tc(const __grid_constant__ TcNet tc, CellBuf cb, int64_t n_cells, 
     }
     const float n_i = xch[r].x + xch[128 + r].x;
     if (half == 0) nrm_s[r] = n_i;
+    FT(25);
     mbar_wait(bar_mma, phase); phase ^= 1;
     tc_fence_after();
+    FT(26);
 
     // ================= group-run bookkeeping =================
     bool use_acc = false;
@@ -821,6 +859,7 @@ k_chain_fused_tc(const __grid_constant__ TcNet tc, CellBuf cb, int64_t n_cells, 
     } else {
       wg_sync(wg);  // publishes nrm_s
     }
+    FT(27);
     // ================= distance epilogue: this thread's chunks of row r =================
 #pragma unroll 1
     for (int c = ch_lo; c < ch_hi; ++c) {
@@ -924,6 +963,7 @@ k_chain_fused_tc(const __grid_constant__ TcNet tc, CellBuf cb, int64_t n_cells, 
         }
       }
     }
+    FT(28);
     if (use_acc) {
       tmem_st_wait();
       tc_fence_before();
@@ -932,6 +972,7 @@ k_chain_fused_tc(const __grid_constant__ TcNet tc, CellBuf cb, int64_t n_cells, 
     }
     tc_fence_before();
     wg_sync(wg);  // Gram / scratch fully consumed before the next tile reuses them
+    FT(29);
   }
 
   tc_fence_before();
