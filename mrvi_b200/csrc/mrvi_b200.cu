@@ -22,8 +22,6 @@
 #include "tc_kernels.cuh"
 #include "tc_encoder.cuh"
 #include "tc_fused.cuh"
-#include "tc_fused3.cuh"
-#include "tc_fused4.cuh"
 #include "tc_dist.cuh"
 #include "sampled_kernels.cuh"
 
@@ -527,15 +525,11 @@ static int run_device_impl(MrviHandle* h, int64_t n, const float* X, int64_t ldx
     float* z = z_out ? z_out + lo * net.S * net.L : h->zbuf;
     if ((err = launch_encoder(h, X + lo * ldx, ldx, sid + lo, m, st))) return err;
     if (time_stages) cudaEventRecord(e1, st);
-    const bool f3 = h->precision == MRVI_PRECISION_TC && tc_fused3_supported(h->tc, net.S, net.L, norm);
-    const bool f4 = h->precision == MRVI_PRECISION_TC && tc_fused4_supported(h->tc, net.S, norm);
-    if (h->precision == MRVI_PRECISION_TC && need_dist && (f3 || f4 || (h->tc.fused_smem_bytes && tc_fused_supported(h->tc, net.S, norm)))) {
+    if (h->precision == MRVI_PRECISION_TC && need_dist && h->tc.fused_smem_bytes && tc_fused_supported(h->tc, net.S, norm)) {
       // fused: chain + distances + group sums in one kernel; z never leaves the SM unless asked for
       GroupPlan gp;
       if ((err = plan_groups(h, m, n_keys, codes, lo, n_groups, sums, &gp, st))) return err;
-      if (f4) tc_launch_fused4(h->tc, h->net, m, h->cb, z_out ? z : nullptr, cell_out ? cell_out + lo * net.S * net.S : nullptr, gp, st);
-      else if (f3) tc_launch_fused3(h->tc, h->net, m, h->cb, z_out ? z : nullptr, cell_out ? cell_out + lo * net.S * net.S : nullptr, gp, st);
-      else tc_launch_fused(h->tc, h->net, m, h->cb, z_out ? z : nullptr, cell_out ? cell_out + lo * net.S * net.S : nullptr, gp, st);
+      tc_launch_fused(h->tc, h->net, m, h->cb, z_out ? z : nullptr, cell_out ? cell_out + lo * net.S * net.S : nullptr, gp, st);
       LAUNCH_CHECK();
       if (time_stages) { cudaEventRecord(e2, st); cudaEventRecord(e3, st); }
       if (u_out) CUDA_TRY(cudaMemcpyAsync(u_out + lo * net.Lq, h->cb.u, m * net.Lq * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -543,9 +537,7 @@ static int run_device_impl(MrviHandle* h, int64_t n, const float* X, int64_t ldx
     }
     if (need_z) {
       if (h->precision == MRVI_PRECISION_TC) {
-        if (h->tc.fused4_smem_bytes) { GroupPlan none; memset(&none, 0, sizeof(none)); tc_launch_fused4(h->tc, h->net, m, h->cb, z, nullptr, none, st); }
-        else if (h->tc.fused3_smem_bytes) { GroupPlan none; memset(&none, 0, sizeof(none)); tc_launch_fused3(h->tc, h->net, m, h->cb, z, nullptr, none, st); }
-        else if (h->tc.fused_smem_bytes) tc_launch_fused_chain(h->tc, h->net, m, h->cb, z, st);  // two threads per row, 1 CTA / SM
+        if (h->tc.fused_smem_bytes) tc_launch_fused_chain(h->tc, h->net, m, h->cb, z, st);  // two threads per row, 1 CTA / SM
         else if ((err = tc_launch_qz(h->tc, h->net, m, h->cb, z, st))) return err;
         LAUNCH_CHECK();
       } else {
@@ -590,20 +582,14 @@ static int chain_and_dist(MrviHandle* h, const CellBuf& cb, int64_t n, int norm,
   const NetW& net = h->net;
   const bool need_dist = cell_out != nullptr || gp.n_keys > 0;
   int err;
-  const bool f3 = h->precision == MRVI_PRECISION_TC && tc_fused3_supported(h->tc, net.S, net.L, norm);
-  const bool f4 = h->precision == MRVI_PRECISION_TC && tc_fused4_supported(h->tc, net.S, norm);
-  if (h->precision == MRVI_PRECISION_TC && need_dist && (f3 || f4 || (h->tc.fused_smem_bytes && tc_fused_supported(h->tc, net.S, norm)))) {
-    if (f4) tc_launch_fused4(h->tc, net, n, cb, z_out, cell_out, gp, st);
-    else if (f3) tc_launch_fused3(h->tc, net, n, cb, z_out, cell_out, gp, st);
-    else tc_launch_fused(h->tc, net, n, cb, z_out, cell_out, gp, st);
+  if (h->precision == MRVI_PRECISION_TC && need_dist && h->tc.fused_smem_bytes && tc_fused_supported(h->tc, net.S, norm)) {
+    tc_launch_fused(h->tc, net, n, cb, z_out, cell_out, gp, st);
     LAUNCH_CHECK();
     return 0;
   }
   float* z = z_out ? z_out : z_scratch;
   if (h->precision == MRVI_PRECISION_TC) {
-    if (h->tc.fused4_smem_bytes) { GroupPlan none; memset(&none, 0, sizeof(none)); tc_launch_fused4(h->tc, net, n, cb, z, nullptr, none, st); }
-    else if (h->tc.fused3_smem_bytes) { GroupPlan none; memset(&none, 0, sizeof(none)); tc_launch_fused3(h->tc, net, n, cb, z, nullptr, none, st); }
-    else if (h->tc.fused_smem_bytes) tc_launch_fused_chain(h->tc, net, n, cb, z, st);
+    if (h->tc.fused_smem_bytes) tc_launch_fused_chain(h->tc, net, n, cb, z, st);
     else if ((err = tc_launch_qz(h->tc, net, n, cb, z, st))) return err;
     LAUNCH_CHECK();
   } else {
@@ -1033,10 +1019,6 @@ int mrvi_create(const MrviDims* dims, int32_t n_params, const char* const* names
     if ((err = enc_tc_build(h->enc_tc, h->net, pt.m, h->arena))) return fail(err, "%s", tc_error());
     if (h->enc_tc.ready) CUDA_TRY(h->arena.alloc((void**)&h->h1buf, (size_t)h->chunk_cells * 128 * sizeof(float)));
     if ((err = tc_fused_prepare(h->tc, h->dims.n_latent))) return fail(err, "%s", tc_error());
-    // tc_fused3.cuh (dedicated issuer warp + attention producer warps, setmaxnreg) is an opt-in experiment: measured
-    // slower than the two-warpgroup kernel once that one issues its MMAs from a warp-uniform branch
-    if (getenv("MRVI_B200_FUSED") && atoi(getenv("MRVI_B200_FUSED")) == 3 && (err = tc_fused3_prepare(h->tc))) return fail(err, "%s", tc_error());
-    if (getenv("MRVI_B200_FUSED") && atoi(getenv("MRVI_B200_FUSED")) == 4 && (err = tc_fused4_prepare(h->tc, h->dims.n_latent))) return fail(err, "%s", tc_error());
     if (dist_tc_supported(h->net.S, h->net.L, MRVI_NORM_L2) && (err = dist_tc_prepare(h->net.L, h->net.S, &h->dist_tc_smem)))
       return fail(err, "%s", tc_error());
     if (h->enc_tc.ready && !getenv("MRVI_B200_FP32_ENCODER_TAIL")) {
@@ -1374,12 +1356,6 @@ int mrvi_run_de_host(MrviHandle* h, int64_t n_cells, const float* X, int64_t ldx
 
 #ifdef MRVI_DBG_FUSED
 int mrvi_dbg_fused_read(long long* out, int n) { return (int)cudaMemcpyFromSymbol(out, mrvi::g_dbg_fused, sizeof(long long) * n); }
-#endif
-#ifdef MRVI_DBG_F3
-int mrvi_dbg_f3_read(long long* out, int n) { return (int)cudaMemcpyFromSymbol(out, mrvi::g_dbg_f3, sizeof(long long) * n); }
-#endif
-#ifdef MRVI_DBG_F4
-int mrvi_dbg_f4_read(long long* out, int n) { return (int)cudaMemcpyFromSymbol(out, mrvi::g_dbg_f4, sizeof(long long) * n); }
 #endif
 #ifdef MRVI_DBG_ENC
 int mrvi_dbg_enc_read(long long* out, int n) { return (int)cudaMemcpyFromSymbol(out, mrvi::g_dbg_enc, sizeof(long long) * n); }

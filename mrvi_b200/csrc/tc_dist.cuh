@@ -5,7 +5,7 @@
 // kernel forms the S x S matrix from z on the tensor cores instead of the fp32 direct-difference kernel:
 //
 //   * one persistent CTA per SM, 512 threads; a CTA owns a contiguous range of SORTED cell positions;
-//   * prep (all threads, two per sample row): z rows are re-centred on the cell's sample 0 (any per-cell
+//   * prep (all threads, two per sample row): z rows are re-centred on the mean of four of the cell's rows (any per-cell
 //     shift cancels in the distances; it keeps the norms small), split into (hi, lo) f16 and stored as a
 //     K-major UMMA operand of 256 rows, double buffered so that the prep of cell p+1 overlaps the MMAs of p;
 //   * the matrix is covered by the three 128 x 128 blocks (0,0), (0,1), (1,1) -- D is symmetric, block (1,0)
@@ -160,7 +160,17 @@ k_dist_gram_tc(const float* __restrict__ z, int64_t n_cells, int S, int L, float
 #pragma unroll
     for (int j2 = 0; j2 < 4; ++j2) {
       const int k0 = c * 8 + 2 * j2;
-      z0p[j2] = make_float2(k0 < L ? -stage[k0] : 0.f, k0 + 1 < L ? -stage[k0 + 1] : 0.f);
+      // centre = mean of four of the cell's rows (samples 0, S/4, S/2, 3S/4): closer to the cell's mean than one sample, so
+      // fewer entries fall under the exact-recompute threshold (see the fused kernel; the whole tile is staged here, so
+      // four rows cost four loads per chunk element and cell)
+      float cx = 0.f, cy = 0.f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float* zq = stage + ((q * S) >> 2) * L;
+        cx += k0 < L ? zq[k0] : 0.f;
+        cy += k0 + 1 < L ? zq[k0 + 1] : 0.f;
+      }
+      z0p[j2] = make_float2(-0.25f * cx, -0.25f * cy);
     }
     const bool even = (L & 1) == 0;
 #pragma unroll 2

@@ -48,6 +48,7 @@ struct FusedSmemMap {
   uint32_t total;
   int zf_ld;             // row stride (floats) of the fp32 z tile, odd
   int Kz;                // padded K of the Gram operands (32 or 64)
+  int cref_rows;         // reference rows per cell whose mean is the centre of the Gram operands (2; 1 when n_latent > 32)
 };
 
 __host__ __device__ inline FusedSmemMap fused_smem_map(uint32_t wimg_bytes, int K1, int K3, int L) {
@@ -62,12 +63,13 @@ __host__ __device__ inline FusedSmemMap fused_smem_map(uint32_t wimg_bytes, int 
   m.zf_ld = m.Kz + 1;
   // A1 / A3 are dead after GEMM5.  The fp32 z tile (only when z is an output) is copied out before the Gram operands
   // overwrite it; behind the operands: the keep_cell staging tiles T (8 warps x 2 KB) and the per-cell reference rows
-  // cref [32 cells][Kz] fp32 (sample 0 of each cell, subtracted before the Gram).
+  // cref [32 cells][2][Kz] fp32 (samples 0 and S / 2 of each cell; their mean is subtracted before the Gram).
   const uint32_t zf = up(128 * m.zf_ld * 4), zk = up(128 * m.Kz * 2);
   m.off_zf = 0; m.off_zh = 0; m.off_zl = zk; m.off_T = 2 * zk; m.off_cref = 2 * zk + 16384;
   uint32_t scratch = abytes;
   if (scratch < zf) scratch = zf;
-  if (scratch < m.off_cref + 32u * m.Kz * 4u) scratch = m.off_cref + 32u * m.Kz * 4u;
+  m.cref_rows = m.Kz == 32 ? 2 : 1;
+  if (scratch < m.off_cref + 32u * m.Kz * 4u * m.cref_rows) scratch = m.off_cref + 32u * m.Kz * 4u * m.cref_rows;
   m.wg[0] = o; o += scratch;
   m.wg[1] = o; o += scratch;
   m.nrm[0] = o; o += 512;
@@ -91,19 +93,6 @@ struct FusedCtrl {
 };
 
 __device__ __forceinline__ void wg_sync(int wg) { asm volatile("bar.sync %0, 256;" ::"r"(wg + 1) : "memory"); }
-// warpgroup-wide AND of a predicate (bar.red on the warpgroup's named barrier)
-__device__ __forceinline__ int wg_all(int wg, int pred) {
-  int out;
-  asm volatile(
-      "{\n\t.reg .pred p, q;\n\t"
-      "setp.ne.b32 q, %2, 0;\n\t"
-      "bar.red.and.pred p, %1, 256, q;\n\t"
-      "selp.b32 %0, 1, 0, p;\n\t}"
-      : "=r"(out)
-      : "r"(wg + 1), "r"(pred)
-      : "memory");
-  return out;
-}
 // the two warps that own the column halves of the same 32 rows (warps w and w + 4 of a warpgroup: same scheduler, same TMEM
 // lane quarter): the LayerNorm statistics exchange needs only them, not the whole warpgroup
 __device__ __forceinline__ void pair_sync(int wg, int r) { asm volatile("bar.sync %0, 64;" ::"r"(3 + wg * 4 + (r >> 5)) : "memory"); }
@@ -203,7 +192,8 @@ __device__ __forceinline__ float dist_chunk_fast(float (&g)[32], const float* nr
       const float2 d2 = __ffma2_rn(make_float2(g[q], g[q + 1]), m2, sn);
       const float2 tt = __ffma2_rn(sn, thr2, d2);  // < 0: cancellation dominated
       float t0 = tt.x, t1 = tt.y;
-      float r0 = sqrt_approx(fmaxf(d2.x, 0.f)), r1 = sqrt_approx(fmaxf(d2.y, 0.f));
+      // |d2|: the operand modifier is free; an entry with d2 < 0 is below the threshold (tt < 0) and recomputed anyway
+      float r0 = sqrt_approx(fabsf(d2.x)), r1 = sqrt_approx(fabsf(d2.y));
       if (DIAG) {
         const bool dg0 = q == lane, dg1 = q + 1 == lane;
         t0 = dg0 ? 0.f : t0; t1 = dg1 ? 0.f : t1;
@@ -428,6 +418,7 @@ k_chain_fused_tc(const __grid_constant__ TcNet tc, CellBuf cb, int64_t n_cells, 
   FusedCtrl* ctrl = reinterpret_cast<FusedCtrl*>(smem + sm.ctrl);
   const int tid = threadIdx.x, wg = tid >> 8, wt = tid & 255, half = wt >> 7, r = wt & 127, warp_q = (wt >> 5) & 3;
   const int Kz = sm.Kz, zld = sm.zf_ld;
+  const bool kc2 = sm.cref_rows == 2;
   float* lnv = reinterpret_cast<float*>(smem + sm.lnv);
 
   if (tid == 0) {
@@ -455,8 +446,6 @@ k_chain_fused_tc(const __grid_constant__ TcNet tc, CellBuf cb, int64_t n_cells, 
   const uint32_t t_lane = t_r0 + lane_off, t_d2_lane = t_d2 + lane_off, t_acc_lane = tmem_base + 384 + lane_off;
   uint8_t* scratch = smem + sm.wg[wg];
   const uint32_t s_w = smem_u32(smem + sm.w);
-  const uint32_t s_a1h = smem_u32(scratch), s_a1l = s_a1h + sm.off_a1l, s_a3h = s_a1h + sm.off_a3h, s_a3l = s_a1h + sm.off_a3l;
-  const uint32_t s_zh = s_a1h + sm.off_zh, s_zl = s_a1h + sm.off_zl;
   uint8_t* row_a1h = scratch + r * 16;
   uint8_t* row_a1l = scratch + sm.off_a1l + r * 16;
   uint8_t* row_a3h = scratch + sm.off_a3h + r * 16;
@@ -519,7 +508,6 @@ k_chain_fused_tc(const __grid_constant__ TcNet tc, CellBuf cb, int64_t n_cells, 
     const int sr = tiles_per_cell > 1 ? (int)(tile % tiles_per_cell) * kTcRows + r : s;
     const bool valid = tiles_per_cell > 1 ? (sr < S && pos < n_cells) : (row_in_tile && pos < n_cells);
     const int64_t cell = valid ? (gp.order ? (int64_t)gp.order[pos] : pos) : 0;
-    const int code = (valid && gp.n_keys) ? gp.comp_sorted[pos] : -2;
     const int ss = valid ? sr : 0;
     // sampled paths: every (cell, s) row carries its own draw of u (CellBuf::per_row); z_base then differs
     // between the rows of a cell and no longer cancels in the distances
@@ -527,9 +515,8 @@ k_chain_fused_tc(const __grid_constant__ TcNet tc, CellBuf cb, int64_t n_cells, 
 
     // ================= attention features of head `half` -> A1 chunks 2*half, 2*half+1 =================
     if (tc.att_tab != nullptr && !cb.per_row) {
-      // table path (tc_build): the 16 features of this thread are 16 look-ups of ITS sample's cubic-Hermite table; the rows
+      // table path (tc_build): the 16 features of this thread are 16 look-ups of ITS sample's table of cubics; the rows
       // of a cell share the cell's query tokens, so the lanes of a warp read consecutive 16-byte entries of one interval
-      const float4* tb = tc.att_tab + ss;
       const float4* qp4 = reinterpret_cast<const float4*>(cb.q_tok + fi * 16);
       const float t0s = -tc.att_t0 * tc.att_scale;
       const float as = a_h * tc.att_scale, bs = fmaf(b_h, tc.att_scale, t0s);   // x = (alpha q + beta - t0) * scale
@@ -544,7 +531,7 @@ k_chain_fused_tc(const __grid_constant__ TcNet tc, CellBuf cb, int64_t n_cells, 
           const float x = fminf(fmaxf(fmaf(as, qv[f], bs), 0.f), tc.att_xmax);
           const int k = (int)x;
           fr[f] = x - (float)k;
-          nd[f] = __ldg(tb + (size_t)k * S);
+          nd[f] = __ldg(tc.att_tab + (uint32_t)(k * S + ss));   // uniform base + 32-bit index
         }
 #pragma unroll
         for (int f2 = 0; f2 < 4; ++f2) {
@@ -552,9 +539,8 @@ k_chain_fused_tc(const __grid_constant__ TcNet tc, CellBuf cb, int64_t n_cells, 
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
             const float4 n4 = nd[2 * f2 + e];
-            const float u = fr[2 * f2 + e], df = n4.z - n4.x;
-            const float c3 = fmaf(-2.f, df, n4.y + n4.w), c2 = fmaf(3.f, df, fmaf(-2.f, n4.y, -n4.w));
-            mm[e] = fmaf(u, fmaf(u, fmaf(u, c3, c2), n4.y), n4.x);
+            const float u = fr[2 * f2 + e];
+            mm[e] = fmaf(u, fmaf(u, fmaf(u, n4.w, n4.z), n4.y), n4.x);   // entries are the cubic's coefficients
           }
           uint32_t hw, lw;
           split2(mm[0], mm[1], hw, lw);
@@ -607,20 +593,6 @@ k_chain_fused_tc(const __grid_constant__ TcNet tc, CellBuf cb, int64_t n_cells, 
       if (half == 0) {  // constant-one column (k = 32) and zero padding of A1
         for (int c = 4; c < tc.K1 / 8; ++c)   // (the lo copy of A1 holds the feature chunks only: issue_gemm K_lo = 32)
           *reinterpret_cast<uint4*>(row_a1h + c * 2048) = make_uint4(c == 4 ? 0x00003C00u : 0u, 0u, 0u, 0u);
-      } else {          // A3 static part: column 32 = 1.0, columns 33.. = u_ln[0..Lq), then zeros
-        const float* ul = cb.u_ln + fi * Lq;
-        for (int c = 4; c < tc.K3 / 8; ++c) {
-          uint32_t hw[4], lw[4];
-#pragma unroll
-          for (int j2 = 0; j2 < 4; ++j2) {
-            const int k0 = (c - 4) * 8 + 2 * j2 - 1, k1 = k0 + 1;   // index into u_ln; -1 = the constant column
-            const float a = k0 < 0 ? 1.0f : (k0 < Lq ? __ldg(ul + k0) : 0.f);
-            const float b = k1 < Lq ? __ldg(ul + k1) : 0.f;
-            split2(a, b, hw[j2], lw[j2]);
-          }
-          *reinterpret_cast<uint4*>(row_a3h + c * 2048) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-          *reinterpret_cast<uint4*>(row_a3l + c * 2048) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-        }
       }
     }
     FT(1);
@@ -637,6 +609,21 @@ k_chain_fused_tc(const __grid_constant__ TcNet tc, CellBuf cb, int64_t n_cells, 
         issue_gemm_cat(iu_td2, iu_a1h, iu_a1l, s_w, tc.b2a, tc.K1, 32, idesc64, idesc32);
       }
       __syncwarp();
+    }
+    if (half == 1) {  // A3 static part under GEMM1 (GEMM3 is its first reader): column 32 = 1.0, columns 33.. = u_ln[0..Lq), then zeros
+      const float* ul = cb.u_ln + fi * Lq;
+      for (int c = 4; c < tc.K3 / 8; ++c) {
+        uint32_t hw[4], lw[4];
+#pragma unroll
+        for (int j2 = 0; j2 < 4; ++j2) {
+          const int k0 = (c - 4) * 8 + 2 * j2 - 1, k1 = k0 + 1;   // index into u_ln; -1 = the constant column
+          const float a = k0 < 0 ? 1.0f : (k0 < Lq ? __ldg(ul + k0) : 0.f);
+          const float b = k1 < Lq ? __ldg(ul + k1) : 0.f;
+          split2(a, b, hw[j2], lw[j2]);
+        }
+        *reinterpret_cast<uint4*>(row_a3h + c * 2048) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+        *reinterpret_cast<uint4*>(row_a3l + c * 2048) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+      }
     }
     FT(3);
     mbar_wait(bar_mma, phase); phase ^= 1;
@@ -769,18 +756,24 @@ k_chain_fused_tc(const __grid_constant__ TcNet tc, CellBuf cb, int64_t n_cells, 
     }
 
     // ================= reference row per cell, norms, (hi, lo) Gram operands =================
-    // Distances are invariant under a per-cell shift: every row is re-centred on the cell's sample 0 (keeps the
-    // norms, and with them the cancellation in n_i + n_j - 2 g, small; the same choice as k_dist_gram_tc).
-    if (row_in_tile && s == 0) {
+    // Distances are invariant under a per-cell shift: every row is re-centred on the mean of two of the cell's rows (samples 0
+    // and S / 2), which keeps the norms -- and with them the cancellation in n_i + n_j - 2 g -- small.  The closer the centre is
+    // to the cell's mean, the fewer entries fall under the exact-recompute threshold (a ~1.5 K clk detour each, in groupby mode
+    // under the accumulator lock): on random models with S = 128, 0.1-21 entries per cell with sample 0 alone, 0-3.7 with two
+    // samples, 0-1.7 with the exact mean (which would cost a reduction over the rows).
+    if (row_in_tile && (s == 0 || (kc2 && s == (S >> 1)))) {
+      float* dst = cref_s + (lc * 2 + (s == 0 ? 0 : 1)) * Kz + col0;
 #pragma unroll
       for (int l = 0; l < 32; ++l)
-        if (l < ncol) cref_s[lc * Kz + col0 + l] = v[l];
+        if (l < ncol) dst[l] = v[l];
     }
     FT(21);
     wg_sync(wg);  // reference rows visible; with z output: every thread is done with zf / rowinfo
     FT(22);
     {
-      const float* crow = cref_s + (row_in_tile ? lc : 0) * Kz + col0;
+      const float* crow = cref_s + (row_in_tile ? lc : 0) * 2 * Kz + col0;
+      const int c1off = kc2 ? Kz : 0;   // one reference row only (n_latent > 32: shared memory): the "second" row is the first
+      const float2 mh2 = make_float2(-0.5f, -0.5f);
       float nrm_p = 0.f;
       const int nch = Kz >> 4;  // K chunks per half
 #pragma unroll
@@ -791,9 +784,9 @@ k_chain_fused_tc(const __grid_constant__ TcNet tc, CellBuf cb, int64_t n_cells, 
 #pragma unroll
           for (int j2 = 0; j2 < 4; ++j2) {
             const int k0 = cc * 8 + 2 * j2;
-            const float2 cr = *reinterpret_cast<const float2*>(crow + k0);
-            const float a = v[k0] - cr.x;
-            const float b = v[k0 + 1] - cr.y;
+            const float2 cr0 = *reinterpret_cast<const float2*>(crow + k0), cr1 = *reinterpret_cast<const float2*>(crow + c1off + k0);
+            const float2 ab = __ffma2_rn(cr1, mh2, __ffma2_rn(cr0, mh2, make_float2(v[k0], v[k0 + 1])));
+            const float a = ab.x, b = ab.y;
             split2(a, b, hw[j2], lw[j2]);
             // norms from the values the tensor core sees (hi + lo), so that n_i + n_j - 2 g cancels consistently
             const float ar = h2f_lo(hw[j2]) + h2f_lo(lw[j2]), br = h2f_hi(hw[j2]) + h2f_hi(lw[j2]);
@@ -831,6 +824,14 @@ k_chain_fused_tc(const __grid_constant__ TcNet tc, CellBuf cb, int64_t n_cells, 
       }
       __syncwarp();
     }
+    // group-run bookkeeping, first half: the composite codes of the tile's first and last cell travel under the Gram MMAs.  The
+    // cells are sorted by that code, so the tile lies inside one group run exactly when the two agree -- every thread sees it
+    // without a reduction barrier.
+    int first_code = -1, last_code = -1;
+    if (gp.n_keys > 0) {
+      first_code = gp.comp_sorted[min(tile * cells_per_tile, n_cells - 1)];
+      last_code = gp.comp_sorted[min(tile * cells_per_tile + cells_per_tile - 1, n_cells - 1)];
+    }
     const float n_i = xch[r].x + xch[128 + r].x;
     if (half == 0) nrm_s[r] = n_i;
     FT(25);
@@ -841,8 +842,8 @@ k_chain_fused_tc(const __grid_constant__ TcNet tc, CellBuf cb, int64_t n_cells, 
     // ================= group-run bookkeeping =================
     bool use_acc = false;
     if (gp.n_keys > 0) {
-      const int first_code = gp.comp_sorted[min(tile * cells_per_tile, n_cells - 1)];
-      use_acc = wg_all(wg, ((!valid) || code == first_code) ? 1 : 0) != 0;  // also publishes nrm_s
+      use_acc = first_code == last_code;
+      if (!use_acc) wg_sync(wg);  // publishes nrm_s (the lock's barrier does otherwise)
       if (use_acc) {
         if (issuer) { while (atomicCAS(&ctrl->lock, 0, 1) != 0) __nanosleep(20); }
         wg_sync(wg);

@@ -71,7 +71,8 @@ struct TcNet {
   int K1 = 48, K3 = 48, K5 = 48, N5 = 32;
   float alpha[2] = {0, 0}, beta[2] = {0, 0};  // t[h,i] = alpha[h] * q_tok[i] + beta[h]
   // Attention table (see tc_build): m_s(t) = sum_j softmax_j(t kv_s[j]) kv_s[j] is ONE smooth scalar function per sample;
-  // att_tab[k][s] = (f, h f', f_next, h f'_next) of interval k of a uniform grid over the whole reachable range of t.
+  // att_tab[k][s] = coefficients (a0, a1, a2, a3) of the cubic Hermite interpolant of interval k (a(u) = a0 + u (a1 + u (a2 + u a3)),
+  // u in [0, 1)) of a uniform grid over the whole reachable range of t.
   const float4* att_tab = nullptr;  // [att_n][S], nullptr = evaluate the softmax directly (16 ex2 per feature)
   int att_n = 0;                    // intervals
   float att_t0 = 0.f, att_scale = 0.f, att_xmax = 0.f;  // x = (t - t0) * scale clamped to [0, xmax], xmax < att_n
@@ -80,8 +81,6 @@ struct TcNet {
   int sm_count = 148;
   size_t smem_bytes = 0;
   size_t fused_smem_bytes = 0;  // 0: fused kernel unavailable for this shape
-  size_t fused3_smem_bytes = 0; // 0: warp-specialised fused kernel (tc_fused3.cuh) unavailable for this shape
-  size_t fused4_smem_bytes = 0; // 0: ping-pong fused kernel (tc_fused4.cuh) unavailable for this shape / not selected
   bool ready = false;
 };
 
@@ -240,13 +239,19 @@ __device__ __forceinline__ float gelu2x_fast(float x) {
   const float t = tanh_approx(x * p);
   return fmaf(x, t, x);
 }
-// (hi, lo) f16 split of two floats: hi = leading 11 significant bits (exact in f16 when the
-// exponent is in range), lo = remainder rounded to f16.  Returns packed f16x2 words.
+// (hi, lo) f16 split of two floats, returned as packed f16x2 words:
+// hi = RN_f16(x) (one packed conversion for the pair), lo = RN_f16(x - hi) with the remainder formed by the mixed-precision
+// FMA (FHFMA: f32 = f16 * f16 + f32, the half selected by an operand modifier): 4 instructions per pair instead of 5-6
 __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
-  const float ah = __uint_as_float(__float_as_uint(a) & 0xFFFFE000u);
-  const float bh = __uint_as_float(__float_as_uint(b) & 0xFFFFE000u);
-  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(bh), "f"(ah));  // upper half = first source
-  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(b - bh), "f"(a - ah));
+  float la, lb;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));  // upper half = first source
+  asm("{\n\t.reg .b16 l, u, m;\n\t"
+      "mov.b32 {l, u}, %2;\n\t"
+      "mov.b16 m, 0xBC00;\n\t"   // -1.0
+      "fma.rn.f32.f16 %0, l, m, %3;\n\t"
+      "fma.rn.f32.f16 %1, u, m, %4;\n\t}"
+      : "=f"(la), "=f"(lb) : "r"(hi), "f"(a), "f"(b));
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(lb), "f"(la));
 }
 
 // ------------------------------------------------------------------------------------------
@@ -827,10 +832,13 @@ inline int tc_build(TcNet& tc, const NetW& net, const MrviDims& d, const tc_deta
         for (int k = 0; k < N; ++k) {
           double d1;
           const double f1 = feval(s, T0 + (k + 1) * hstep, &d1);
-          const float4 e = make_float4((float)f0, (float)(d0 * hstep), (float)f1, (float)(d1 * hstep));
+          // the cubic Hermite interpolant of the interval in monomial form (a0, a1, a2, a3), a(u) = a0 + u (a1 + u (a2 + u a3)):
+          // three FMAs per look-up in the kernel instead of eight instructions
+          const double hd0 = d0 * hstep, hd1 = d1 * hstep, dfd = f1 - f0;
+          const float4 e = make_float4((float)f0, (float)hd0, (float)(3 * dfd - 2 * hd0 - hd1), (float)(hd0 + hd1 - 2 * dfd));
           tab[(size_t)k * S + s] = e;
-          for (double u : {0.25, 0.5, 0.75}) {   // the float32 entry, evaluated as the kernel does
-            const double df = (double)e.z - e.x, c3 = (double)e.y + e.w - 2 * df, c2 = 3 * df - 2 * (double)e.y - e.w;
+          for (double u : {0.25, 0.5, 0.75, 1.0}) {   // the float32 entry, evaluated as the kernel does (u = 1: continuity)
+            const double c2 = e.z, c3 = e.w;
             const double val = e.x + u * (e.y + u * (c2 + u * c3));
             worst = std::max(worst, std::fabs(val - feval(s, T0 + (k + u) * hstep, nullptr)) / std::max(scale_s, 1e-30));
           }
@@ -915,13 +923,8 @@ __device__ __forceinline__ float log1p_fast(float x) {
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(1.0f + x));
   return y * 0.6931471805599453f;
 }
-// (hi, lo) f16 split of a pair (see split2): the two remainders come from one FADD2
-__device__ __forceinline__ void split2v(float2 a, uint32_t& hi, uint32_t& lo) {
-  const float2 ah = make_float2(__uint_as_float(__float_as_uint(a.x) & 0xFFFFE000u), __uint_as_float(__float_as_uint(a.y) & 0xFFFFE000u));
-  const float2 r = __fadd2_rn(a, make_float2(-ah.x, -ah.y));
-  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(ah.y), "f"(ah.x));
-  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(r.y), "f"(r.x));
-}
+// (hi, lo) f16 split of a pair (see split2)
+__device__ __forceinline__ void split2v(float2 a, uint32_t& hi, uint32_t& lo) { split2(a.x, a.y, hi, lo); }
 
 // log1p of a pair through MUFU.LG2, packed add / multiply
 __device__ __forceinline__ float2 log1p_fast2(float2 x) {
