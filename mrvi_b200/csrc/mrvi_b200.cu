@@ -1200,6 +1200,14 @@ static int run_host_impl(MrviHandle* h, int64_t n_cells, const float* X, int x_k
   h->ev_used = 0;
   h->last_h2d_bytes = 0;
   int pack_mode[2] = {0, 0};
+  int64_t pack_rows[2] = {0, 0};   // leading rows of the chunk that travel narrowed (the rest, if any, is copied raw)
+  bool x_pinned = false;           // the caller's matrix is page-locked: raw rows can be pulled by the copy engine concurrently
+  if (!csr && x_kind == 0 && X != nullptr && !getenv("MRVI_B200_NO_SPLIT_H2D")) {
+    cudaPointerAttributes pa;
+    if (cudaPointerGetAttributes(&pa, X) == cudaSuccess) x_pinned = pa.type == cudaMemoryTypeHost;
+    else cudaGetLastError();
+  }
+  const double pcie_gbps = getenv("MRVI_B200_PCIE_GBPS") ? std::max(1.0, atof(getenv("MRVI_B200_PCIE_GBPS"))) : 47.0;  // raw float32 rate of the link
   CUDA_TRY(cudaEventRecord(h->ev_call[0], hs.s_comp));
   int64_t c = 0;
   for (int64_t lo = 0; lo < n_cells; lo += ch, ++c) {
@@ -1207,6 +1215,7 @@ static int run_host_impl(MrviHandle* h, int64_t n_cells, const float* X, int x_k
     const int64_t m = std::min(ch, n_cells - lo);
     // H2D (wait until the kernels of chunk c-2 released input buffers b)
     if (c >= 2) CUDA_TRY(cudaStreamWaitEvent(hs.s_h2d, hs.ev_comp[b], 0));
+    pack_rows[b] = m;
     if (csr) {
       const int64_t nz0 = indptr[lo], nnz = indptr[lo + m] - nz0;
       CUDA_TRY(cudaMemcpyAsync(hs.csr_ptr[b], indptr + lo, (m + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, hs.s_h2d));
@@ -1238,34 +1247,52 @@ static int run_host_impl(MrviHandle* h, int64_t n_cells, const float* X, int x_k
       }
     } else {
       int narrow = 0;
-      // The narrowing pays only if the host reads X faster than PCIe would carry it raw (~47 GB/s measured): keep it
-      // while the measured rate stays above the threshold.  (Mixing narrowed and raw chunks to keep both the host
-      // threads and the copy engine busy was measured SLOWER: DMA reads and the packer share the host memory bus.)
-      if (use_pack && hs.pack_rate_gbps != 0.0 && hs.pack_rate_gbps < pack_floor && ++hs.pack_skipped >= 64) {
-        hs.pack_rate_gbps = 0.0;  // the host may have been busy when the rate was measured: probe again now and then
+      // Pageable input: the narrowing pays only if the host reads X faster than PCIe would carry it raw (~47 GB/s measured);
+      // it is kept while the measured rate stays above that floor and re-probed now and then (the host may have been busy).
+      // Page-locked input needs no floor: the split below gives the host threads the share of rows they can keep up with.
+      const double floor_gbps = x_pinned ? 0.08 * pack_floor : pack_floor;
+      if (use_pack && hs.pack_rate_gbps != 0.0 && hs.pack_rate_gbps < floor_gbps && ++hs.pack_skipped >= 64) {
+        hs.pack_rate_gbps = 0.0;
         hs.pack_skipped = 0;
       }
       const bool want_pack = use_pack && !hs.pack_unavailable && hs.hpack[b] != nullptr &&
-                             (hs.pack_rate_gbps == 0.0 || hs.pack_rate_gbps >= pack_floor);
+                             (hs.pack_rate_gbps == 0.0 || hs.pack_rate_gbps >= floor_gbps);
+      auto copy_raw = [&](int64_t r0, int64_t rows) -> cudaError_t {   // rows [r0, r0 + rows) of the chunk as float32
+        if (rows <= 0) return cudaSuccess;
+        h->last_h2d_bytes += rows * G * 4;
+        if (ldx == G)
+          return cudaMemcpyAsync(hs.X[b] + r0 * G, X + (lo + r0) * ldx, (size_t)rows * G * sizeof(float), cudaMemcpyHostToDevice, hs.s_h2d);
+        return cudaMemcpy2DAsync(hs.X[b] + r0 * G, (size_t)G * sizeof(float), X + (lo + r0) * ldx, (size_t)ldx * sizeof(float),
+                                 (size_t)G * sizeof(float), (size_t)rows, cudaMemcpyHostToDevice, hs.s_h2d);
+      };
+      // Split of the chunk between the two ways across: the host threads narrow the leading m_pack rows (they read float32 at
+      // C GB/s, the link then carries 1/4 of it) while the copy engine pulls the remaining rows raw from the caller's
+      // page-locked matrix (P GB/s of float32) -- both finish together for m_pack / m = C / (P + 3/4 C).  Neither the host
+      // cores nor PCIe alone bounds the transfer any more (C = 61, P = 47: 0.66 of the rows are narrowed and the chunk
+      // crosses 1.5x faster than all-narrowed, 2x faster than all-raw).  Pageable input is narrowed as a whole: a raw copy
+      // from pageable memory is staged by the driver on the calling thread.
+      int64_t m_pack = m;
+      if (want_pack && x_pinned && hs.pack_rate_gbps > 0.0) {
+        const double C = hs.pack_rate_gbps, P = pcie_gbps * std::min(1.0, 2.0 / sharers);
+        const double f = C / (P + 0.75 * C);
+        if (f < 0.92) m_pack = std::min<int64_t>(m, ((int64_t)(f * (double)m) + 63) / 64 * 64);
+      }
       if (want_pack) {
+        CUDA_TRY(copy_raw(m_pack, m - m_pack));   // travels while the host narrows the leading rows
         if (c >= 2) CUDA_TRY(cudaEventSynchronize(hs.ev_h2d[b]));  // the copy of chunk c-2 has left the pinned staging buffer
         const auto t0 = std::chrono::steady_clock::now();
-        narrow = narrow_counts(*hs.pool, X + lo * ldx, ldx, m, G, hs.hpack[b]);
+        narrow = narrow_counts(*hs.pool, X + lo * ldx, ldx, m_pack, G, hs.hpack[b]);
         const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-        const double gbps = (double)m * G * 4 / std::max(sec, 1e-9) * 1e-9;
-        if (m * (int64_t)G >= (1ll << 22)) hs.pack_rate_gbps = hs.pack_rate_gbps == 0.0 ? gbps : 0.7 * hs.pack_rate_gbps + 0.3 * gbps;
+        const double gbps = (double)m_pack * G * 4 / std::max(sec, 1e-9) * 1e-9;
+        if (m_pack * (int64_t)G >= (1ll << 21)) hs.pack_rate_gbps = hs.pack_rate_gbps == 0.0 ? gbps : 0.7 * hs.pack_rate_gbps + 0.3 * gbps;
       }
       pack_mode[b] = narrow;
+      pack_rows[b] = m_pack;
       if (narrow) {
-        CUDA_TRY(cudaMemcpyAsync(hs.dpack[b], hs.hpack[b], (size_t)m * G * narrow, cudaMemcpyHostToDevice, hs.s_h2d));
-        h->last_h2d_bytes += (int64_t)m * G * narrow;
+        CUDA_TRY(cudaMemcpyAsync(hs.dpack[b], hs.hpack[b], (size_t)m_pack * G * narrow, cudaMemcpyHostToDevice, hs.s_h2d));
+        h->last_h2d_bytes += (int64_t)m_pack * G * narrow;
       } else {
-        if (ldx == G)
-          CUDA_TRY(cudaMemcpyAsync(hs.X[b], X + lo * ldx, (size_t)m * G * sizeof(float), cudaMemcpyHostToDevice, hs.s_h2d));
-        else
-          CUDA_TRY(cudaMemcpy2DAsync(hs.X[b], (size_t)G * sizeof(float), X + lo * ldx, (size_t)ldx * sizeof(float),
-                                     (size_t)G * sizeof(float), (size_t)m, cudaMemcpyHostToDevice, hs.s_h2d));
-        h->last_h2d_bytes += (int64_t)m * G * 4;
+        CUDA_TRY(copy_raw(0, m_pack));
       }
     }
     CUDA_TRY(cudaMemcpyAsync(hs.sid[b], sample_idx + lo, m * sizeof(int32_t), cudaMemcpyHostToDevice, hs.s_h2d));
@@ -1276,7 +1303,7 @@ static int run_host_impl(MrviHandle* h, int64_t n_cells, const float* X, int x_k
     CUDA_TRY(cudaStreamWaitEvent(hs.s_comp, hs.ev_h2d[b], 0));
     if (c >= 2) CUDA_TRY(cudaStreamWaitEvent(hs.s_comp, hs.ev_d2h[b], 0));
     if (!csr && pack_mode[b]) {  // widen the narrowed counts back to float32
-      const int64_t ne = m * (int64_t)G;
+      const int64_t ne = pack_rows[b] * (int64_t)G;
       const unsigned blocks = (unsigned)((ne + 16 * 256 - 1) / (16 * 256));
       if (pack_mode[b] == 1) k_unpack_counts<uint8_t><<<blocks, 256, 0, hs.s_comp>>>(hs.dpack[b], hs.X[b], ne);
       else k_unpack_counts<uint16_t><<<blocks, 256, 0, hs.s_comp>>>(reinterpret_cast<const uint16_t*>(hs.dpack[b]), hs.X[b], ne);

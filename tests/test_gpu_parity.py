@@ -129,6 +129,39 @@ def test_host_narrowing_is_bit_transparent(built_library, precision):
     h.close()
 
 
+def test_split_h2d_of_page_locked_input_is_bit_transparent(built_library, monkeypatch):
+    """Page-locked float32 input: the leading rows of every chunk are narrowed by the host threads while the copy engine
+    pulls the rest raw (run_host_impl: m_pack / m = C / (P + 3/4 C)).  Which rows go which way depends on the measured host
+    rate, so the result must be bit-identical to the all-narrowed route and to pageable input, whatever the split
+    (ragged last chunk, uint16 chunks, a pitched matrix)."""
+    dims = mrvi_b200.MrviDims(n_input=1200, n_sample=8)
+    params, h = _model(dims, seed=3, precision="tc")
+    n = 9000
+    X, sid = _inputs(n, 1200, 8, seed=4)
+    X[::11, 7] = 30000.0                       # some uint16 chunks
+    ref = h.run_host(X, sid, keep_cell=True, chunk_cells=2048)["cell"].copy()   # pageable: all narrowed
+    Xp = _capi.pinned_empty((n, 1200))
+    Xp[:] = X
+    monkeypatch.setenv("MRVI_B200_NO_SPLIT_H2D", "1")
+    a = h.run_host(Xp, sid, keep_cell=True, chunk_cells=2048)["cell"].copy()
+    bytes_narrow = h.last_h2d_bytes()
+    monkeypatch.delenv("MRVI_B200_NO_SPLIT_H2D")
+    sent = {}
+    for pcie in ("47", "5", "400"):            # assumed raw rate of the link: default / all rows narrowed / mostly raw
+        monkeypatch.setenv("MRVI_B200_PCIE_GBPS", pcie)
+        for _ in range(2):                     # the first call measures the host rate, the second one splits
+            b = h.run_host(Xp, sid, keep_cell=True, chunk_cells=2048)["cell"]
+        sent[pcie] = h.last_h2d_bytes()
+        assert np.array_equal(a, b), pcie
+    assert sent["400"] > sent["5"], (sent, bytes_narrow)   # more rows travel raw when the link is assumed faster: the split is live
+    assert np.array_equal(a, ref)
+    Xw = _capi.pinned_empty((n, 1300))         # ldx > G: pitched copies of the raw rows
+    Xw[:, :1200] = X
+    c = h.run_host(Xw[:, :1200], sid, keep_cell=True, chunk_cells=2048)["cell"]
+    assert np.array_equal(a, c)
+    h.close()
+
+
 @pytest.mark.parametrize("dtype", [np.uint8, np.uint16, np.int32, np.int64])
 def test_integer_count_matrix_input(built_library, dtype):
     """`mrvi_run_host_counts`: adata.X stored as integer counts gives bit-identical results to its float32 copy (what
