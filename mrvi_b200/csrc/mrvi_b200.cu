@@ -1249,8 +1249,10 @@ static int run_host_impl(MrviHandle* h, int64_t n_cells, const float* X, int x_k
       int narrow = 0;
       // Pageable input: the narrowing pays only if the host reads X faster than PCIe would carry it raw (~47 GB/s measured);
       // it is kept while the measured rate stays above that floor and re-probed now and then (the host may have been busy).
-      // Page-locked input needs no floor: the split below gives the host threads the share of rows they can keep up with.
-      const double floor_gbps = x_pinned ? 0.08 * pack_floor : pack_floor;
+      // Page-locked input needs no floor: the split below gives the host threads the share of rows they can keep up with --
+      // as long as the host memory bus has room for the extra pass (one or two GPUs per host; with more, the raw copies alone
+      // saturate it -- 180 GB/s aggregate at 8 GPUs -- and narrowing would add traffic, so the floor stays).
+      const double floor_gbps = (x_pinned && sharers <= 2) ? 0.08 * pack_floor : pack_floor;
       if (use_pack && hs.pack_rate_gbps != 0.0 && hs.pack_rate_gbps < floor_gbps && ++hs.pack_skipped >= 64) {
         hs.pack_rate_gbps = 0.0;
         hs.pack_skipped = 0;

@@ -1,8 +1,8 @@
 #!/bin/bash
 # A/B of the device-resident bench (ms per step, fused stage, parity) under different environment switches.
-# usage (under gpurun): bash tools/gpu_ab.sh "" "MRVI_B200_NO_ATT_TABLE=1" ...     (one argument = one environment prefix)
+# usage (under gpurun): [WL="c4 c2"] bash tools/gpu_ab.sh "" "MRVI_B200_LIBRARY=build_ab/x.so" ...     (one argument = one environment prefix)
 for envs in "$@"; do
-  for w in "c4" "c2" "c3"; do
+  for w in ${WL:-c4 c2 c3}; do
     env $envs timeout 200 python bench.py --workload $w --steps 10 --warmup 3 --no-cpu-baseline --no-extras --no-api 2>>gpurun_out/ab_err.log | python -c "
 import json,sys
 d=json.loads(sys.stdin.read()); p=d.get('parity') or {}
