@@ -347,11 +347,12 @@ class Job:
                 "peak_source": f"MEASURED_PEAKS.json bf16 {'burst' if burst else 'sustained'} ({pk['source']})",
                 "stage_ms_last_step": stage,
                 "algorithmic_flop_per_cell": (fl["chain"] + (fl["dist"] if fused else 0)),
-                "cuda_core_bound": {"sm_clk_per_row": clk_per_row, "mufu_floor_clk_per_row": 62.0,
+                "cuda_core_bound": {"sm_clk_per_row": clk_per_row, "issue_floor_clk_per_row": 46.0, "mufu_floor_clk_per_row": 30.0,
                                     "note": "the fused chain is bound by its fp32 epilogues, not the tensor pipe: per (cell,sample) row "
-                                            "~992 MUFU ops (512 attention ex2, 320 tanh, 128 sqrt, 32 rcp) at the measured 16/clk/SM "
-                                            "= 62 clk and ~70 clk of issue slots; tensor work is ~28 clk/row with the 3-term "
-                                            "(hi, lo) products (DESIGN.md section 4)"},
+                                            "183 warp-instructions (ncu inst_executed / rows, profiles/r2_fused_c4_ncu.json) = 46 issue clk "
+                                            "on 4 schedulers, ~480 MUFU ops (320 tanh, 128 sqrt, 32 rcp/rsq) at the measured 16/clk/SM = "
+                                            "30 clk, ~28 clk of tensor pipe with the 3-term (hi, lo) products; measured time = "
+                                            "instructions x dependency stalls at 4 warps per scheduler (DESIGN.md section 4)"},
                 "note": "achieved = algorithmic FLOP/cell (SURVEY 8d: 2*S*(att+mlp0+mlp1) [+ 3*S^2*L fused]) x cells / kernel CUDA-event time"}
 
     def config(self):
@@ -558,8 +559,9 @@ def main():
                 "e2e": {"value": e2e_value, "unit": "cells/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "steps": e2e_steps, "ms_per_step": e2e_wall / e2e_steps * 1e3,
                         "host_input_bytes_per_step": n_per * (G * 4 + 4 + (4 if n_groups else 0)),
-                        "api": "mrvi_run_host (C-ABI, pinned host float32 buffers; integer count chunks are narrowed "
-                               "losslessly to uint8/uint16 on the host, inside the timed region, before the copy)"},
+                        "api": "mrvi_run_host (C-ABI, pinned host float32 buffers; inside the timed region the host threads narrow "
+                               "the leading rows of every chunk losslessly to uint8/uint16 while the copy engine pulls the remaining "
+                               "rows raw; widened back on the GPU, bit-identical)"},
                 "gpu_launches": int(launches), "roofline": job.roofline(stage, clocks), "clocks": clocks,
                 "collective": (("mrvi_allreduce_groups (NCCL, library communicator)" if job.own_comm else "torch.distributed all_reduce (NCCL)")
                                + f", {n_groups * S * S * 8} bytes per step") if (world > 1 and n_groups) else None}
