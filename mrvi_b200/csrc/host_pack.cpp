@@ -85,6 +85,8 @@ void PackPool::run(const std::function<void(int, int)>& fn) {
   impl_->cv_done.wait(lk, [&] { return impl_->pending == 0; });
 }
 
+constexpr int kPrefetchBytes = 2048;   // (a prefetch past the end of the matrix is harmless: the instruction never faults)
+
 // ------------------------------------------------------------------------------------------ row kernels
 // flags: bit 0 = a value is not a non-negative integer < 2^31 (cannot narrow), bit 1 = a value is >= 256
 namespace {
@@ -120,6 +122,10 @@ __attribute__((target("avx2"))) uint32_t narrow_rows_u8_avx2(const float* X, int
     const bool stream16 = (reinterpret_cast<uintptr_t>(o) & 15) == 0;
     int k = 0;
     for (; k + 32 <= G; k += 32) {
+      // software prefetch 2 KB ahead (two lines per iteration = what the iteration consumes): on the pool's virtualised Xeon
+      // hosts the hardware prefetchers leave a streaming core at ~4 GB/s; with it 8 threads read 54-63 GB/s instead of 35
+      _mm_prefetch(reinterpret_cast<const char*>(x + k) + kPrefetchBytes, _MM_HINT_T0);
+      _mm_prefetch(reinterpret_cast<const char*>(x + k) + kPrefetchBytes + 64, _MM_HINT_T0);
       const __m256 a0 = _mm256_loadu_ps(x + k), a1 = _mm256_loadu_ps(x + k + 8), a2 = _mm256_loadu_ps(x + k + 16),
                    a3 = _mm256_loadu_ps(x + k + 24);
       const __m256i i0 = _mm256_cvttps_epi32(a0), i1 = _mm256_cvttps_epi32(a1), i2 = _mm256_cvttps_epi32(a2),
@@ -212,10 +218,19 @@ uint32_t narrow_rows_int(const SRC* X, int64_t ldx, int64_t r0, int64_t r1, int 
   for (int64_t r = r0; r < r1; ++r) {
     const SRC* x = X + r * ldx;
     T* o = out + r * G;
-    for (int k = 0; k < G; ++k) {
-      const SRC v = x[k];
-      ored |= (uint64_t)(int64_t)v;   // a negative value sets the high bits
-      o[k] = (T)v;
+    for (int k0 = 0; k0 < G; k0 += 64) {
+      __builtin_prefetch(reinterpret_cast<const char*>(x + k0) + kPrefetchBytes);
+      __builtin_prefetch(reinterpret_cast<const char*>(x + k0) + kPrefetchBytes + 64);
+      if (sizeof(SRC) == 8) {
+        __builtin_prefetch(reinterpret_cast<const char*>(x + k0) + kPrefetchBytes + 128);
+        __builtin_prefetch(reinterpret_cast<const char*>(x + k0) + kPrefetchBytes + 192);
+      }
+      const int k1 = std::min(G, k0 + 64);
+      for (int k = k0; k < k1; ++k) {
+        const SRC v = x[k];
+        ored |= (uint64_t)(int64_t)v;   // a negative value sets the high bits
+        o[k] = (T)v;
+      }
     }
   }
   const uint64_t limit = sizeof(T) == 1 ? ~uint64_t(0xFF) : ~uint64_t(0xFFFF);

@@ -762,7 +762,7 @@ k_chain_fused_tc(const __grid_constant__ TcNet tc, CellBuf cb, int64_t n_cells, 
     // under the accumulator lock): on random models with S = 128, 0.1-21 entries per cell with sample 0 alone, 0-3.7 with two
     // samples, 0-1.7 with the exact mean (which would cost a reduction over the rows).
     if (row_in_tile && (s == 0 || (kc2 && s == (S >> 1)))) {
-      float* dst = cref_s + (lc * 2 + (s == 0 ? 0 : 1)) * Kz + col0;
+      float* dst = cref_s + (lc * sm.cref_rows + (s == 0 ? 0 : 1)) * Kz + col0;   // [cell][cref_rows][Kz]
 #pragma unroll
       for (int l = 0; l < 32; ++l)
         if (l < ncol) dst[l] = v[l];
@@ -771,7 +771,7 @@ k_chain_fused_tc(const __grid_constant__ TcNet tc, CellBuf cb, int64_t n_cells, 
     wg_sync(wg);  // reference rows visible; with z output: every thread is done with zf / rowinfo
     FT(22);
     {
-      const float* crow = cref_s + (row_in_tile ? lc : 0) * 2 * Kz + col0;
+      const float* crow = cref_s + (row_in_tile ? lc : 0) * sm.cref_rows * Kz + col0;
       const int c1off = kc2 ? Kz : 0;   // one reference row only (n_latent > 32: shared memory): the "second" row is the first
       const float2 mh2 = make_float2(-0.5f, -0.5f);
       float nrm_p = 0.f;

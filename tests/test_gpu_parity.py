@@ -521,7 +521,7 @@ def test_tc_kernels_are_run_to_run_deterministic(built_library):
 
 
 # ------------------------------------------------------------------------------------------------
-# Regression cases from the round-1 random sweeps (tools/fuzz_parity.py, gpurun_out/fuzz*.log): the eight
+# Regression cases from the random sweeps (tools/fuzz_parity.py).  Round 1 (gpurun_out/fuzz*.log): the eight
 # configurations whose worst cell sat ABOVE the bar -- six in tensor-core mode (1.0e-3 .. 2.2e-3: single-f16 chain
 # weights; fixed in round 2 by the (hi, lo) weight image, 3-term products) and two in fp32 mode (1.0e-5 / 1.4e-5 with
 # one or few distances per cell).  The bar is applied PER CELL BLOCK (oracle/parity.py).
@@ -535,6 +535,12 @@ FUZZ_FAILS = [
     ("tc_S255_L5_Lu16_usemapF", "tc", dict(n_input=31, n_sample=255, n_latent=5, n_latent_u=16, use_map=False, encoder_n_layers=1), 34),
     ("fp32_S8_L5_Lu16_qz2", "fp32", dict(n_input=31, n_sample=8, n_latent=5, n_latent_u=16, qz_n_layers=2, encoder_n_layers=3), 347),
     ("fp32_S2_L31_Lu5_qz2", "fp32", dict(n_input=256, n_sample=2, n_latent=31, n_latent_u=5, qz_n_layers=2), 9948),
+    # round 2, second sweep on the two-sample centre: n_latent > 32 keeps ONE reference row per cell (shared memory) and the
+    # rows were still indexed with the two-row stride -- with many cells per tile (small S) they ran past the buffer
+    # (NaN blocks, wrong group sums, an illegal address)
+    ("tc_S5_L33_Lu8_usemapF", "tc", dict(n_input=31, n_sample=5, n_latent=33, n_latent_u=8, use_map=False, encoder_n_layers=1), 97),
+    ("tc_S5_L50_Lu8", "tc", dict(n_input=101, n_sample=5, n_latent=50, n_latent_u=8), 541),
+    ("tc_S4_L33_Lu8", "tc", dict(n_input=8, n_sample=4, n_latent=33, n_latent_u=8), 2477),
 ]
 
 
