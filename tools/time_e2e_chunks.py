@@ -16,7 +16,7 @@ sid = rng.integers(0, S, n).astype(np.int32)
 codes = rng.integers(0, ng, n).astype(np.int32)
 X8 = torch.from_numpy(X.astype(np.uint8)).pin_memory().numpy()
 for name, A in (("float32", X), ("uint8", X8)):
-    for ch in (0, 2048, 4096, 8192, 16384):
+    for ch in (0, 4096, 8192, 12288, 16384, 24576, 32768):
         for _ in range(2):
             h.run_host(A, sid, [codes], [ng], keep_cell=False, chunk_cells=ch)
         t = time.perf_counter()
