@@ -1127,11 +1127,14 @@ static int run_host_impl(MrviHandle* h, int64_t n_cells, const float* X, int x_k
   const int x_elem = x_kind == 1 ? 1 : x_kind == 2 ? 2 : x_kind == 4 ? 8 : 4;  // bytes per element of the caller's matrix
   const bool narrow_in = !csr && (x_kind == 1 || x_kind == 2);  // already uint8 / uint16: copied as it is, widened on the GPU
   const bool int_in = !csr && (x_kind == 3 || x_kind == 4);     // int32 / int64 counts: always narrowed (or converted) on the host
-  const bool use_pack = !csr && !narrow_in && (int_in || (!pack_disabled && n_cells * (int64_t)G >= (1ll << 22)));
-  const size_t pack_elem = int_in ? 4 : 2;   // staging bytes per value: the int path may have to fall back to float32
   // GPUs fed from this host: ranks of a torchrun job (one process per GPU) or handles of one process (MrVI(devices=...))
   int sharers = std::max(1, live_devices());
   if (const char* e = getenv("LOCAL_WORLD_SIZE")) sharers = std::max(sharers, atoi(e));
+  // float32 input is narrowed with one or two GPUs per host; with four or more the host cores per GPU are too few to matter
+  // and the probing costs more than it finds (measured at 4 GPUs, C4 shards: 22.3 M cells/s all raw, 19.0 M with narrowing
+  // attempts that fall back to raw)
+  const bool use_pack = !csr && !narrow_in && (int_in || (!pack_disabled && sharers <= 2 && n_cells * (int64_t)G >= (1ll << 22)));
+  const size_t pack_elem = int_in ? 4 : 2;   // staging bytes per value: the int path may have to fall back to float32
   if (use_pack && !hs.pool) {
     int nt = (int)std::thread::hardware_concurrency() / sharers;   // they share the host cores
     if (const char* e = getenv("MRVI_B200_PACK_THREADS")) nt = atoi(e);
@@ -1277,7 +1280,7 @@ static int run_host_impl(MrviHandle* h, int64_t n_cells, const float* X, int x_k
       // from pageable memory is staged by the driver on the calling thread.
       int64_t m_pack = m;
       if (want_pack && x_pinned && hs.pack_rate_gbps > 0.0) {
-        const double C = hs.pack_rate_gbps, P = pcie_gbps * std::min(1.0, 2.0 / sharers);
+        const double C = hs.pack_rate_gbps, P = pcie_gbps * std::min(1.0, 4.0 / sharers);   // (8 GPUs pull 180 GB/s raw in aggregate)
         const double f = C / (P + 0.75 * C);
         if (f < 0.92) m_pack = std::min<int64_t>(m, ((int64_t)(f * (double)m) + 63) / 64 * 64);
       }
