@@ -231,6 +231,10 @@ int mrvi_run_host_counts(MrviHandle* h, int64_t n_cells, const void* X, int32_t 
  * mrvi_run_host narrows dense count chunks losslessly before the host->device copy: a chunk whose float32 values are
  * all integers in [0, 255] ([0, 65535]) crosses PCIe as uint8 (uint16) and is widened back to the identical float32
  * values on the GPU; any other chunk is copied as it is (env MRVI_B200_NO_HOST_PACK=1 disables the narrowing).
+ * When X is page-locked, the copy engine pulls the trailing rows of every chunk raw while the host threads narrow the
+ * leading rows, in the proportion of the measured host rate (env MRVI_B200_NO_SPLIT_H2D=1: all rows narrowed;
+ * MRVI_B200_PCIE_GBPS: assumed raw rate of the link, default 47).  Results are bit-identical on every route.  With four
+ * or more GPUs fed from one host, float32 input travels raw.
  * mrvi_last_h2d_bytes: bytes of X the most recent mrvi_run_host call actually copied host->device.
  * mrvi_narrow_counts: the host-side narrowing itself (no GPU needed; exposed for tests): writes dense
  * [n_rows][n_cols] uint8 / uint16 to `out` (capacity 2 * n_rows * n_cols bytes) and returns 1 / 2, or 0 when the
