@@ -24,6 +24,13 @@ for wl in which:
     t0 = time.perf_counter()
     X = mrvi_b200.synthetic_counts(n, G, seed=1000, dtype=np.uint8 if wl == "c5" else np.float32)
     t_gen = time.perf_counter() - t0
+    t_pin = 0.0
+    if wl == "c5":   # page-locked input (a pageable 10 GB matrix is staged by the driver at ~11 GB/s and bounds the whole run)
+        t0 = time.perf_counter()
+        Xp = _capi.pinned_empty(X.shape, X.dtype)
+        Xp[:] = X
+        X = Xp
+        t_pin = time.perf_counter() - t0
     rng = np.random.default_rng(1101)
     sid = rng.integers(0, S, size=n).astype(np.int32)
     codes = rng.integers(0, ng, size=n).astype(np.int32) if ng else None
@@ -46,7 +53,7 @@ for wl in which:
     idx = stratified_indices(n, 256)
     line = {"config": wl, "cells": n, "genes": G, "samples": S, "n_latent": L, "n_groups": ng, "keep_cell": keep,
             "x_dtype": str(X.dtype), "x_host_gb": X.nbytes / 1e9, "seconds": t, "seconds_runs": times, "cells_per_s": n / t,
-            "h2d_bytes": h.last_h2d_bytes(), "h2d_gbs": h.last_h2d_bytes() / t / 1e9, "gen_seconds": t_gen, "pinned_alloc_seconds": t_alloc}
+            "h2d_bytes": h.last_h2d_bytes(), "h2d_gbs": h.last_h2d_bytes() / t / 1e9, "gen_seconds": t_gen, "pinned_alloc_seconds": t_alloc, "x_pinned": wl == "c5", "x_pin_seconds": t_pin}
     if keep:
         out_bytes = n * S * S * 4
         line.update({"d2h_bytes": out_bytes, "d2h_gbs": out_bytes / t / 1e9})
